@@ -1,0 +1,507 @@
+// extern "C" entry points of libfemocs_b200 (see include/femocs_b200.h for the contract and the
+// reference interface each one replaces).  Host orchestration only: uploads, kernel launches,
+// CUDA-graph capture of the CG loop, pinned staging for host<->device copies.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <string>
+
+#include "kernels.h"
+
+static std::string g_create_error;
+
+#define FB_REQUIRE(ctx, cond, msg) \
+    do { if (!(cond)) return (ctx)->fail(FB_ERR_ARG, "%s", msg); } while (0)
+
+static int sync_check(fb_ctx* c, const char* what) {
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return c->fail(FB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return FB_OK;
+}
+
+static void drop_graph(fb_ctx* c) {
+    if (c->cg_graph) { cudaGraphExecDestroy(c->cg_graph); c->cg_graph = nullptr; }
+    c->cg_graph_n = 0;
+}
+
+extern "C" {
+
+const char* fb_create_error(void) { return g_create_error.c_str(); }
+
+fb_ctx* fb_create(int device) {
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libfemocs_b200 has no CPU fallback";
+        return nullptr;
+    }
+    if (device < 0 || device >= n_dev) { g_create_error = "invalid CUDA device ordinal"; return nullptr; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return nullptr; }
+    fb_ctx* c = new fb_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->n_sm = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e); delete c; return nullptr;
+    }
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    // partials: 2 values x max grid (n_sm * 16 blocks) + counter slot, zero-initialised once
+    const size_t np = 2 * (size_t) c->n_sm * 16 + 8;
+    if (c->d_partial.alloc(np) != cudaSuccess || c->d_cg.alloc(2) != cudaSuccess || c->d_minmax.alloc(2) != cudaSuccess ||
+        c->d_flag.alloc(4) != cudaSuccess || c->pin_out.reserve(4096) != cudaSuccess) {
+        g_create_error = "device allocation failed"; fb_destroy(c); return nullptr;
+    }
+    c->d_partial.zero(c->stream); c->d_cg.zero(c->stream);
+    cudaStreamSynchronize(c->stream);
+    return c;
+}
+
+void fb_destroy(fb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    drop_graph(c);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) { cudaStreamSynchronize(c->stream); }
+    cudaStream_t s = c->stream;
+    delete c;                       // frees device buffers
+    if (s) cudaStreamDestroy(s);
+}
+
+const char* fb_last_error(const fb_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+long fb_kernel_launches(const fb_ctx* c) { return c->launches; }
+
+int fb_set_option(fb_ctx* c, const char* key, double value) {
+    const std::string k(key);
+    if (k == "cg_graph_iters") { c->cg_graph_iters = std::max(1, (int) value); drop_graph(c); }
+    else if (k == "cheb_degree") c->cheb_degree = (int) value;
+    else if (k == "dof_order") c->dof_order = (int) value;
+    else return c->fail(FB_ERR_ARG, "unknown option %s", key);
+    return FB_OK;
+}
+
+int fb_synchronize(fb_ctx* c) { return sync_check(c, "fb_synchronize"); }
+
+// ------------------------------------------------------------------------------------------
+int fb_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {
+    FB_REQUIRE(c, xyz && hex8 && hex_marker && n_nodes > 0 && n_hex > 0, "fb_import_mesh: empty mesh");
+    cudaSetDevice(c->device);
+    c->setup_ok = c->assembled = c->matrix_ok = c->interp_ok = false;
+    drop_graph(c);
+    int rc = fb_host_import_mesh(c, xyz, n_nodes, hex8, hex_marker, n_hex);
+    if (rc) return rc;
+    const int n = c->n_dofs;
+    cudaStream_t s = c->stream;
+    // coordinates in DoF order
+    std::vector<double> vxyz(3 * (size_t) n);
+    for (int d = 0; d < n; ++d) {
+        const double* p = &c->xyz[3 * (size_t) c->vert2node[c->dof2vertex[d]]];
+        vxyz[3 * (size_t) d] = p[0]; vxyz[3 * (size_t) d + 1] = p[1]; vxyz[3 * (size_t) d + 2] = p[2];
+    }
+    static const int FV[6][4] = {{0, 2, 4, 6}, {1, 3, 5, 7}, {0, 1, 4, 5}, {2, 3, 6, 7}, {0, 1, 2, 3}, {4, 5, 6, 7}};
+    std::vector<int> top;
+    for (const auto& bf : c->bfaces)
+        if (bf.id == 8) for (int k = 0; k < 4; ++k) top.push_back(c->cells_dof[8 * (size_t) bf.cell + FV[bf.face][k]]);
+    FB_CUDA(c, c->d_vxyz.upload(vxyz, s));
+    FB_CUDA(c, c->d_cells.upload(c->cells_dof, s));
+    FB_CUDA(c, c->d_rowptr.upload(c->rowptr, s));
+    FB_CUDA(c, c->d_col.upload(c->col, s));
+    FB_CUDA(c, c->d_topfaces.upload(top, s));
+    FB_CUDA(c, c->d_vertex2dof.upload(c->vertex2dof, s));
+    FB_CUDA(c, c->d_cell2hex.upload(c->cell2hex, s));
+    FB_CUDA(c, c->d_hex2cell.upload(c->hex2cell, s));
+    FB_CUDA(c, c->d_val.alloc(c->nnz)); FB_CUDA(c, c->d_val_save.alloc(c->nnz));
+    FB_CUDA(c, c->d_diagpos.alloc(n));
+    for (fb::DevBuf<double>* b : {&c->d_rhs, &c->d_x, &c->d_g, &c->d_d, &c->d_h, &c->d_dinv, &c->d_z, &c->d_w, &c->d_bcval})
+        FB_CUDA(c, b->alloc(n));
+    FB_CUDA(c, c->d_bcflag.alloc(n));
+    FB_CUDA(c, cudaMemsetAsync(c->d_x.p, 0, n * sizeof(double), s));
+    return sync_check(c, "fb_import_mesh");
+}
+
+int fb_get_sizes(const fb_ctx* c, long* out) {
+    out[0] = c->n_dofs; out[1] = c->n_cells; out[2] = c->nnz; out[3] = c->n_vert;
+    out[4] = (long) c->bfaces.size(); out[5] = c->n_top_faces; out[6] = c->n_dirichlet;
+    return FB_OK;
+}
+
+int fb_poisson_setup(fb_ctx* c, double field, double potential, int anode_is_dirichlet) {
+    FB_REQUIRE(c, c->mesh_ok, "fb_poisson_setup: no mesh imported");
+    cudaSetDevice(c->device);
+    c->applied_field = field; c->applied_potential = potential; c->anode_dirichlet = anode_is_dirichlet;
+    c->setup_ok = true; c->assembled = false; c->matrix_ok = false;
+    FB_CUDA(c, cudaMemsetAsync(c->d_x.p, 0, c->n_dofs * sizeof(double), c->stream));     // solution = dirichlet_bc_value (0)
+    FB_CUDA(c, cudaMemsetAsync(c->d_rhs.p, 0, c->n_dofs * sizeof(double), c->stream));
+    return FB_OK;
+}
+
+static int assemble_impl(fb_ctx* c, int first_time, const double* d_pxyz, const int* d_pcell, long n_parts, double charge_factor) {
+    cudaStream_t s = c->stream;
+    const int n = c->n_dofs;
+    if (first_time || !c->matrix_ok) {
+        // stiffness matrix -> val_save (the reference's system_matrix_save)
+        FB_CUDA(c, cudaMemsetAsync(c->d_val_save.p, 0, c->nnz * sizeof(double), s));
+        fb::launch_assemble_stiffness(c, nullptr);
+        // boundary values: copper = 0 (+ anode = V0 in Dirichlet mode); map semantics: later wins
+        FB_CUDA(c, cudaMemsetAsync(c->d_bcflag.p, 0, n * sizeof(int), s));
+        FB_CUDA(c, cudaMemsetAsync(c->d_bcval.p, 0, n * sizeof(double), s));
+        fb::DevBuf<int> tmp;
+        std::vector<int> all(c->copper_dofs);
+        all.insert(all.end(), c->top_dofs.begin(), c->top_dofs.end());
+        FB_CUDA(c, tmp.upload(all, s));
+        fb::launch_set_bc(c, tmp.p, (int) c->copper_dofs.size(), 0.0);
+        std::vector<unsigned char> mark(n, 0);
+        for (int d : c->copper_dofs) mark[d] = 1;
+        if (c->anode_dirichlet) {
+            fb::launch_set_bc(c, tmp.p + c->copper_dofs.size(), (int) c->top_dofs.size(), c->applied_potential);
+            for (int d : c->top_dofs) mark[d] = 1;
+        }
+        c->n_dirichlet = (int) std::count(mark.begin(), mark.end(), (unsigned char) 1);
+        fb::launch_apply_bc_matrix(c);      // val, Dirichlet lift (kept in d_w), dinv, diagpos
+        FB_CUDA(c, cudaStreamSynchronize(s));   // tmp goes out of scope
+        c->matrix_ok = true;
+    }
+    // right-hand side: Neumann faces (or nothing), space charge, then Dirichlet lift
+    FB_CUDA(c, cudaMemsetAsync(c->d_rhs.p, 0, n * sizeof(double), s));
+    if (!c->anode_dirichlet) fb::launch_neumann(c);
+    if (n_parts > 0) {
+        FB_REQUIRE(c, c->interp_ok, "fb_poisson_assemble: space charge needs fb_interp_initialize (LinearHexahedra tables)");
+        fb::launch_space_charge(c, n_parts, d_pxyz, d_pcell, charge_factor);
+    }
+    fb::launch_apply_bc_rhs(c);
+    c->assembled = true;
+    return FB_OK;
+}
+
+int fb_poisson_assemble_dev(fb_ctx* c, int first_time, const double* pxyz_dev, const int* pcell_dev, long n, double cf) {
+    FB_REQUIRE(c, c->setup_ok, "fb_poisson_assemble: call fb_poisson_setup first");
+    cudaSetDevice(c->device);
+    return assemble_impl(c, first_time, pxyz_dev, pcell_dev, n, cf);
+}
+
+int fb_poisson_assemble(fb_ctx* c, int first_time, const double* pxyz, const int* pcell, long n, double cf) {
+    FB_REQUIRE(c, c->setup_ok, "fb_poisson_assemble: call fb_poisson_setup first");
+    cudaSetDevice(c->device);
+    if (n > 0) {
+        FB_REQUIRE(c, pxyz && pcell, "fb_poisson_assemble: particle arrays missing");
+        FB_CUDA(c, c->d_pts.alloc(3 * (size_t) n)); FB_CUDA(c, c->d_cellsA.alloc(n));
+        FB_CUDA(c, cudaMemcpyAsync(c->d_pts.p, pxyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        FB_CUDA(c, cudaMemcpyAsync(c->d_cellsA.p, pcell, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    int rc = assemble_impl(c, first_time, c->d_pts.p, c->d_cellsA.p, n, cf);
+    if (rc) return rc;
+    return sync_check(c, "fb_poisson_assemble");
+}
+
+int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* n_iter, double* final_residual) {
+    FB_REQUIRE(c, c->assembled, "fb_poisson_solve: system not assembled");
+    FB_REQUIRE(c, precond == FB_PRECOND_JACOBI, "fb_poisson_solve: only FB_PRECOND_JACOBI is implemented in this build");
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    const int lanes = fb::choose_lanes(c);
+    fb::CgScalars init; memset(&init, 0, sizeof init);
+    init.tol2 = abs_tol * abs_tol; init.max_iter = max_iter;
+    fb::CgScalars* h = (fb::CgScalars*) c->pin_out.p;
+    *h = init;
+    FB_CUDA(c, cudaEventRecord(c->ev0, s));
+    FB_CUDA(c, cudaMemcpyAsync(c->d_cg.p, h, sizeof(fb::CgScalars), cudaMemcpyHostToDevice, s));
+    fb::launch_cg_init(c, lanes);
+    long spmv = 1;
+    // CUDA graph of cg_graph_iters iterations; kernels become no-ops once cgs->done is set
+    if (!c->cg_graph || c->cg_graph_n != c->cg_graph_iters || c->cg_graph_precond != lanes) {
+        drop_graph(c);
+        cudaGraph_t graph;
+        const long before = c->launches;
+        FB_CUDA(c, cudaStreamSynchronize(s));
+        FB_CUDA(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < c->cg_graph_iters; ++i) fb::launch_cg_iteration(c, lanes);
+        FB_CUDA(c, cudaStreamEndCapture(s, &graph));
+        c->launches = before;     // captured, not launched
+        FB_CUDA(c, cudaGraphInstantiate(&c->cg_graph, graph, 0));
+        cudaGraphDestroy(graph);
+        c->cg_graph_n = c->cg_graph_iters; c->cg_graph_precond = lanes;
+    }
+    FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
+    FB_CUDA(c, cudaStreamSynchronize(s));
+    while (!h->done) {
+        FB_CUDA(c, cudaGraphLaunch(c->cg_graph, s));
+        c->launches += 3L * c->cg_graph_n;
+        spmv += c->cg_graph_n;
+        FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
+        FB_CUDA(c, cudaStreamSynchronize(s));
+    }
+    FB_CUDA(c, cudaEventRecord(c->ev1, s));
+    FB_CUDA(c, cudaEventSynchronize(c->ev1));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_solve_ms = ms; c->last_iters = h->it; c->last_spmv = spmv;
+    if (n_iter) *n_iter = (h->done == 1) ? h->it : -h->it;
+    if (final_residual) *final_residual = std::sqrt(h->res2);
+    return sync_check(c, "fb_poisson_solve");
+}
+
+int fb_last_solve_stats(const fb_ctx* c, double* ms, int* it, long* spmv) {
+    if (ms) *ms = c->last_solve_ms; if (it) *it = c->last_iters; if (spmv) *spmv = c->last_spmv;
+    return FB_OK;
+}
+
+static int export_by_vertex(fb_ctx* c, const double* d_src, double* out) {
+    FB_CUDA(c, c->d_sol.alloc(c->n_vert));
+    fb::launch_gather(c, c->n_vert, c->d_vertex2dof.p, d_src, c->d_sol.p);
+    FB_CUDA(c, cudaMemcpyAsync(out, c->d_sol.p, c->n_vert * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return sync_check(c, "export");
+}
+
+int fb_export_solution(fb_ctx* c, double* phi_vertex) {
+    FB_REQUIRE(c, c->mesh_ok && phi_vertex, "fb_export_solution: no mesh");
+    cudaSetDevice(c->device);
+    return export_by_vertex(c, c->d_x.p, phi_vertex);
+}
+
+int fb_export_charge_dens(fb_ctx* c, double* rho_vertex) {
+    // PoissonSolver.cpp:198-207: charge_density is only filled when a file is being written
+    // (outside the hot path); otherwise it is reinit'ed to zeros, which is what export returns.
+    FB_REQUIRE(c, c->mesh_ok && rho_vertex, "fb_export_charge_dens: no mesh");
+    std::fill(rho_vertex, rho_vertex + c->n_vert, 0.0);
+    return FB_OK;
+}
+
+int fb_import_solution(fb_ctx* c, const double* phi_vertex) {
+    FB_REQUIRE(c, c->mesh_ok && phi_vertex, "fb_import_solution: no mesh");
+    cudaSetDevice(c->device);
+    FB_CUDA(c, c->d_sol.alloc(c->n_vert));
+    FB_CUDA(c, cudaMemcpyAsync(c->d_sol.p, phi_vertex, c->n_vert * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    fb::launch_scatter(c, c->n_vert, c->d_vertex2dof.p, c->d_sol.p, c->d_x.p);
+    return sync_check(c, "fb_import_solution");
+}
+
+int fb_check_limits(fb_ctx* c, double lo, double hi, int* bad, double* mn, double* mx) {
+    FB_REQUIRE(c, c->mesh_ok, "fb_check_limits: no mesh");
+    cudaSetDevice(c->device);
+    fb::launch_minmax(c);
+    double* h = (double*) c->pin_out.p;
+    FB_CUDA(c, cudaMemcpyAsync(h, c->d_minmax.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    int rc = sync_check(c, "fb_check_limits");
+    if (rc) return rc;
+    if (mn) *mn = h[0]; if (mx) *mx = h[1];
+    if (bad) *bad = (h[0] < lo || h[1] > hi);
+    return FB_OK;
+}
+
+int fb_get_cell_volumes(fb_ctx* c, double* vol) {
+    FB_REQUIRE(c, c->mesh_ok && vol, "fb_get_cell_volumes: no mesh");
+    cudaSetDevice(c->device);
+    // volumes come out of the assembly kernel (sum of JxW); run it into a scratch matrix
+    fb::DevBuf<double> v, scratch;
+    FB_CUDA(c, v.alloc(c->n_cells)); FB_CUDA(c, scratch.alloc(c->nnz));
+    double* keep = c->d_val_save.p;
+    c->d_val_save.p = scratch.p;
+    fb::launch_assemble_stiffness(c, v.p);
+    c->d_val_save.p = keep;
+    FB_CUDA(c, cudaMemcpyAsync(vol, v.p, c->n_cells * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return sync_check(c, "fb_get_cell_volumes");
+}
+
+int fb_get_system(fb_ctx* c, int* rowptr, int* col, double* val, double* val_save, double* rhs, double* sol,
+                  int* vertex2dof, int* vertex2node) {
+    FB_REQUIRE(c, c->mesh_ok, "fb_get_system: no mesh");
+    cudaSetDevice(c->device);
+    if (rowptr) std::copy(c->rowptr.begin(), c->rowptr.end(), rowptr);
+    if (col) std::copy(c->col.begin(), c->col.end(), col);
+    if (vertex2dof) std::copy(c->vertex2dof.begin(), c->vertex2dof.end(), vertex2dof);
+    if (vertex2node) std::copy(c->vert2node.begin(), c->vert2node.end(), vertex2node);
+    cudaStream_t s = c->stream;
+    if (val) FB_CUDA(c, cudaMemcpyAsync(val, c->d_val.p, c->nnz * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (val_save) FB_CUDA(c, cudaMemcpyAsync(val_save, c->d_val_save.p, c->nnz * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (rhs) FB_CUDA(c, cudaMemcpyAsync(rhs, c->d_rhs.p, c->n_dofs * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (sol) FB_CUDA(c, cudaMemcpyAsync(sol, c->d_x.p, c->n_dofs * sizeof(double), cudaMemcpyDeviceToHost, s));
+    return sync_check(c, "fb_get_system");
+}
+
+// ------------------------------------------------------------------------------------------
+int fb_interp_initialize(fb_ctx* c, const int* node_marker, const int* tet4, const int* tet_nbr4, const int* tet_marker, int n_tet,
+                         const int* tri3, const int* tri2tet, const double* tri_norm3, int n_tri,
+                         const int* quad4, const int* quad2hex, int n_quad, double tet_edgemax,
+                         const int* voro_off, const int* voro_list, int n_voro) {
+    FB_REQUIRE(c, c->mesh_ok, "fb_interp_initialize: call fb_import_mesh first");
+    FB_REQUIRE(c, node_marker && tet4 && tet_nbr4 && tet_marker && n_tet > 0, "fb_interp_initialize: tetrahedra missing");
+    FB_REQUIRE(c, 4L * n_tet == c->n_hex, "fb_interp_initialize: expected 4 hexahedra per tetrahedron");
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    c->interp_ok = false;
+    fb_interp_tables T;
+    fb_host_interp_tables(c, node_marker, tet4, tet_nbr4, tet_marker, n_tet, tri3, tri_norm3, n_tri, quad4, n_quad, T);
+    c->n_tet = n_tet; c->n_tri = n_tri; c->n_quad = n_quad; c->n_voro = n_voro;
+    c->decay_factor = -1.0 / tet_edgemax;            // InterpolatorCells.cpp:534
+    FB_CUDA(c, c->d_nxyz.upload(c->xyz, s));
+    FB_CUDA(c, c->d_hex8.upload(c->hex8, s));
+    FB_CUDA(c, c->d_node2vert.upload(c->node2vert, s));
+    FB_CUDA(c, c->d_nodal.alloc(5 * (size_t) c->n_nodes));
+    FB_CUDA(c, cudaMemsetAsync(c->d_nodal.p, 0, 5 * (size_t) c->n_nodes * sizeof(double), s));   // empty_value = 0
+    FB_CUDA(c, c->d_n2c_off.upload(T.n2c_off, s)); FB_CUDA(c, c->d_n2c_list.upload(T.n2c_list, s));
+    FB_CUDA(c, c->d_tet.upload(T.tet, s)); FB_CUDA(c, c->d_tet_cent.upload(T.tet_cent, s)); FB_CUDA(c, c->d_tet_mark.upload(T.tet_mark, s));
+    FB_CUDA(c, c->d_tet_nbr_off.upload(T.tet_nbr_off, s)); FB_CUDA(c, c->d_tet_nbr.upload(T.tet_nbr, s));
+    FB_CUDA(c, c->d_tet4.upload(tet4, 4 * (size_t) n_tet, s));
+    FB_CUDA(c, c->d_hex.upload(T.hex, s));
+    FB_CUDA(c, c->d_qtet.upload(T.qtet, s));
+    if (n_tri > 0) {
+        FB_CUDA(c, c->d_tri.upload(T.tri, s)); FB_CUDA(c, c->d_tri_cent.upload(T.tri_cent, s));
+        FB_CUDA(c, c->d_tri_nbr_off.upload(T.tri_nbr_off, s)); FB_CUDA(c, c->d_tri_nbr.upload(T.tri_nbr, s));
+        FB_CUDA(c, c->d_tri2tet.upload(tri2tet, 2 * (size_t) n_tri, s));
+        FB_CUDA(c, c->d_qtri.upload(T.qtri, s));
+    }
+    if (n_quad > 0) FB_CUDA(c, c->d_quad2hex.upload(quad2hex, 2 * (size_t) n_quad, s));
+    if (n_voro > 0) {
+        FB_CUDA(c, c->d_voro_off.upload(voro_off, (size_t) n_voro + 1, s));
+        FB_CUDA(c, c->d_voro_list.upload(voro_list, (size_t) std::max(1, voro_off[n_voro]), s));
+    }
+    int rc = sync_check(c, "fb_interp_initialize");
+    if (rc) return rc;
+    c->interp_ok = true;
+    return FB_OK;
+}
+
+int fb_extract_solution(fb_ctx* c, int smoothen) {
+    FB_REQUIRE(c, c->interp_ok, "fb_extract_solution: interpolator not initialised");
+    cudaSetDevice(c->device);
+    fb::launch_extract(c, smoothen);
+    return sync_check(c, "fb_extract_solution");
+}
+
+int fb_get_nodal_solutions(fb_ctx* c, double* sol5) {
+    FB_REQUIRE(c, c->interp_ok && sol5, "fb_get_nodal_solutions: interpolator not initialised");
+    cudaSetDevice(c->device);
+    FB_CUDA(c, cudaMemcpyAsync(sol5, c->d_nodal.p, 5 * (size_t) c->n_nodes * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return sync_check(c, "fb_get_nodal_solutions");
+}
+
+int fb_set_nodal_solutions(fb_ctx* c, const double* sol5) {
+    FB_REQUIRE(c, c->interp_ok && sol5, "fb_set_nodal_solutions: interpolator not initialised");
+    cudaSetDevice(c->device);
+    FB_CUDA(c, cudaMemcpyAsync(c->d_nodal.p, sol5, 5 * (size_t) c->n_nodes * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return sync_check(c, "fb_set_nodal_solutions");
+}
+
+static int check_dim_rank(fb_ctx* c, int dim, int rank) {
+    FB_REQUIRE(c, c->interp_ok, "interpolator not initialised");
+    FB_REQUIRE(c, dim == 2 || dim == 3, "invalid interpolation dimension");       // SolutionReader.h:61
+    FB_REQUIRE(c, rank >= 1 && rank <= 3, "invalid interpolation rank");          // SolutionReader.h:62
+    FB_REQUIRE(c, dim == 3 || c->n_tri > 0, "surface interpolation needs triangles");
+    return FB_OK;
+}
+
+static int reserve_query(fb_ctx* c, long n) {
+    FB_CUDA(c, c->d_cellsA.alloc(n)); FB_CUDA(c, c->d_cellsB.alloc(n)); FB_CUDA(c, c->d_scan.alloc(n));
+    FB_CUDA(c, c->d_dirtyA.alloc(n)); FB_CUDA(c, c->d_dirtyB.alloc(n));
+    return FB_OK;
+}
+
+int fb_locate_interpolate_dev(fb_ctx* c, int dim, int rank, long n, const double* xyz_dev, int* cells_dev, double* sol5_dev) {
+    int rc = check_dim_rank(c, dim, rank);
+    if (rc) return rc;
+    if (n <= 0) return FB_OK;
+    cudaSetDevice(c->device);
+    if ((rc = reserve_query(c, n))) return rc;
+    int* base = nullptr;
+    if ((rc = fb::launch_locate_chain(c, dim, rank, n, xyz_dev, &base))) return rc;
+    fb::launch_finish_interp(c, dim, rank, n, xyz_dev, base, 0, cells_dev, sol5_dev);
+    return FB_OK;
+}
+
+// host staging: x/y/z with stride -> packed device points
+static int stage_points(fb_ctx* c, long n, const double* x, const double* y, const double* z, int stride) {
+    FB_REQUIRE(c, x && y && z && stride >= 1, "point arrays missing");
+    FB_CUDA(c, c->d_pts.alloc(3 * (size_t) n));
+    cudaStream_t s = c->stream;
+    if (stride == 3 && y == x + 1 && z == x + 2) {
+        FB_CUDA(c, cudaMemcpyAsync(c->d_pts.p, x, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+    } else if (stride == 1) {
+        FB_CUDA(c, c->d_sol.alloc(3 * (size_t) n));
+        FB_CUDA(c, cudaMemcpyAsync(c->d_sol.p, x, n * sizeof(double), cudaMemcpyHostToDevice, s));
+        FB_CUDA(c, cudaMemcpyAsync(c->d_sol.p + n, y, n * sizeof(double), cudaMemcpyHostToDevice, s));
+        FB_CUDA(c, cudaMemcpyAsync(c->d_sol.p + 2 * n, z, n * sizeof(double), cudaMemcpyHostToDevice, s));
+        fb::launch_pack_points(c, n, c->d_sol.p, c->d_sol.p + n, c->d_sol.p + 2 * n, 1, c->d_pts.p);
+        FB_CUDA(c, cudaStreamSynchronize(s));      // d_sol is reused for the results below
+    } else {
+        std::vector<double> tmp(3 * (size_t) n);
+        for (long i = 0; i < n; ++i) { tmp[3 * i] = x[i * stride]; tmp[3 * i + 1] = y[i * stride]; tmp[3 * i + 2] = z[i * stride]; }
+        FB_CUDA(c, cudaMemcpyAsync(c->d_pts.p, tmp.data(), 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+        FB_CUDA(c, cudaStreamSynchronize(s));
+    }
+    return FB_OK;
+}
+
+int fb_locate_interpolate(fb_ctx* c, int dim, int rank, long n, const double* x, const double* y, const double* z, int stride,
+                          int* cells_out, double* sol5_out) {
+    int rc = check_dim_rank(c, dim, rank);
+    if (rc) return rc;
+    if (n <= 0) return FB_OK;
+    cudaSetDevice(c->device);
+    if ((rc = stage_points(c, n, x, y, z, stride))) return rc;
+    if ((rc = reserve_query(c, n))) return rc;
+    FB_CUDA(c, c->d_sol.alloc(5 * (size_t) n));
+    int* base = nullptr;
+    if ((rc = fb::launch_locate_chain(c, dim, rank, n, c->d_pts.p, &base))) return rc;
+    int* final_cells = (base == c->d_cellsA.p) ? c->d_cellsB.p : c->d_cellsA.p;
+    fb::launch_finish_interp(c, dim, rank, n, c->d_pts.p, base, 0, final_cells, c->d_sol.p);
+    if (cells_out) FB_CUDA(c, cudaMemcpyAsync(cells_out, final_cells, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (sol5_out) FB_CUDA(c, cudaMemcpyAsync(sol5_out, c->d_sol.p, 5 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return sync_check(c, "fb_locate_interpolate");
+}
+
+int fb_interpolate(fb_ctx* c, int dim, int rank, long n, const double* x, const double* y, const double* z, int stride,
+                   const int* cells, double* sol5_out) {
+    int rc = check_dim_rank(c, dim, rank);
+    if (rc) return rc;
+    if (n <= 0) return FB_OK;
+    FB_REQUIRE(c, cells && sol5_out, "fb_interpolate: arrays missing");
+    cudaSetDevice(c->device);
+    if ((rc = stage_points(c, n, x, y, z, stride))) return rc;
+    FB_CUDA(c, c->d_cellsA.alloc(n)); FB_CUDA(c, c->d_sol.alloc(5 * (size_t) n));
+    FB_CUDA(c, cudaMemcpyAsync(c->d_cellsA.p, cells, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    fb::launch_finish_interp(c, dim, rank, n, c->d_pts.p, c->d_cellsA.p, 1, nullptr, c->d_sol.p);
+    FB_CUDA(c, cudaMemcpyAsync(sol5_out, c->d_sol.p, 5 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return sync_check(c, "fb_interpolate");
+}
+
+int fb_particle_cells_dev(fb_ctx* c, long n, const double* xyz_dev, int* cell_inout_dev) {
+    FB_REQUIRE(c, c->interp_ok, "fb_particle_cells: interpolator not initialised");
+    if (n <= 0) return FB_OK;
+    cudaSetDevice(c->device);
+    fb::launch_particle_cells(c, n, xyz_dev, cell_inout_dev);
+    return FB_OK;
+}
+
+int fb_particle_cells(fb_ctx* c, long n, const double* xyz, int* cell_inout) {
+    FB_REQUIRE(c, c->interp_ok && xyz && cell_inout, "fb_particle_cells: interpolator not initialised");
+    if (n <= 0) return FB_OK;
+    cudaSetDevice(c->device);
+    FB_CUDA(c, c->d_pts.alloc(3 * (size_t) n)); FB_CUDA(c, c->d_cellsA.alloc(n));
+    FB_CUDA(c, cudaMemcpyAsync(c->d_pts.p, xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    FB_CUDA(c, cudaMemcpyAsync(c->d_cellsA.p, cell_inout, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    fb::launch_particle_cells(c, n, c->d_pts.p, c->d_cellsA.p);
+    FB_CUDA(c, cudaMemcpyAsync(cell_inout, c->d_cellsA.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return sync_check(c, "fb_particle_cells");
+}
+
+int fb_particle_field_dev(fb_ctx* c, long n, const double* xyz_dev, const int* cells_dev, double* E3_dev) {
+    FB_REQUIRE(c, c->interp_ok, "fb_particle_field: interpolator not initialised");
+    if (n <= 0) return FB_OK;
+    cudaSetDevice(c->device);
+    fb::launch_particle_field(c, n, xyz_dev, cells_dev, E3_dev);
+    return FB_OK;
+}
+
+int fb_particle_field(fb_ctx* c, long n, const double* xyz, const int* cells, double* E3) {
+    FB_REQUIRE(c, c->interp_ok && xyz && cells && E3, "fb_particle_field: interpolator not initialised");
+    if (n <= 0) return FB_OK;
+    cudaSetDevice(c->device);
+    FB_CUDA(c, c->d_pts.alloc(3 * (size_t) n)); FB_CUDA(c, c->d_cellsA.alloc(n)); FB_CUDA(c, c->d_sol.alloc(3 * (size_t) n));
+    FB_CUDA(c, cudaMemcpyAsync(c->d_pts.p, xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    FB_CUDA(c, cudaMemcpyAsync(c->d_cellsA.p, cells, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    fb::launch_particle_field(c, n, c->d_pts.p, c->d_cellsA.p, c->d_sol.p);
+    FB_CUDA(c, cudaMemcpyAsync(E3, c->d_sol.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return sync_check(c, "fb_particle_field");
+}
+
+}  // extern "C"

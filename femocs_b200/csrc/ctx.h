@@ -1,0 +1,167 @@
+// Internal context of libfemocs_b200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/femocs_b200.h"
+
+namespace fb {
+
+// ---- tiny RAII device buffer ---------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;       // keep capacity
+        release();
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc((void**) &p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    cudaError_t upload(const T* h, size_t count, cudaStream_t s) {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    cudaError_t upload(const std::vector<T>& h, cudaStream_t s) { return upload(h.data(), h.size(), s); }
+    cudaError_t zero(cudaStream_t s) { return p ? cudaMemsetAsync(p, 0, n * sizeof(T), s) : cudaSuccess; }
+};
+
+// pinned host staging buffer (grows, never shrinks)
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    cudaError_t reserve(size_t b) {
+        if (b <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMallocHost(&p, b);
+        if (e == cudaSuccess) bytes = b;
+        return e;
+    }
+};
+
+// cell tables of the interpolator, flattened for the device ----------------------------
+struct TetRec { double det0; double d[4][4]; };                 // 136 B: LinearTetrahedra det0..det4
+struct TriRec { double vert0[3], edge1[3], edge2[3], pvec[3], norm[3], maxd; };   // 128 B
+struct HexRec { double f[8][3]; };                              // 192 B: LinearHexahedra f0..f7
+
+struct CgScalars {          // device-resident CG state (one struct, updated by the kernels)
+    double gh;              // g.h of the previous iteration
+    double res2;            // ||g||^2 after the last update
+    double tol2;            // abs_tol^2
+    int it;                 // iterations completed
+    int done;               // 1 = converged, 2 = max_iter reached
+    int max_iter;
+    int pad;
+};
+
+}  // namespace fb
+
+struct fb_ctx {
+    int device = 0;
+    int n_sm = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long launches = 0;
+
+    // options
+    int cg_graph_iters = 32;
+    int cheb_degree = 2;
+    int dof_order = 0;
+
+    // ---- host copies of the mesh (femocs numbering) ----
+    int n_nodes = 0, n_hex = 0;
+    std::vector<double> xyz;
+    std::vector<int> hex8, hex_marker;
+    std::vector<int> node2vert, vert2node, hex2cell, cell2hex;
+    std::vector<int> vertex2dof, dof2vertex;
+    std::vector<int> cells_dof;              // 8 dof ids per solver cell, lexicographic (deal) order
+    int n_vert = 0, n_cells = 0, n_dofs = 0;
+    long nnz = 0;
+    std::vector<int> rowptr, col;            // CSR pattern, columns sorted
+    struct BFace { int cell, face, id; };
+    std::vector<BFace> bfaces;
+    std::vector<int> copper_dofs, top_dofs;  // Dirichlet candidates
+    int n_top_faces = 0;
+    bool mesh_ok = false, setup_ok = false, assembled = false, matrix_ok = false;
+    double applied_field = 0, applied_potential = 0;
+    int anode_dirichlet = 0;
+    int n_dirichlet = 0;
+
+    // ---- device: solver ----
+    fb::DevBuf<double> d_vxyz;               // coordinates per DoF (3*n_dofs)
+    fb::DevBuf<int> d_cells;                 // 8*n_cells dof ids (lexicographic)
+    fb::DevBuf<int> d_rowptr, d_col, d_diagpos;
+    fb::DevBuf<double> d_val, d_val_save;
+    fb::DevBuf<double> d_rhs, d_x, d_g, d_d, d_h, d_dinv, d_z, d_w;
+    fb::DevBuf<int> d_topfaces;              // 4 dof ids per top (Neumann) face
+    fb::DevBuf<int> d_bcflag; fb::DevBuf<double> d_bcval;
+    fb::DevBuf<double> d_partial;            // block partials for dot products
+    fb::DevBuf<fb::CgScalars> d_cg;
+    fb::DevBuf<int> d_vertex2dof;            // n_vert
+    fb::DevBuf<int> d_cell2hex, d_hex2cell;
+    fb::DevBuf<double> d_minmax;
+    cudaGraphExec_t cg_graph = nullptr;
+    int cg_graph_precond = -1, cg_graph_n = 0;
+    double last_solve_ms = 0; int last_iters = 0; long last_spmv = 0;
+    double cheb_lmax = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // ---- interpolator ----
+    bool interp_ok = false;
+    int n_tet = 0, n_tri = 0, n_quad = 0, n_voro = 0;
+    double decay_factor = -1;
+    fb::DevBuf<double> d_nxyz;               // all femocs nodes (3*n_nodes)
+    fb::DevBuf<int> d_hex8, d_node2vert;
+    fb::DevBuf<double> d_nodal;              // 5*n_nodes
+    fb::DevBuf<int> d_n2c_off, d_n2c_list;   // node -> (hex*8 + local) CSR
+    fb::DevBuf<int> d_voro_off, d_voro_list;
+    fb::DevBuf<fb::TetRec> d_tet; fb::DevBuf<double> d_tet_cent; fb::DevBuf<int> d_tet_mark, d_tet_nbr_off, d_tet_nbr, d_tet4;
+    fb::DevBuf<fb::TriRec> d_tri; fb::DevBuf<double> d_tri_cent; fb::DevBuf<int> d_tri_nbr_off, d_tri_nbr, d_tri2tet;
+    fb::DevBuf<fb::HexRec> d_hex; fb::DevBuf<int> d_quad2hex;
+    fb::DevBuf<int> d_qtet, d_qtri;          // 10 / 6 node ids
+    // scratch for queries
+    fb::DevBuf<double> d_pts; fb::DevBuf<int> d_cellsA, d_cellsB, d_scan, d_flag; fb::DevBuf<double> d_sol;
+    fb::DevBuf<unsigned char> d_dirtyA, d_dirtyB;
+    fb::PinnedBuf pin_in, pin_out;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define FB_CUDA(ctx, call)                                                                      \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return (ctx)->fail(FB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+// implemented in host_setup.cpp
+int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
+struct fb_interp_tables {
+    std::vector<fb::TetRec> tet; std::vector<double> tet_cent; std::vector<int> tet_mark, tet_nbr_off, tet_nbr;
+    std::vector<fb::TriRec> tri; std::vector<double> tri_cent; std::vector<int> tri_nbr_off, tri_nbr;
+    std::vector<fb::HexRec> hex;
+    std::vector<int> qtet, qtri, n2c_off, n2c_list;
+};
+void fb_host_interp_tables(const fb_ctx* c, const int* node_marker, const int* tet4, const int* tet_nbr4,
+                           const int* tet_marker, int n_tet, const int* tri3, const double* tri_norm3, int n_tri,
+                           const int* quad4, int n_quad, fb_interp_tables& out);

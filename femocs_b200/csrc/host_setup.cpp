@@ -1,0 +1,441 @@
+// Host-side setup of libfemocs_b200: everything the north star keeps on the host
+// ("Mesh generation and DoF numbering stay on the host in C++"): vertex compaction, cell
+// orientation, boundary marking, DoF numbering, CSR sparsity, and the interpolator's
+// per-cell precompute tables.  OpenMP-parallel, no CUDA calls here.
+//
+// Reference behaviour followed (paths relative to the reference root):
+//   src/TetgenCells.cpp:673-686   Hexahedra::export_vacuum
+//   src/DealSolver.cpp:191-209    import_mesh (delete_unused_vertices, invert_all_cells_of_negative_grid,
+//                                 create_triangulation_compatibility)
+//   src/DealSolver.cpp:460-518    mark_boundary, src/PoissonSolver.cpp:52-55 mark_mesh
+//   src/DealSolver.cpp:368-387    setup_system (distribute_dofs, make_sparsity_pattern)
+//   src/InterpolatorCells.cpp:523-629,1205-1267,1585-1637,1151-1173,1873-1895  precompute()
+//   src/Interpolator.cpp:60-76    node2cells
+#include <omp.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <numeric>
+
+#include "ctx.h"
+
+namespace {
+
+// lexicographic (deal.II) local vertex d  <-  femocs/UCD local vertex: lex[ucd_to_lex[k]] = ucd[k]
+const int UCD_TO_LEX[8] = {0, 1, 5, 4, 2, 3, 7, 6};
+// vertices of the six faces of the lexicographic cube (deal.II GeometryInfo<3>)
+const int FACE_VERTS[6][4] = {{0, 2, 4, 6}, {1, 3, 5, 7}, {0, 1, 4, 5}, {2, 3, 6, 7}, {0, 1, 2, 3}, {4, 5, 6, 7}};
+
+struct P3 { double x, y, z; };
+
+// signed volume of a trilinear hexahedron by 2x2x2 Gauss quadrature of det(J) (exact)
+double hex_volume(const P3 v[8]) {
+    const double a = 0.5 * (1.0 - 1.0 / std::sqrt(3.0)), b = 0.5 * (1.0 + 1.0 / std::sqrt(3.0));
+    const double g[2] = {a, b};
+    double vol = 0;
+    for (int q = 0; q < 8; ++q) {
+        const double xi[3] = {g[q & 1], g[(q >> 1) & 1], g[(q >> 2) & 1]};
+        double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int i = 0; i < 8; ++i) {
+            double f[3], df[3];
+            for (int d = 0; d < 3; ++d) {
+                const int bit = (i >> d) & 1;
+                f[d] = bit ? xi[d] : 1.0 - xi[d];
+                df[d] = bit ? 1.0 : -1.0;
+            }
+            const double dn[3] = {df[0] * f[1] * f[2], f[0] * df[1] * f[2], f[0] * f[1] * df[2]};
+            for (int e = 0; e < 3; ++e) {
+                J[0][e] += v[i].x * dn[e]; J[1][e] += v[i].y * dn[e]; J[2][e] += v[i].z * dn[e];
+            }
+        }
+        vol += 0.125 * (J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1])
+                      - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0])
+                      + J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]));
+    }
+    return vol;
+}
+
+inline uint64_t spread21(uint64_t v) {          // interleave helper for 63-bit Morton keys
+    v &= 0x1fffff;
+    v = (v | v << 32) & 0x1f00000000ffffULL;
+    v = (v | v << 16) & 0x1f0000ff0000ffULL;
+    v = (v | v << 8) & 0x100f00f00f00f00fULL;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+    v = (v | v << 2) & 0x1249249249249249ULL;
+    return v;
+}
+
+}  // namespace
+
+int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {
+    c->mesh_ok = false;
+    c->n_nodes = n_nodes; c->n_hex = n_hex;
+    c->xyz.assign(xyz, xyz + 3 * (size_t) n_nodes);
+    c->hex8.assign(hex8, hex8 + 8 * (size_t) n_hex);
+    c->hex_marker.assign(hex_marker, hex_marker + n_hex);
+    for (size_t i = 0; i < c->hex8.size(); ++i)
+        if (c->hex8[i] < 0 || c->hex8[i] >= n_nodes) return c->fail(FB_ERR_MESH, "hexahedron %zu references node %d", i / 8, c->hex8[i]);
+
+    // ---- solver cells and order-preserving vertex compaction ----
+    c->hex2cell.assign(n_hex, -1); c->cell2hex.clear();
+    c->node2vert.assign(n_nodes, -1);
+    for (int h = 0; h < n_hex; ++h)
+        if (hex_marker[h] > 0) {
+            c->hex2cell[h] = (int) c->cell2hex.size();
+            c->cell2hex.push_back(h);
+            for (int k = 0; k < 8; ++k) c->node2vert[hex8[8 * h + k]] = 0;
+        }
+    const int n_cells = c->n_cells = (int) c->cell2hex.size();
+    if (n_cells == 0) return c->fail(FB_ERR_MESH, "no vacuum hexahedra (marker > 0) in the mesh");
+    c->vert2node.clear();
+    for (int i = 0; i < n_nodes; ++i)
+        if (c->node2vert[i] == 0) { c->node2vert[i] = (int) c->vert2node.size(); c->vert2node.push_back(i); }
+    const int n_vert = c->n_vert = (int) c->vert2node.size();
+
+    std::vector<int> cv(8 * (size_t) n_cells);       // lexicographic vertex ids
+#pragma omp parallel for schedule(static)
+    for (int ce = 0; ce < n_cells; ++ce) {
+        const int* h = &hex8[8 * (size_t) c->cell2hex[ce]];
+        for (int k = 0; k < 8; ++k) cv[8 * (size_t) ce + UCD_TO_LEX[k]] = c->node2vert[h[k]];
+    }
+
+    // ---- orientation (invert_all_cells_of_negative_grid) ----
+    long n_neg = 0;
+#pragma omp parallel for schedule(static) reduction(+ : n_neg)
+    for (int ce = 0; ce < n_cells; ++ce) {
+        P3 v[8];
+        for (int k = 0; k < 8; ++k) {
+            const double* p = &xyz[3 * (size_t) c->vert2node[cv[8 * (size_t) ce + k]]];
+            v[k] = {p[0], p[1], p[2]};
+        }
+        if (hex_volume(v) < 0) ++n_neg;
+    }
+    if (n_neg == n_cells) {
+#pragma omp parallel for schedule(static)
+        for (int ce = 0; ce < n_cells; ++ce)
+            for (int k = 0; k < 4; ++k) std::swap(cv[8 * (size_t) ce + k], cv[8 * (size_t) ce + k + 4]);
+    } else if (n_neg > 0) {
+        return c->fail(FB_ERR_MESH, "%ld of %d hexahedra have negative volume", n_neg, n_cells);
+    }
+
+    // ---- vertex -> cells adjacency (CSR) ----
+    std::vector<int> v2c_off(n_vert + 1, 0);
+    for (size_t i = 0; i < cv.size(); ++i) v2c_off[cv[i] + 1]++;
+    for (int v = 0; v < n_vert; ++v) v2c_off[v + 1] += v2c_off[v];
+    std::vector<int> v2c(cv.size()), fill(v2c_off.begin(), v2c_off.end() - 1);
+    for (int ce = 0; ce < n_cells; ++ce)
+        for (int k = 0; k < 8; ++k) v2c[fill[cv[8 * (size_t) ce + k]]++] = ce;     // ascending cell ids per vertex
+
+    // ---- boundary faces: a face is interior iff another cell holds all 4 of its vertices ----
+    std::vector<unsigned char> is_b(6 * (size_t) n_cells, 0);
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int ce = 0; ce < n_cells; ++ce)
+        for (int f = 0; f < 6; ++f) {
+            int fv[4];
+            for (int k = 0; k < 4; ++k) fv[k] = cv[8 * (size_t) ce + FACE_VERTS[f][k]];
+            int best = 0;
+            for (int k = 1; k < 4; ++k)
+                if (v2c_off[fv[k] + 1] - v2c_off[fv[k]] < v2c_off[fv[best] + 1] - v2c_off[fv[best]]) best = k;
+            bool interior = false;
+            for (int q = v2c_off[fv[best]]; q < v2c_off[fv[best] + 1] && !interior; ++q) {
+                const int other = v2c[q];
+                if (other == ce) continue;
+                int hit = 0;
+                for (int k = 0; k < 8; ++k) {
+                    const int ov = cv[8 * (size_t) other + k];
+                    hit += (ov == fv[0]) + (ov == fv[1]) + (ov == fv[2]) + (ov == fv[3]);
+                }
+                interior = (hit == 4);
+            }
+            is_b[6 * (size_t) ce + f] = !interior;
+        }
+    auto face_centre = [&](int ce, int f, double ctr[3]) {      // TriaAccessor::center: vertex mean
+        double s[3] = {0, 0, 0};
+        for (int k = 0; k < 4; ++k) {
+            const double* p = &xyz[3 * (size_t) c->vert2node[cv[8 * (size_t) ce + FACE_VERTS[f][k]]]];
+            s[0] += p[0]; s[1] += p[1]; s[2] += p[2];
+        }
+        ctr[0] = s[0] / 4.0; ctr[1] = s[1] / 4.0; ctr[2] = s[2] / 4.0;
+    };
+    c->bfaces.clear();
+    double mx[3] = {-1e16, -1e16, -1e16}, mn[3] = {1e16, 1e16, 1e16};
+    for (int ce = 0; ce < n_cells; ++ce)
+        for (int f = 0; f < 6; ++f)
+            if (is_b[6 * (size_t) ce + f]) {
+                c->bfaces.push_back({ce, f, 0});
+                double p[3]; face_centre(ce, f, p);
+                for (int d = 0; d < 3; ++d) { mx[d] = std::max(mx[d], p[d]); mn[d] = std::min(mn[d], p[d]); }
+            }
+    const double eps = 1e-6;
+    c->n_top_faces = 0;
+    for (auto& bf : c->bfaces) {
+        double p[3]; face_centre(bf.cell, bf.face, p);
+        auto on = [&](double v, double b) { return std::fabs(v - b) <= eps; };
+        if (on(p[0], mn[0]) || on(p[0], mx[0]) || on(p[1], mn[1]) || on(p[1], mx[1])) bf.id = 4;   // vacuum_sides
+        else if (on(p[2], mx[2])) { bf.id = 8; c->n_top_faces++; }                               // vacuum_top
+        else bf.id = 2;                                                                           // copper_surface (bottom & other)
+    }
+
+    // ---- DoF numbering ----
+    c->vertex2dof.assign(n_vert, -1);
+    int n_dofs = 0;
+    if (c->dof_order == 1) {
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int v = 0; v < n_vert; ++v)
+            for (int d = 0; d < 3; ++d) {
+                const double x = xyz[3 * (size_t) c->vert2node[v] + d];
+                lo[d] = std::min(lo[d], x); hi[d] = std::max(hi[d], x);
+            }
+        std::vector<std::pair<uint64_t, int>> keys(n_vert);
+#pragma omp parallel for schedule(static)
+        for (int v = 0; v < n_vert; ++v) {
+            uint64_t q[3];
+            for (int d = 0; d < 3; ++d) {
+                const double t = (xyz[3 * (size_t) c->vert2node[v] + d] - lo[d]) / std::max(hi[d] - lo[d], 1e-300);
+                q[d] = (uint64_t) std::min(2097151.0, std::max(0.0, t * 2097151.0));
+            }
+            keys[v] = {spread21(q[0]) | (spread21(q[1]) << 1) | (spread21(q[2]) << 2), v};
+        }
+        std::sort(keys.begin(), keys.end());
+        for (int i = 0; i < n_vert; ++i) c->vertex2dof[keys[i].second] = i;
+        n_dofs = n_vert;
+    } else {
+        // FE_Q(1) first-touch numbering: cells in order, local vertices 0..7 (deal.II distribute_dofs)
+        for (size_t i = 0; i < cv.size(); ++i)
+            if (c->vertex2dof[cv[i]] < 0) c->vertex2dof[cv[i]] = n_dofs++;
+    }
+    c->n_dofs = n_dofs;
+    c->dof2vertex.assign(n_dofs, -1);
+    for (int v = 0; v < n_vert; ++v) c->dof2vertex[c->vertex2dof[v]] = v;
+    c->cells_dof.resize(cv.size());
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long) cv.size(); ++i) c->cells_dof[i] = c->vertex2dof[cv[i]];
+
+    // ---- CSR sparsity: row r couples to every dof sharing a cell with it ----
+    c->rowptr.assign(n_dofs + 1, 0);
+    {
+        std::vector<int> cnt(n_dofs, 0);
+#pragma omp parallel
+        {
+            std::vector<int> buf;
+#pragma omp for schedule(dynamic, 2048)
+            for (int r = 0; r < n_dofs; ++r) {
+                const int v = c->dof2vertex[r];
+                buf.clear();
+                for (int q = v2c_off[v]; q < v2c_off[v + 1]; ++q)
+                    for (int k = 0; k < 8; ++k) buf.push_back(c->cells_dof[8 * (size_t) v2c[q] + k]);
+                std::sort(buf.begin(), buf.end());
+                cnt[r] = (int) (std::unique(buf.begin(), buf.end()) - buf.begin());
+            }
+        }
+        long tot = 0;
+        for (int r = 0; r < n_dofs; ++r) { tot += cnt[r]; if (tot > 2147483647L) return c->fail(FB_ERR_MESH, "nnz exceeds 32-bit index range"); c->rowptr[r + 1] = (int) tot; }
+        c->nnz = tot;
+        c->col.resize(tot);
+#pragma omp parallel
+        {
+            std::vector<int> buf;
+#pragma omp for schedule(dynamic, 2048)
+            for (int r = 0; r < n_dofs; ++r) {
+                const int v = c->dof2vertex[r];
+                buf.clear();
+                for (int q = v2c_off[v]; q < v2c_off[v + 1]; ++q)
+                    for (int k = 0; k < 8; ++k) buf.push_back(c->cells_dof[8 * (size_t) v2c[q] + k]);
+                std::sort(buf.begin(), buf.end());
+                buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
+                std::copy(buf.begin(), buf.end(), c->col.begin() + c->rowptr[r]);
+            }
+        }
+    }
+
+    // ---- Dirichlet candidate dofs per boundary id (interpolate_boundary_values) ----
+    std::vector<unsigned char> on_cu(n_dofs, 0), on_top(n_dofs, 0);
+    for (const auto& bf : c->bfaces)
+        for (int k = 0; k < 4; ++k) {
+            const int d = c->cells_dof[8 * (size_t) bf.cell + FACE_VERTS[bf.face][k]];
+            if (bf.id == 2) on_cu[d] = 1;
+            if (bf.id == 8) on_top[d] = 1;
+        }
+    c->copper_dofs.clear(); c->top_dofs.clear();
+    for (int d = 0; d < n_dofs; ++d) { if (on_cu[d]) c->copper_dofs.push_back(d); if (on_top[d]) c->top_dofs.push_back(d); }
+    c->mesh_ok = true;
+    return FB_OK;
+}
+
+// =======================================================================================
+//  Interpolator precompute tables.  The arithmetic below must reproduce the reference's
+//  tables bit for bit (cell location is compared bit-exactly), hence the expression order
+//  of src/InterpolatorCells.cpp is kept and this file is compiled with -ffp-contract=off.
+// =======================================================================================
+namespace {
+
+struct V { double x, y, z; };
+inline V operator+(V a, V b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V operator-(V a, V b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V operator*(V a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+inline V operator/(V a, double s) { return {a.x / s, a.y / s, a.z / s}; }
+
+// 3x3 with a unit last column / plain 3x3 (InterpolatorCells.cpp:470-480)
+inline double d2(V a, V b) { return a.x * (b.y - b.z) - a.y * (b.x - b.z) + a.z * (b.x - b.y); }
+inline double d3(V a, V b, V c) {
+    return a.x * (b.y * c.z - c.y * b.z) - b.x * (a.y * c.z - c.y * a.z) + c.x * (a.y * b.z - b.y * a.z);
+}
+
+}  // namespace
+
+void fb_host_interp_tables(const fb_ctx* c, const int* node_marker, const int* tet4, const int* tet_nbr4,
+                           const int* tet_marker, int n_tet, const int* tri3, const double* tri_norm3, int n_tri,
+                           const int* quad4, int n_quad, fb_interp_tables& T) {
+    const int n_nodes = c->n_nodes, n_hex = c->n_hex;
+    auto node = [&](int i) { return V{c->xyz[3 * (size_t) i], c->xyz[3 * (size_t) i + 1], c->xyz[3 * (size_t) i + 2]}; };
+
+    // ---------------- tetrahedra (:523-629) ----------------
+    T.tet.resize(n_tet); T.tet_cent.resize(3 * (size_t) n_tet); T.tet_mark.resize(n_tet);
+    std::vector<int> n2t_off(n_nodes + 1, 0);
+    for (long i = 0; i < 4L * n_tet; ++i) n2t_off[tet4[i] + 1]++;
+    for (int i = 0; i < n_nodes; ++i) n2t_off[i + 1] += n2t_off[i];
+    std::vector<int> n2t(4 * (size_t) n_tet), pos(n2t_off.begin(), n2t_off.end() - 1);
+    for (int t = 0; t < n_tet; ++t) for (int k = 0; k < 4; ++k) n2t[pos[tet4[4 * t + k]]++] = t;
+
+    std::vector<std::vector<int>> nbr(n_tet);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int t = 0; t < n_tet; ++t) {
+        const int* nn = &tet_nbr4[4 * (size_t) t];
+        std::vector<int>& L = nbr[t];
+        auto push_unique = [&](int v) { if (std::find(L.begin(), L.end(), v) == L.end()) L.push_back(v); };
+        // face neighbours in TetGen order, then vertex-sharing tets; duplicates dropped (first
+        // occurrence kept) -- the reference list (:549-560) holds repeats, which never change the
+        // first hit of locate_cell
+        for (int k = 0; k < 4; ++k) if (nn[k] >= 0) push_unique(nn[k]);
+        for (int k = 0; k < 4; ++k) {
+            const int nd = tet4[4 * t + k];
+            for (int q = n2t_off[nd]; q < n2t_off[nd + 1]; ++q) {
+                const int o = n2t[q];
+                if (o != t && o != nn[0] && o != nn[1] && o != nn[2] && o != nn[3]) push_unique(o);
+            }
+        }
+        const V v1 = node(tet4[4 * t]), v2 = node(tet4[4 * t + 1]), v3 = node(tet4[4 * t + 2]), v4 = node(tet4[4 * t + 3]);
+        V ctr = {0, 0, 0};
+        ctr = ctr + v1; ctr = ctr + v2; ctr = ctr + v3; ctr = ctr + v4;
+        ctr = ctr * (1.0 / 4);
+        T.tet_cent[3 * (size_t) t] = ctr.x; T.tet_cent[3 * (size_t) t + 1] = ctr.y; T.tet_cent[3 * (size_t) t + 2] = ctr.z;
+        fb::TetRec& R = T.tet[t];
+        {   // 4x4 determinant with a unit last column (:483-489)
+            const double e1 = d3(v2, v3, v4), e2 = d3(v1, v3, v4), e3 = d3(v1, v2, v4), e4 = d3(v1, v2, v3);
+            R.det0 = 1.0 / (e4 - e3 + e2 - e1);
+        }
+        double a, b, cc, d;
+        a = d2({v2.y, v3.y, v4.y}, {v2.z, v3.z, v4.z}); b = d2({v2.x, v3.x, v4.x}, {v2.z, v3.z, v4.z});
+        cc = d2({v2.x, v3.x, v4.x}, {v2.y, v3.y, v4.y}); d = d3({v2.x, v3.x, v4.x}, {v2.y, v3.y, v4.y}, {v2.z, v3.z, v4.z});
+        R.d[0][0] = a; R.d[0][1] = -b; R.d[0][2] = cc; R.d[0][3] = -d;
+        a = d2({v1.y, v3.y, v4.y}, {v1.z, v3.z, v4.z}); b = d2({v1.x, v3.x, v4.x}, {v1.z, v3.z, v4.z});
+        cc = d2({v1.x, v3.x, v4.x}, {v1.y, v3.y, v4.y}); d = d3({v1.x, v3.x, v4.x}, {v1.y, v3.y, v4.y}, {v1.z, v3.z, v4.z});
+        R.d[1][0] = -a; R.d[1][1] = b; R.d[1][2] = -cc; R.d[1][3] = d;
+        a = d2({v1.y, v2.y, v4.y}, {v1.z, v2.z, v4.z}); b = d2({v1.x, v2.x, v4.x}, {v1.z, v2.z, v4.z});
+        cc = d2({v1.x, v2.x, v4.x}, {v1.y, v2.y, v4.y}); d = d3({v1.x, v2.x, v4.x}, {v1.y, v2.y, v4.y}, {v1.z, v2.z, v4.z});
+        R.d[2][0] = a; R.d[2][1] = -b; R.d[2][2] = cc; R.d[2][3] = -d;
+        a = d2({v1.y, v2.y, v3.y}, {v1.z, v2.z, v3.z}); b = d2({v1.x, v2.x, v3.x}, {v1.z, v2.z, v3.z});
+        cc = d2({v1.x, v2.x, v3.x}, {v1.y, v2.y, v3.y}); d = d3(v1, v2, v3);
+        R.d[3][0] = -a; R.d[3][1] = b; R.d[3][2] = -cc; R.d[3][3] = d;
+        T.tet_mark[t] = tet_marker[t] != 3;       // narrow_search_to(TYPES.VACUUM) (:730-732)
+    }
+    T.tet_nbr_off.assign(n_tet + 1, 0);
+    for (int t = 0; t < n_tet; ++t) T.tet_nbr_off[t + 1] = T.tet_nbr_off[t] + (int) nbr[t].size();
+    T.tet_nbr.resize(T.tet_nbr_off[n_tet]);
+    for (int t = 0; t < n_tet; ++t) std::copy(nbr[t].begin(), nbr[t].end(), T.tet_nbr.begin() + T.tet_nbr_off[t]);
+
+    // ---------------- hexahedra (:1205-1267) ----------------
+    T.hex.resize(n_hex);
+#pragma omp parallel for schedule(static)
+    for (int h = 0; h < n_hex; ++h) {
+        V x[8];
+        for (int k = 0; k < 8; ++k) x[k] = node(c->hex8[8 * (size_t) h + k]);
+        const V x1 = x[0], x2 = x[1], x3 = x[2], x4 = x[3], x5 = x[4], x6 = x[5], x7 = x[6], x8 = x[7];
+        V f[8];
+        f[0] = (x1 + x2 + x3 + x4 + x5 + x6 + x7 + x8) / 8.0;
+        f[1] = ((x1 * -1) + x2 + x3 - x4 - x5 + x6 + x7 - x8) / 8.0;
+        f[2] = ((x1 * -1) - x2 + x3 + x4 - x5 - x6 + x7 + x8) / 8.0;
+        f[3] = ((x1 * -1) - x2 - x3 - x4 + x5 + x6 + x7 + x8) / 8.0;
+        f[4] = (x1 - x2 + x3 - x4 + x5 - x6 + x7 - x8) / 8.0;
+        f[5] = (x1 - x2 - x3 + x4 - x5 + x6 + x7 - x8) / 8.0;
+        f[6] = (x1 + x2 - x3 - x4 - x5 - x6 + x7 + x8) / 8.0;
+        f[7] = ((x1 * -1) + x2 - x3 + x4 + x5 - x6 + x7 - x8) / 8.0;
+        for (int k = 0; k < 8; ++k) { T.hex[h].f[k][0] = f[k].x; T.hex[h].f[k][1] = f[k].y; T.hex[h].f[k][2] = f[k].z; }
+    }
+
+    // ---------------- triangles (:1585-1637) ----------------
+    T.tri.resize(n_tri); T.tri_cent.resize(3 * (size_t) n_tri);
+    std::vector<std::vector<int>> n2r(n_nodes);
+    for (int t = 0; t < n_tri; ++t) for (int k = 0; k < 3; ++k) n2r[tri3[3 * t + k]].push_back(t);
+    std::vector<std::vector<int>> rnbr(n_tri);
+    for (int t = 0; t < n_tri; ++t) {
+        std::vector<int>& L = rnbr[t];
+        for (int k = 0; k < 3; ++k)
+            for (int o : n2r[tri3[3 * t + k]])
+                if (o != t && std::find(L.begin(), L.end(), o) == L.end()) L.push_back(o);
+        const V v0 = node(tri3[3 * t]), v1 = node(tri3[3 * t + 1]), v2 = node(tri3[3 * t + 2]);
+        const V nrm = {tri_norm3[3 * t], tri_norm3[3 * t + 1], tri_norm3[3 * t + 2]};
+        const V e1 = v1 - v0, e2 = v2 - v0;
+        const V pv = {nrm.y * e2.z - nrm.z * e2.y, nrm.z * e2.x - nrm.x * e2.z, nrm.x * e2.y - nrm.y * e2.x};
+        const double i_det = 1.0 / (e1.x * pv.x + e1.y * pv.y + e1.z * pv.z);
+        fb::TriRec& R = T.tri[t];
+        const V e1s = e1 * i_det, pvs = pv * i_det;
+        R.vert0[0] = v0.x; R.vert0[1] = v0.y; R.vert0[2] = v0.z;
+        R.edge1[0] = e1s.x; R.edge1[1] = e1s.y; R.edge1[2] = e1s.z;
+        R.edge2[0] = e2.x; R.edge2[1] = e2.y; R.edge2[2] = e2.z;
+        R.pvec[0] = pvs.x; R.pvec[1] = pvs.y; R.pvec[2] = pvs.z;
+        R.norm[0] = nrm.x; R.norm[1] = nrm.y; R.norm[2] = nrm.z;
+        R.maxd = std::sqrt(e2.x * e2.x + e2.y * e2.y + e2.z * e2.z);
+        const V ctr = (v0 + v1 + v2) / 3.0;           // TetgenFaces::calc_appendices, TetgenCells.cpp:402
+        T.tri_cent[3 * (size_t) t] = ctr.x; T.tri_cent[3 * (size_t) t + 1] = ctr.y; T.tri_cent[3 * (size_t) t + 2] = ctr.z;
+    }
+    T.tri_nbr_off.assign(n_tri + 1, 0);
+    for (int t = 0; t < n_tri; ++t) T.tri_nbr_off[t + 1] = T.tri_nbr_off[t] + (int) rnbr[t].size();
+    T.tri_nbr.resize(T.tri_nbr_off[n_tri]);
+    for (int t = 0; t < n_tri; ++t) std::copy(rnbr[t].begin(), rnbr[t].end(), T.tri_nbr.begin() + T.tri_nbr_off[t]);
+
+    // ---------------- quadratic cells (:1151-1173, :1873-1895) ----------------
+    auto common = [](const int* a, int na, const int* b, int nb) {
+        for (int i = 0; i < na; ++i) for (int j = 0; j < nb; ++j) if (a[i] == b[j]) return a[i];
+        return -1;
+    };
+    T.qtet.assign(10 * (size_t) n_tet, 0);
+    for (int t = 0; t < n_tet; ++t) {
+        if (n_hex <= t) continue;
+        int en[4][8], ne[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 4; ++i)
+            for (int k = 0; k < 8; ++k) {
+                const int hn = c->hex8[8 * (size_t) (4 * t + i) + k];
+                if (node_marker[hn] == 2) en[i][ne[i]++] = hn;       // TYPES.EDGECENTROID
+            }
+        int* q = &T.qtet[10 * (size_t) t];
+        for (int k = 0; k < 4; ++k) q[k] = tet4[4 * t + k];
+        q[4] = common(en[0], ne[0], en[1], ne[1]); q[5] = common(en[1], ne[1], en[2], ne[2]);
+        q[6] = common(en[2], ne[2], en[0], ne[0]); q[7] = common(en[0], ne[0], en[3], ne[3]);
+        q[8] = common(en[1], ne[1], en[3], ne[3]); q[9] = common(en[2], ne[2], en[3], ne[3]);
+    }
+    T.qtri.assign(6 * (size_t) n_tri, 0);
+    for (int f = 0; f < n_tri; ++f) {
+        if (n_quad == 0) continue;
+        int en[3][4], ne[3] = {0, 0, 0};
+        for (int i = 0; i < 3; ++i)
+            for (int k = 0; k < 4; ++k) {
+                const int qn = quad4[4 * (size_t) (3 * f + i) + k];
+                if (node_marker[qn] == 2) en[i][ne[i]++] = qn;
+            }
+        int* q = &T.qtri[6 * (size_t) f];
+        for (int k = 0; k < 3; ++k) q[k] = tri3[3 * f + k];
+        q[3] = common(en[0], ne[0], en[1], ne[1]); q[4] = common(en[1], ne[1], en[2], ne[2]); q[5] = common(en[2], ne[2], en[0], ne[0]);
+    }
+
+    // ---------------- node -> (vacuum hex, local node) CSR (Interpolator.cpp:60-76) ----------------
+    T.n2c_off.assign(n_nodes + 1, 0);
+    for (int h = 0; h < n_hex; ++h)
+        if (c->hex_marker[h] > 0) for (int k = 0; k < 8; ++k) T.n2c_off[c->hex8[8 * (size_t) h + k] + 1]++;
+    for (int i = 0; i < n_nodes; ++i) T.n2c_off[i + 1] += T.n2c_off[i];
+    T.n2c_list.resize(T.n2c_off[n_nodes]);
+    std::vector<int> p2(T.n2c_off.begin(), T.n2c_off.end() - 1);
+    for (int h = 0; h < n_hex; ++h)
+        if (c->hex_marker[h] > 0) for (int k = 0; k < 8; ++k) T.n2c_list[p2[c->hex8[8 * (size_t) h + k]]++] = 8 * h + k;
+}

@@ -1,0 +1,626 @@
+// CUDA kernels (sm_100a) of the solution transfer: nodal field extraction, cell location
+// (bit-exact with the reference's sequential chained-guess loop), interpolation, and the
+// PIC particle look-ups.  THIS FILE IS COMPILED WITH -fmad=false: the reference is built for
+// baseline x86-64 (no FMA contraction) and cell indices are compared bit-for-bit, so every
+// expression below keeps the operation order of src/InterpolatorCells.cpp.
+//
+// Reference behaviour replaced (paths relative to the reference root):
+//   src/Interpolator.cpp:103-190            store_solution / store_elfield / average_nodal_fields
+//   src/InterpolatorCells.cpp:269-307       InterpolatorCells<dim>::locate_cell
+//   src/InterpolatorCells.cpp:631-661       LinearTetrahedra::point_in_cell / shape_functions
+//   src/InterpolatorCells.cpp:1272-1416     LinearHexahedra Newton map, shape functions, gradients
+//   src/InterpolatorCells.cpp:1462-1562     nodal gradients, point_in_cell, locate_cell
+//   src/InterpolatorCells.cpp:1639-1686     LinearTriangles
+//   src/InterpolatorCells.cpp:1838-1982     QuadraticTriangles / LinearQuadrangles
+//   src/SolutionReader.cpp:43-65,136-190    the per-point driver loops
+//   src/Pic.cpp:186-209                     particle cell update and field look-up
+//   src/PoissonSolver.cpp:299-319           space-charge right-hand side
+//
+// These kernels are latency/L2-bound (mesh tables of the native meshes are a few MB and stay
+// in the 126 MB L2); the mandatory HBM traffic is 24 B in + 44 B out per point.
+#include "kernels.h"
+
+namespace fb {
+
+#define FB_ZERO 1e-15      // InterpolatorCells.h:241
+
+struct P3 { double x, y, z; };
+__device__ __forceinline__ P3 operator+(P3 a, P3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ P3 operator-(P3 a, P3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ P3 operator*(P3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ double dot3(P3 a, P3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ P3 cross3(P3 a, P3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ double det3(P3 a, P3 b, P3 c) {          // InterpolatorCells.cpp:477-480
+    return a.x * (b.y * c.z - c.y * b.z) - b.x * (a.y * c.z - c.y * a.z) + c.x * (a.y * b.z - b.y * a.z);
+}
+__device__ __forceinline__ double dist2(P3 a, const double* __restrict__ b) {    // Primitives.h:247-252
+    const double xx = a.x - b[0], yy = a.y - b[1], zz = a.z - b[2];
+    return xx * xx + yy * yy + zz * zz;
+}
+__device__ __forceinline__ P3 ldp(const double* __restrict__ a, long i) { return {a[3 * i], a[3 * i + 1], a[3 * i + 2]}; }
+__device__ __forceinline__ P3 p3(const double* a) { return {a[0], a[1], a[2]}; }
+__device__ __forceinline__ double comp(const P3& a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+struct Tables {                 // device view of the interpolator tables
+    const double* nxyz; const double* nodal; const int* hex8;
+    const TetRec* tet; const double* tet_cent; const int* tet_mark; const int* tet_nbr_off; const int* tet_nbr; const int* tet4; int n_tet;
+    const TriRec* tri; const double* tri_cent; const int* tri_nbr_off; const int* tri_nbr; const int* tri2tet; int n_tri;
+    const HexRec* hex; const int* quad2hex; const int* qtet; const int* qtri;
+};
+
+// ---- tetrahedra ----
+__device__ __forceinline__ double tet_bary(const TetRec& R, P3 p, int k) {
+    return R.det0 * (p.x * R.d[k][0] + p.y * R.d[k][1] + p.z * R.d[k][2] + R.d[k][3]);     // Vec4(point,1).dotProduct
+}
+__device__ __forceinline__ bool tet_in(const TetRec& R, P3 p) {                          // :631-649
+    if (tet_bary(R, p, 0) < -FB_ZERO) return false;
+    if (tet_bary(R, p, 1) < -FB_ZERO) return false;
+    if (tet_bary(R, p, 2) < -FB_ZERO) return false;
+    if (tet_bary(R, p, 3) < -FB_ZERO) return false;
+    return true;
+}
+__device__ __forceinline__ void tet_sf(const TetRec& R, P3 p, double b[4]) {              // :651-661
+#pragma unroll
+    for (int k = 0; k < 4; ++k) b[k] = FB_ZERO + tet_bary(R, p, k);
+}
+
+// ---- triangles ----
+__device__ __forceinline__ bool tri_in(const TriRec& R, P3 p) {                           // :1639-1650
+    const P3 tvec = p - p3(R.vert0);
+    const double u = dot3(tvec, p3(R.pvec));
+    if (u < -FB_ZERO || u > 1 + FB_ZERO) return false;
+    const P3 qvec = cross3(tvec, p3(R.edge1));
+    const double v = dot3(qvec, p3(R.norm));
+    if (v < -FB_ZERO || u + v > 1 + FB_ZERO) return false;
+    return fabs(dot3(qvec, p3(R.edge2))) < R.maxd;
+}
+__device__ __forceinline__ void tri_sf(const TriRec& R, P3 p, double b[3]) {              // :1652-1660
+    const P3 tvec = p - p3(R.vert0);
+    const P3 qvec = cross3(tvec, p3(R.edge1));
+    const double v = dot3(tvec, p3(R.pvec));
+    const double w = dot3(qvec, p3(R.norm));
+    const double u = 1.0 - v - w;
+    b[0] = FB_ZERO + u; b[1] = FB_ZERO + v; b[2] = FB_ZERO + w;
+}
+__device__ __forceinline__ double tri_fast_distance(const TriRec& R, P3 p) {              // :1743-1747
+    const P3 tvec = p - p3(R.vert0);
+    const P3 qvec = cross3(tvec, p3(R.edge1));
+    return dot3(p3(R.edge2), qvec);
+}
+
+// cell families for the generic locate_cell (:269-307)
+struct TetFam {
+    typedef TetRec Rec;
+    static __device__ __forceinline__ const Rec* recs(const Tables& T) { return T.tet; }
+    static __device__ __forceinline__ const double* cents(const Tables& T) { return T.tet_cent; }
+    static __device__ __forceinline__ int count(const Tables& T) { return T.n_tet; }
+    static __device__ __forceinline__ bool searchable(const Tables& T, int c) { return T.tet_mark[c] == 0; }
+    static __device__ __forceinline__ const int* nbr_off(const Tables& T) { return T.tet_nbr_off; }
+    static __device__ __forceinline__ const int* nbr(const Tables& T) { return T.tet_nbr; }
+    static __device__ __forceinline__ bool in(const Rec& R, P3 p) { return tet_in(R, p); }
+};
+struct TriFam {
+    typedef TriRec Rec;
+    static __device__ __forceinline__ const Rec* recs(const Tables& T) { return T.tri; }
+    static __device__ __forceinline__ const double* cents(const Tables& T) { return T.tri_cent; }
+    static __device__ __forceinline__ int count(const Tables& T) { return T.n_tri; }
+    static __device__ __forceinline__ bool searchable(const Tables&, int) { return true; }   // lintri markers are all 0
+    static __device__ __forceinline__ const int* nbr_off(const Tables& T) { return T.tri_nbr_off; }
+    static __device__ __forceinline__ const int* nbr(const Tables& T) { return T.tri_nbr; }
+    static __device__ __forceinline__ bool in(const Rec& R, P3 p) { return tri_in(R, p); }
+};
+
+// the linear-scan tail of locate_cell for ONE point, straight from global/L2 memory
+template <class Fam>
+__device__ int scan_all(const Tables& T, P3 p) {
+    double min_d2 = 1e100; int min_index = 0;
+    const int n = Fam::count(T);
+    for (int c = 0; c < n; ++c) {
+        if (Fam::searchable(T, c) && Fam::in(Fam::recs(T)[c], p)) return c;
+        const double d2 = dist2(p, Fam::cents(T) + 3 * (long) c);
+        if (d2 < min_d2) { min_d2 = d2; min_index = c; }
+    }
+    return -min_index;
+}
+
+// guess -> neighbours -> (fallback) ; returns true on a hit
+template <class Fam>
+__device__ __forceinline__ bool try_guess(const Tables& T, P3 p, int guess, int& cell) {
+    if (guess < 0) return false;
+    if (Fam::in(Fam::recs(T)[guess], p)) { cell = guess; return true; }
+    const int* off = Fam::nbr_off(T); const int* nb = Fam::nbr(T);
+    for (int q = off[guess]; q < off[guess + 1]; ++q) {
+        const int c = nb[q];
+        if (Fam::in(Fam::recs(T)[c], p)) { cell = c; return true; }
+    }
+    return false;
+}
+
+template <class Fam>
+__device__ __forceinline__ int locate_cell(const Tables& T, P3 p, int guess) {
+    int cell;
+    if (try_guess<Fam>(T, p, guess, cell)) return cell;
+    return scan_all<Fam>(T, p);
+}
+
+// ---------------------------------------------------------------------------------------
+// Guess-free linear scan for MANY points: one thread per point, cell records staged through
+// shared memory in tiles so that a block reads each record from L2 once.
+// ---------------------------------------------------------------------------------------
+template <class Fam, int TILE>
+__global__ void __launch_bounds__(128) k_scan_cells(Tables T, long n, const double* __restrict__ pts, int* __restrict__ out) {
+    __shared__ typename Fam::Rec s_rec[TILE];
+    __shared__ double s_cent[TILE * 3];
+    __shared__ int s_ok[TILE];
+    const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n;
+    P3 p = {0, 0, 0};
+    if (active) p = ldp(pts, i);
+    bool found = !active;
+    int result = 0, min_index = 0;
+    double min_d2 = 1e100;
+    const int n_cells = Fam::count(T);
+    constexpr int WORDS = sizeof(typename Fam::Rec) / 8;
+    for (int base = 0; base < n_cells; base += TILE) {
+        const int cnt = min(TILE, n_cells - base);
+        __syncthreads();
+        const double* src = (const double*) (Fam::recs(T) + base);
+        double* dst = (double*) s_rec;
+        for (int w = threadIdx.x; w < cnt * WORDS; w += blockDim.x) dst[w] = src[w];
+        for (int w = threadIdx.x; w < cnt * 3; w += blockDim.x) s_cent[w] = Fam::cents(T)[3 * (long) base + w];
+        for (int w = threadIdx.x; w < cnt; w += blockDim.x) s_ok[w] = Fam::searchable(T, base + w);
+        __syncthreads();
+        if (!found) {
+            for (int k = 0; k < cnt; ++k) {
+                if (s_ok[k] && Fam::in(s_rec[k], p)) { found = true; result = base + k; break; }
+                const double d2 = dist2(p, s_cent + 3 * k);
+                if (d2 < min_d2) { min_d2 = d2; min_index = base + k; }
+            }
+        }
+        if (__syncthreads_and(found)) break;
+    }
+    if (active) out[i] = found ? result : -min_index;
+}
+
+// One Jacobi sweep of the chained-guess recurrence  T_i = F(p_i, |T_{i-1}|), T_{-1} = first_guess:
+// a point is recomputed only if its predecessor changed in the previous sweep.
+template <class Fam>
+__global__ void __launch_bounds__(128) k_chain_sweep(Tables T, long n, const double* __restrict__ pts, const int* __restrict__ scan,
+                                                     const int* __restrict__ prev, int* __restrict__ next,
+                                                     const unsigned char* __restrict__ dirty_prev, unsigned char* __restrict__ dirty_next,
+                                                     int first_guess, int first_sweep, int* __restrict__ changed) {
+    const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool need = first_sweep || (i > 0 && dirty_prev[i - 1]);
+    if (!need) { next[i] = prev[i]; dirty_next[i] = 0; return; }
+    const int guess = (i == 0) ? first_guess : abs(prev[i - 1]);
+    int cell;
+    if (!try_guess<Fam>(T, ldp(pts, i), guess, cell)) cell = scan[i];
+    next[i] = cell;
+    const bool ch = (cell != prev[i]);
+    dirty_next[i] = ch;
+    if (ch) *changed = 1;
+}
+
+// ---- hexahedra -------------------------------------------------------------------------
+__device__ void hex_nat_coords(const HexRec& H, P3 point, double& u, double& v, double& w) {     // :1272-1317
+    const P3 f0 = point - p3(H.f[0]);
+    const P3 f1 = p3(H.f[1]), f2 = p3(H.f[2]), f3 = p3(H.f[3]), f4 = p3(H.f[4]), f5 = p3(H.f[5]), f6 = p3(H.f[6]), f7 = p3(H.f[7]);
+    u = 0; v = 0; w = 0;
+    for (int i = 0; i < 20; ++i) {
+        const P3 f = (f0 - f1 * u - f2 * v - f3 * w - f4 * (u * v) - f5 * (u * w) - f6 * (v * w) - f7 * (u * v * w));
+        const P3 fu = f1 + f4 * v + f5 * w + f7 * (v * w);
+        const P3 fv = f2 + f4 * u + f6 * w + f7 * (u * w);
+        const P3 fw = f3 + f5 * u + f6 * v + f7 * (u * v);
+        double D = det3(fu, fv, fw);
+        D = 1.0 / D;
+        const double du = det3(f, fv, fw) * D;
+        const double dv = det3(fu, f, fw) * D;
+        const double dw = det3(fu, fv, f) * D;
+        u += du; v += dv; w += dw;
+        if (du * du + dv * dv + dw * dw < FB_ZERO) return;
+    }
+}
+
+__device__ __forceinline__ void hex_sf(const HexRec& H, P3 point, double sf[8]) {                 // :1334-1353
+    double u, v, w;
+    hex_nat_coords(H, point, u, v, w);
+    sf[0] = (1 - u) * (1 - v) * (1 - w) / 8.0;
+    sf[1] = (1 + u) * (1 - v) * (1 - w) / 8.0;
+    sf[2] = (1 + u) * (1 + v) * (1 - w) / 8.0;
+    sf[3] = (1 - u) * (1 + v) * (1 - w) / 8.0;
+    sf[4] = (1 - u) * (1 - v) * (1 + w) / 8.0;
+    sf[5] = (1 + u) * (1 - v) * (1 + w) / 8.0;
+    sf[6] = (1 + u) * (1 + v) * (1 + w) / 8.0;
+    sf[7] = (1 - u) * (1 + v) * (1 + w) / 8.0;
+}
+
+__device__ __forceinline__ bool hex_in(const Tables& T, P3 p, int cell) {                         // :1507-1528
+    double b[4];
+    tet_sf(T.tet[cell / 4], p, b);
+    if (b[0] >= 0 && b[1] >= 0 && b[2] >= 0 && b[3] >= 0) {
+        switch (cell % 4) {
+            case 0: return b[0] >= b[1] && b[0] >= b[2] && b[0] >= b[3];
+            case 1: return b[1] >= b[0] && b[1] >= b[2] && b[1] >= b[3];
+            case 2: return b[2] >= b[0] && b[2] >= b[1] && b[2] >= b[3];
+            case 3: return b[3] >= b[0] && b[3] >= b[1] && b[3] >= b[2];
+        }
+    }
+    return false;
+}
+
+// tail of LinearHexahedra::locate_cell (:1544-1561): signed tet -> signed hex
+__device__ __forceinline__ int hex_from_tet(const Tables& T, P3 p, int tet_signed) {
+    const int sign = tet_signed < 0 ? -1 : 1;
+    const int tet = abs(tet_signed);
+    double b[4];
+    tet_sf(T.tet[tet], p, b);
+    if (b[0] >= b[1] && b[0] >= b[2] && b[0] >= b[3]) return sign * (4 * tet + 0);
+    if (b[1] >= b[0] && b[1] >= b[2] && b[1] >= b[3]) return sign * (4 * tet + 1);
+    if (b[2] >= b[0] && b[2] >= b[1] && b[2] >= b[3]) return sign * (4 * tet + 2);
+    if (b[3] >= b[0] && b[3] >= b[1] && b[3] >= b[2]) return sign * (4 * tet + 3);
+    return -1;
+}
+// tail of LinearQuadrangles::locate_cell (:1961-1981)
+__device__ __forceinline__ int quad_from_tri(const Tables& T, P3 p, int tri_signed) {
+    const int sign = tri_signed < 0 ? -1 : 1;
+    const int tri = abs(tri_signed);
+    double b[3];
+    tri_sf(T.tri[tri], p, b);
+    if (b[0] >= b[1] && b[0] >= b[2]) return sign * (3 * tri + 0);
+    if (b[1] >= b[0] && b[1] >= b[2]) return sign * (3 * tri + 1);
+    if (b[2] >= b[0] && b[2] >= b[1]) return sign * (3 * tri + 2);
+    return -1;
+}
+
+__device__ __forceinline__ int hex_locate(const Tables& T, P3 p, int guess_hex) {                 // :1536-1562
+    return hex_from_tet(T, p, locate_cell<TetFam>(T, p, guess_hex / 4));
+}
+
+// ---- weighted sums of nodal Solutions (:359-380) ----
+template <int N>
+__device__ __forceinline__ void weighted(const Tables& T, const int* __restrict__ nodes, const double* w, double out[5]) {
+    double vx = 0, vy = 0, vz = 0, s1 = 0, s2 = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double* s = T.nodal + 5 * (long) nodes[i];
+        vx += s[0] * w[i]; vy += s[1] * w[i]; vz += s[2] * w[i];
+        s1 += s[3] * w[i]; s2 += s[4] * w[i];
+    }
+    out[0] = vx; out[1] = vy; out[2] = vz; out[3] = s1; out[4] = s2;
+}
+
+__device__ void tet_interp(const Tables& T, P3 p, int c, double out[5]) {
+    const int cell = abs(c);
+    double w[4];
+    tet_sf(T.tet[cell], p, w);
+    weighted<4>(T, T.tet4 + 4 * (long) cell, w, out);
+}
+__device__ void qtet_interp(const Tables& T, P3 p, int c, double out[5]) {                        // :795-816
+    const int cell = abs(c);
+    double b[4];
+    tet_sf(T.tet[cell], p, b);
+    const double b1 = b[0], b2 = b[1], b3 = b[2], b4 = b[3];
+    const double w[10] = {b1 * (2 * b1 - 1), b2 * (2 * b2 - 1), b3 * (2 * b3 - 1), b4 * (2 * b4 - 1),
+                          4 * b1 * b2, 4 * b2 * b3, 4 * b3 * b1, 4 * b1 * b4, 4 * b2 * b4, 4 * b3 * b4};
+    weighted<10>(T, T.qtet + 10 * (long) cell, w, out);
+}
+__device__ void hex_interp(const Tables& T, P3 p, int c, double out[5]) {
+    const int cell = abs(c);
+    double w[8];
+    hex_sf(T.hex[cell], p, w);
+    weighted<8>(T, T.hex8 + 8 * (long) cell, w, out);
+}
+
+// dim = 2 variants hop from the surface cell to the adjacent 3D cell (:1662-1686, :1838-1861, :1898-1920)
+__device__ void surface_interp(const Tables& T, int rank, P3 p, int c, double out[5]) {
+    const int cell = abs(c);
+    if (rank == 3) {
+        const int h0 = T.quad2hex[2 * cell], h1 = T.quad2hex[2 * cell + 1];
+        const double d = fabs(tri_fast_distance(T.tri[cell / 3], p));
+        if (d <= 100.0 * FB_ZERO) { hex_interp(T, p, h0, out); return; }
+        if (hex_in(T, p, h0)) { hex_interp(T, p, h0, out); return; }
+        hex_interp(T, p, hex_locate(T, p, h1), out);
+        return;
+    }
+    const int t0 = T.tri2tet[2 * cell], t1 = T.tri2tet[2 * cell + 1];
+    const double d = fabs(tri_fast_distance(T.tri[cell], p));
+    int tet;
+    if (d <= 100.0 * FB_ZERO) tet = t0;
+    else if (tet_in(T.tet[t0], p)) tet = t0;
+    else tet = locate_cell<TetFam>(T, p, t1);
+    if (rank == 1) tet_interp(T, p, tet, out); else qtet_interp(T, p, tet, out);
+}
+
+// final stage of locate_interpolate: base-family cell -> reported cell + interpolation
+__global__ void __launch_bounds__(128) k_finish_interp(Tables T, int dim, int rank, long n, const double* __restrict__ pts,
+                                                       const int* __restrict__ base_cells, int cells_are_final,
+                                                       int* __restrict__ cells_out, double* __restrict__ sol5) {
+    const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const P3 p = ldp(pts, i);
+    int cell = base_cells[i];
+    if (!cells_are_final && rank == 3) cell = (dim == 2) ? quad_from_tri(T, p, cell) : hex_from_tet(T, p, cell);
+    if (cells_out) cells_out[i] = cell;
+    double out[5];
+    if (dim == 2) surface_interp(T, rank, p, cell, out);
+    else if (rank == 1) tet_interp(T, p, cell, out);
+    else if (rank == 2) qtet_interp(T, p, cell, out);
+    else hex_interp(T, p, cell, out);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) sol5[5 * i + k] = out[k];
+}
+
+// ---- gradients ----------------------------------------------------------------------
+__device__ P3 hex_point_gradient(const Tables& T, P3 point, int hex) {                            // :1363-1416, :410-423
+    double u, v, w;
+    hex_nat_coords(T.hex[hex], point, u, v, w);
+    const int* shex = T.hex8 + 8 * (long) hex;
+    P3 dN[8] = {
+        {-(1 - v) * (1 - w), -(1 - u) * (1 - w), -(1 - u) * (1 - v)},
+        { (1 - v) * (1 - w), -(1 + u) * (1 - w), -(1 + u) * (1 - v)},
+        { (1 + v) * (1 - w),  (1 + u) * (1 - w), -(1 + u) * (1 + v)},
+        {-(1 + v) * (1 - w),  (1 - u) * (1 - w), -(1 - u) * (1 + v)},
+        {-(1 - v) * (1 + w), -(1 - u) * (1 + w),  (1 - u) * (1 - v)},
+        { (1 - v) * (1 + w), -(1 + u) * (1 + w),  (1 + u) * (1 - v)},
+        { (1 + v) * (1 + w),  (1 + u) * (1 + w),  (1 + u) * (1 + v)},
+        {-(1 + v) * (1 + w),  (1 - u) * (1 + w),  (1 - u) * (1 + v)}};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dN[i] = dN[i] * 0.125;
+    P3 J[3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const P3 x = ldp(T.nxyz, shex[k]);
+        J[0] = J[0] + x * dN[k].x; J[1] = J[1] + x * dN[k].y; J[2] = J[2] + x * dN[k].z;
+    }
+    double Jdet = det3(J[0], J[1], J[2]);
+    Jdet = 1.0 / Jdet;
+    P3 Jinv[3] = {
+        {J[1].y * J[2].z - J[2].y * J[1].z, J[2].x * J[1].z - J[1].x * J[2].z, J[1].x * J[2].y - J[2].x * J[1].y},
+        {J[2].y * J[0].z - J[0].y * J[2].z, J[0].x * J[2].z - J[2].x * J[0].z, J[2].x * J[0].y - J[0].x * J[2].y},
+        {J[0].y * J[1].z - J[1].y * J[0].z, J[1].x * J[0].z - J[0].x * J[1].z, J[0].x * J[1].y - J[1].x * J[0].y}};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) Jinv[i] = Jinv[i] * Jdet;
+    P3 r = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        P3 g = {0, 0, 0};
+        g = g + Jinv[0] * dN[k].x; g = g + Jinv[1] * dN[k].y; g = g + Jinv[2] * dN[k].z;
+        r = r - g * T.nodal[5 * (long) shex[k] + 4];
+    }
+    return r;
+}
+
+// closed-form nodal gradient (:1319-1332, :1462-1505) and interp_gradient(cell,node) (:425-439)
+__device__ P3 hex_nodal_gradient(const double* __restrict__ nxyz, const double* __restrict__ nodal,
+                                 const int* __restrict__ hex8, int hex, int node) {
+    const double su = (node == 1 || node == 2 || node == 5 || node == 6) ? 1.0 : -1.0;
+    const double sv = (node == 2 || node == 3 || node == 6 || node == 7) ? 1.0 : -1.0;
+    const double sw = (node >= 4) ? 1.0 : -1.0;
+    int n1, n2, n3;
+    switch (node) {
+        case 0: n1 = 1; n2 = 3; n3 = 4; break;
+        case 1: n1 = 0; n2 = 2; n3 = 5; break;
+        case 2: n1 = 3; n2 = 1; n3 = 6; break;
+        case 3: n1 = 2; n2 = 0; n3 = 7; break;
+        case 4: n1 = 5; n2 = 7; n3 = 0; break;
+        case 5: n1 = 4; n2 = 6; n3 = 1; break;
+        case 6: n1 = 7; n2 = 5; n3 = 2; break;
+        default: n1 = 6; n2 = 4; n3 = 3; break;
+    }
+    const int* shex = hex8 + 8 * (long) hex;
+    const int g0 = shex[node], g1 = shex[n1], g2 = shex[n2], g3 = shex[n3];
+    const P3 vec0 = ldp(nxyz, g0);
+    const P3 J0 = (vec0 - ldp(nxyz, g1)) * (su * 0.5);
+    const P3 J1 = (vec0 - ldp(nxyz, g2)) * (sv * 0.5);
+    const P3 J2 = (vec0 - ldp(nxyz, g3)) * (sw * 0.5);
+    double Jdet = det3(J0, J1, J2);
+    Jdet = 1.0 / Jdet;
+    P3 Jinv[3] = {
+        {J1.y * J2.z - J2.y * J1.z, J2.y * J0.z - J0.y * J2.z, J0.y * J1.z - J1.y * J0.z},
+        {J2.x * J1.z - J1.x * J2.z, J0.x * J2.z - J2.x * J0.z, J1.x * J0.z - J0.x * J1.z},
+        {J1.x * J2.y - J2.x * J1.y, J2.x * J0.y - J0.x * J2.y, J0.x * J1.y - J1.x * J0.y}};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) Jinv[i] = Jinv[i] * Jdet;
+    const P3 uvw = {su, sv, sw};
+    // sfg[node][i] = 0.5 * Jinv[i].uvw ; sfg[n_j][i] = -0.5 * Jinv[i][j] * uvw[j] ; other nodes 0
+    P3 s0, s1, s2, s3;
+    s0.x = 0.5 * dot3(Jinv[0], uvw); s0.y = 0.5 * dot3(Jinv[1], uvw); s0.z = 0.5 * dot3(Jinv[2], uvw);
+    s1.x = -0.5 * Jinv[0].x * su; s1.y = -0.5 * Jinv[1].x * su; s1.z = -0.5 * Jinv[2].x * su;
+    s2.x = -0.5 * Jinv[0].y * sv; s2.y = -0.5 * Jinv[1].y * sv; s2.z = -0.5 * Jinv[2].y * sv;
+    s3.x = -0.5 * Jinv[0].z * sw; s3.y = -0.5 * Jinv[1].z * sw; s3.z = -0.5 * Jinv[2].z * sw;
+    // vector_i -= sfg[i] * phi_i for i = 0..7 in local order (zero rows subtract +-0)
+    P3 r = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        P3 s = {0, 0, 0};
+        if (i == node) s = s0; else if (i == n1) s = s1; else if (i == n2) s = s2; else if (i == n3) s = s3;
+        r = r - s * nodal[5 * (long) shex[i] + 4];
+    }
+    return r;
+}
+
+// Interpolator::store_solution (:103-123): Solution(Vec3(0), charge_dens, potential) on vacuum nodes
+__global__ void k_store_solution(int n_nodes, const int* __restrict__ node2vert, const int* __restrict__ vertex2dof,
+                                 const double* __restrict__ x, double* __restrict__ nodal) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const int v = node2vert[i];
+    double* s = nodal + 5 * (long) i;
+    s[0] = 0; s[1] = 0; s[2] = 0; s[3] = 0;
+    s[4] = v >= 0 ? x[vertex2dof[v]] : 0.0;
+}
+
+// Interpolator::store_elfield (:125-140): mean over incident vacuum hexes of the nodal gradient
+__global__ void __launch_bounds__(128) k_nodal_field(int n_nodes, const int* __restrict__ node2vert, const int* __restrict__ n2c_off,
+                                                     const int* __restrict__ n2c_list, const double* __restrict__ nxyz,
+                                                     const int* __restrict__ hex8, double* nodal) {
+    // reads only the potentials (slot 4), writes only the vectors (slots 0..2): race free
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes || node2vert[i] < 0) return;
+    P3 mean = {0, 0, 0};
+    const int lo = n2c_off[i], hi = n2c_off[i + 1];
+    if (hi > lo) {
+        for (int q = lo; q < hi; ++q) {
+            const int e = n2c_list[q];
+            mean = mean + hex_nodal_gradient(nxyz, nodal, hex8, e >> 3, e & 7);
+        }
+        mean = mean * (1.0 / (hi - lo));
+    }
+    nodal[5 * (long) i] = mean.x; nodal[5 * (long) i + 1] = mean.y; nodal[5 * (long) i + 2] = mean.z;
+}
+
+// Interpolator::average_nodal_fields (:142-170): only tet nodes are written, only centroid-type
+// nodes are read (TetgenMesh.cpp:819-837), so the in-place update is order independent.
+__global__ void k_smooth(int n_voro, const int* __restrict__ off, const int* __restrict__ list, const double* __restrict__ nxyz,
+                         double decay, double* __restrict__ nodal) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_voro) return;
+    const int lo = off[i], hi = off[i + 1];
+    if (hi == lo) return;
+    const P3 tetnode = ldp(nxyz, i);
+    P3 vec = {0, 0, 0};
+    double w_sum = 0;
+    for (int q = lo; q < hi; ++q) {
+        const int nb = list[q];
+        const double w = exp(decay * sqrt(dist2(tetnode, nxyz + 3 * (long) nb)));
+        w_sum += w;
+        vec = vec + P3{nodal[5 * (long) nb], nodal[5 * (long) nb + 1], nodal[5 * (long) nb + 2]} * w;
+    }
+    if (w_sum > 0) {
+        vec = vec * (1.0 / w_sum);
+        nodal[5 * (long) i] = vec.x; nodal[5 * (long) i + 1] = vec.y; nodal[5 * (long) i + 2] = vec.z;
+    }
+}
+
+// ---- PIC particles --------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_particle_cells(Tables T, long n, const double* __restrict__ pts, const int* __restrict__ cell2hex,
+                                                        const int* __restrict__ hex2cell, int* __restrict__ cell_inout) {
+    const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cell_inout[i];
+    const int guess = c < 0 ? 0 : cell2hex[c];
+    const int fc = hex_locate(T, ldp(pts, i), guess);
+    cell_inout[i] = fc < 0 ? -1 : hex2cell[fc];
+}
+
+__global__ void __launch_bounds__(128) k_particle_field(Tables T, long n, const double* __restrict__ pts, const int* __restrict__ cell2hex,
+                                                        const int* __restrict__ cells, double* __restrict__ E3) {
+    const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const P3 E = hex_point_gradient(T, ldp(pts, i), cell2hex[cells[i]]);
+    E3[3 * i] = E.x; E3[3 * i + 1] = E.y; E3[3 * i + 2] = E.z;
+}
+
+// PoissonSolver<3>::assemble_space_charge_fast (PoissonSolver.cpp:299-319): 8 scatter-adds per particle
+__global__ void __launch_bounds__(128) k_space_charge(const HexRec* __restrict__ hexrec, long n, const double* __restrict__ pts,
+                                                      const int* __restrict__ pcell, int n_cells, const int* __restrict__ cell2hex,
+                                                      const int* __restrict__ cells_dof, double charge_factor, double* __restrict__ rhs) {
+    const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cell = pcell[i];
+    if (cell < 0 || cell >= n_cells) return;
+    double sf[8];
+    hex_sf(hexrec[cell2hex[cell]], ldp(pts, i), sf);
+    const int perm[8] = {0, 1, 4, 5, 3, 2, 7, 6};       // shape_funs_dealii (:1355-1358)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&rhs[cells_dof[8 * (long) cell + k]], sf[perm[k]] * charge_factor);
+}
+
+__global__ void k_pack_points(long n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                              int stride, double* __restrict__ out) {
+    const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[3 * i] = x[i * stride]; out[3 * i + 1] = y[i * stride]; out[3 * i + 2] = z[i * stride];
+}
+
+// ---------------------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------------------
+static Tables make_tables(const fb_ctx* c) {
+    Tables T;
+    T.nxyz = c->d_nxyz.p; T.nodal = c->d_nodal.p; T.hex8 = c->d_hex8.p;
+    T.tet = c->d_tet.p; T.tet_cent = c->d_tet_cent.p; T.tet_mark = c->d_tet_mark.p; T.tet_nbr_off = c->d_tet_nbr_off.p;
+    T.tet_nbr = c->d_tet_nbr.p; T.tet4 = c->d_tet4.p; T.n_tet = c->n_tet;
+    T.tri = c->d_tri.p; T.tri_cent = c->d_tri_cent.p; T.tri_nbr_off = c->d_tri_nbr_off.p; T.tri_nbr = c->d_tri_nbr.p;
+    T.tri2tet = c->d_tri2tet.p; T.n_tri = c->n_tri;
+    T.hex = c->d_hex.p; T.quad2hex = c->d_quad2hex.p; T.qtet = c->d_qtet.p; T.qtri = c->d_qtri.p;
+    return T;
+}
+
+void launch_extract(fb_ctx* c, int smoothen) {
+    const int g = (c->n_nodes + 127) / 128;
+    k_store_solution<<<(c->n_nodes + 255) / 256, 256, 0, c->stream>>>(c->n_nodes, c->d_node2vert.p, c->d_vertex2dof.p, c->d_x.p, c->d_nodal.p);
+    k_nodal_field<<<g, 128, 0, c->stream>>>(c->n_nodes, c->d_node2vert.p, c->d_n2c_off.p, c->d_n2c_list.p, c->d_nxyz.p, c->d_hex8.p,
+                                            c->d_nodal.p);
+    c->launches += 2;
+    if (smoothen && c->n_voro > 0) {
+        k_smooth<<<(c->n_voro + 127) / 128, 128, 0, c->stream>>>(c->n_voro, c->d_voro_off.p, c->d_voro_list.p, c->d_nxyz.p, c->decay_factor, c->d_nodal.p);
+        c->launches++;
+    }
+}
+
+void launch_pack_points(fb_ctx* c, long n, const double* x, const double* y, const double* z, int stride, double* out) {
+    k_pack_points<<<(unsigned) ((n + 255) / 256), 256, 0, c->stream>>>(n, x, y, z, stride, out);
+    c->launches++;
+}
+
+// chained-guess location for n points already on the device; returns base-family cells in c->d_cellsA or B
+int launch_locate_chain(fb_ctx* c, int dim, int rank, long n, const double* d_pts, int** result) {
+    const Tables T = make_tables(c);
+    const unsigned g = (unsigned) ((n + 127) / 128);
+    // abs(-1) = 1 is the first guess of the reference loop (SolutionReader.cpp:145, InterpolatorCells.cpp:443);
+    // hex/quad ranks divide it by 4/3 (:1539, :1955)
+    const int first_guess = (rank == 3) ? 0 : 1;
+    int* changed = c->d_flag.p;
+    if (dim == 2) k_scan_cells<TriFam, 64><<<g, 128, 0, c->stream>>>(T, n, d_pts, c->d_scan.p);
+    else k_scan_cells<TetFam, 64><<<g, 128, 0, c->stream>>>(T, n, d_pts, c->d_scan.p);
+    c->launches++;
+    int* prev = c->d_scan.p; int* next = c->d_cellsA.p;
+    unsigned char* dp = c->d_dirtyA.p; unsigned char* dn = c->d_dirtyB.p;
+    int* h_changed = (int*) c->pin_out.p;
+    for (long sweep = 0; sweep <= n; ++sweep) {
+        cudaMemsetAsync(changed, 0, sizeof(int), c->stream);
+        if (dim == 2) k_chain_sweep<TriFam><<<g, 128, 0, c->stream>>>(T, n, d_pts, c->d_scan.p, prev, next, dp, dn, first_guess, sweep == 0, changed);
+        else k_chain_sweep<TetFam><<<g, 128, 0, c->stream>>>(T, n, d_pts, c->d_scan.p, prev, next, dp, dn, first_guess, sweep == 0, changed);
+        c->launches++;
+        cudaMemcpyAsync(h_changed, changed, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return c->fail(FB_ERR_CUDA, "locate chain sweep failed: %s", cudaGetErrorString(e));
+        int* cur = next;
+        next = (cur == c->d_cellsA.p) ? c->d_cellsB.p : c->d_cellsA.p;
+        prev = cur;
+        std::swap(dp, dn);
+        if (!*h_changed) break;
+    }
+    *result = prev;
+    return FB_OK;
+}
+
+void launch_finish_interp(fb_ctx* c, int dim, int rank, long n, const double* d_pts, const int* d_base, int final_cells,
+                          int* d_cells_out, double* d_sol) {
+    const Tables T = make_tables(c);
+    k_finish_interp<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(T, dim, rank, n, d_pts, d_base, final_cells, d_cells_out, d_sol);
+    c->launches++;
+}
+
+void launch_particle_cells(fb_ctx* c, long n, const double* d_pts, int* d_cells) {
+    const Tables T = make_tables(c);
+    k_particle_cells<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(T, n, d_pts, c->d_cell2hex.p, c->d_hex2cell.p, d_cells);
+    c->launches++;
+}
+
+void launch_particle_field(fb_ctx* c, long n, const double* d_pts, const int* d_cells, double* d_E) {
+    const Tables T = make_tables(c);
+    k_particle_field<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(T, n, d_pts, c->d_cell2hex.p, d_cells, d_E);
+    c->launches++;
+}
+
+void launch_space_charge(fb_ctx* c, long n, const double* d_pts, const int* d_pcell, double charge_factor) {
+    if (n <= 0) return;
+    k_space_charge<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(c->d_hex.p, n, d_pts, d_pcell, c->n_cells, c->d_cell2hex.p,
+                                                                     c->d_cells.p, charge_factor, c->d_rhs.p);
+    c->launches++;
+}
+
+}  // namespace fb

@@ -1,0 +1,32 @@
+// Launch wrappers shared between the translation units of libfemocs_b200 (internal).
+#pragma once
+#include <utility>
+
+#include "ctx.h"
+
+namespace fb {
+
+// poisson_kernels.cu
+int choose_lanes(const fb_ctx* c);
+void launch_assemble_stiffness(fb_ctx* c, double* d_cell_vol);
+void launch_neumann(fb_ctx* c);
+void launch_set_bc(fb_ctx* c, const int* d_dofs, int n, double value);
+void launch_apply_bc_matrix(fb_ctx* c);
+void launch_apply_bc_rhs(fb_ctx* c);
+void launch_cg_init(fb_ctx* c, int lanes);
+void launch_cg_iteration(fb_ctx* c, int lanes);
+void launch_minmax(fb_ctx* c);
+void launch_gather(fb_ctx* c, int n, const int* idx, const double* src, double* dst);
+void launch_scatter(fb_ctx* c, int n, const int* idx, const double* src, double* dst);
+
+// interp_kernels.cu
+void launch_extract(fb_ctx* c, int smoothen);
+void launch_pack_points(fb_ctx* c, long n, const double* x, const double* y, const double* z, int stride, double* out);
+int launch_locate_chain(fb_ctx* c, int dim, int rank, long n, const double* d_pts, int** result);
+void launch_finish_interp(fb_ctx* c, int dim, int rank, long n, const double* d_pts, const int* d_base, int final_cells,
+                          int* d_cells_out, double* d_sol);
+void launch_particle_cells(fb_ctx* c, long n, const double* d_pts, int* d_cells);
+void launch_particle_field(fb_ctx* c, long n, const double* d_pts, const int* d_cells, double* d_E);
+void launch_space_charge(fb_ctx* c, long n, const double* d_pts, const int* d_pcell, double charge_factor);
+
+}  // namespace fb

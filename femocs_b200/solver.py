@@ -1,0 +1,377 @@
+"""Host-side mirror of the reference's operator interface for the electrostatic hot path.
+
+Class and method names follow the reference (include/PoissonSolver.h, include/DealSolver.h,
+include/Interpolator.h, include/SolutionReader.h, include/Pic.h) so that the parity tests
+read like the reference's call sites in src/ProjectRunaway.cpp:
+
+    solver = PoissonSolver(ctx, conf)                  # ProjectRunaway.cpp:38
+    solver.import_mesh(nodes, hexs, hex_markers)       # :216
+    solver.setup(-E0, V0); solver.assemble(True)       # :424-425
+    ncg = solver.solve()                               # :431   (+#CG / -#CG)
+    interp = Interpolator(ctx); interp.initialize(mesh)          # :435
+    interp.extract_solution(solver, smoothen)                    # :436
+    fields = FieldReader(interp); fields.set_preferences(False, 2, 1)
+    fields.interpolate(points)                                   # :303-304
+
+Everything numerical happens in libfemocs_b200.so (CUDA, sm_100a) behind the C ABI of
+include/femocs_b200.h; this module only marshals numpy arrays.  No CPU fallback exists.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import lib as _lib
+
+PRECOND_JACOBI = 1
+PRECOND_CHEBYSHEV = 2
+
+
+class FemocsB200Error(RuntimeError):
+    pass
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One CUDA device context (fb_ctx): owns the stream, the mesh and all device arrays."""
+
+    def __init__(self, device=0):
+        self.L = _lib.load()
+        h = self.L.fb_create(device)
+        if not h:
+            raise FemocsB200Error("fb_create failed: " + self.L.fb_create_error().decode())
+        self.h = C.c_void_p(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            raise FemocsB200Error("libfemocs_b200 error %d: %s" % (rc, self.L.fb_last_error(self.h).decode()))
+
+    def set_option(self, key, value):
+        self.check(self.L.fb_set_option(self.h, key.encode(), float(value)))
+
+    @property
+    def kernel_launches(self):
+        return int(self.L.fb_kernel_launches(self.h))
+
+    def synchronize(self):
+        self.check(self.L.fb_synchronize(self.h))
+
+
+@dataclass
+class FieldConfig:
+    """Subset of Config::Field used on the hot path (defaults: src/Config.cpp:63-71)."""
+    E0: float = 0.0
+    V0: float = 0.0
+    ssor_param: float = 1.2         # accepted for config compatibility; the GPU path uses Jacobi
+    cg_tolerance: float = 1e-9
+    n_cg: int = 10000
+    anode_BC: str = "neumann"
+    mode: str = "laplace"
+    V_min: float = -1.0
+    V_max: float = 1e4
+    precond: int = PRECOND_JACOBI
+
+
+class PoissonSolver:
+    """femocs::PoissonSolver<3> (+ DealSolver<3>) behind libfemocs_b200."""
+
+    def __init__(self, ctx, conf=None):
+        self.ctx = ctx
+        self.conf = conf or FieldConfig()
+        self.stat_sol_min = 0.0
+        self.stat_sol_max = 0.0
+        self.last_residual = 0.0
+        self._particles = None
+
+    # DealSolver::import_mesh (src/DealSolver.cpp:191-209); returns True on success like the reference
+    def import_mesh(self, nodes, hexs, hex_markers):
+        nodes = _f(nodes); hexs = _i(hexs); hex_markers = _i(hex_markers)
+        rc = self.ctx.L.fb_import_mesh(self.ctx.h, _p(nodes), len(nodes), _p(hexs), _p(hex_markers), len(hexs))
+        if rc == 3:
+            return False
+        self.ctx.check(rc)
+        sz = np.zeros(7, np.int64)
+        self.ctx.check(self.ctx.L.fb_get_sizes(self.ctx.h, _p(sz)))
+        (self.n_dofs, self.n_cells, self.nnz, self.n_vertices, self.n_bfaces, self.n_top_faces, _) = [int(v) for v in sz]
+        return True
+
+    def size(self):
+        return self.n_dofs
+
+    def get_n_cells(self):
+        return self.n_cells
+
+    # PoissonSolver::set_particles (include/PoissonSolver.h:29): (xyz[n,3], solver cell ids[n], charge factor)
+    def set_particles(self, xyz, cells, charge_factor):
+        self._particles = None if xyz is None else (_f(xyz), _i(cells), float(charge_factor))
+
+    # PoissonSolver::setup (src/PoissonSolver.cpp:162-167)
+    def setup(self, field, potential=0.0):
+        self.ctx.check(self.ctx.L.fb_poisson_setup(self.ctx.h, float(field), float(potential),
+                                                   int(self.conf.anode_BC.lower() == "dirichlet")))
+
+    # PoissonSolver::assemble (src/PoissonSolver.cpp:170-210)
+    def assemble(self, first_time=True):
+        if self.conf.mode != "laplace" and self._particles is not None and len(self._particles[1]):
+            xyz, cells, cf = self._particles
+            self.ctx.check(self.ctx.L.fb_poisson_assemble(self.ctx.h, int(first_time), _p(xyz), _p(cells), len(cells), cf))
+        else:
+            self.ctx.check(self.ctx.L.fb_poisson_assemble(self.ctx.h, int(first_time), None, None, 0, 0.0))
+
+    # PoissonSolver::solve (include/PoissonSolver.h:54): +#CG on success, -#CG when n_cg was hit
+    def solve(self, n_cg=None, cg_tolerance=None):
+        it = C.c_int(0); res = C.c_double(0)
+        self.ctx.check(self.ctx.L.fb_poisson_solve(
+            self.ctx.h, int(self.conf.n_cg if n_cg is None else n_cg),
+            float(self.conf.cg_tolerance if cg_tolerance is None else cg_tolerance),
+            int(self.conf.precond), C.byref(it), C.byref(res)))
+        self.last_residual = res.value
+        return it.value
+
+    def solve_stats(self):
+        ms = C.c_double(0); it = C.c_int(0); sp = C.c_long(0)
+        self.ctx.L.fb_last_solve_stats(self.ctx.h, C.byref(ms), C.byref(it), C.byref(sp))
+        return ms.value, it.value, sp.value
+
+    # DealSolver::check_limits (src/DealSolver.cpp:157-167)
+    def check_limits(self, low_limit, high_limit):
+        bad = C.c_int(0); a = C.c_double(0); b = C.c_double(0)
+        self.ctx.check(self.ctx.L.fb_check_limits(self.ctx.h, low_limit, high_limit, C.byref(bad), C.byref(a), C.byref(b)))
+        self.stat_sol_min, self.stat_sol_max = a.value, b.value
+        return bool(bad.value)
+
+    # DealSolver::export_solution / PoissonSolver::export_charge_dens (vertex order)
+    def export_solution(self):
+        out = np.zeros(self.n_vertices)
+        self.ctx.check(self.ctx.L.fb_export_solution(self.ctx.h, _p(out)))
+        return out
+
+    def export_charge_dens(self):
+        out = np.zeros(self.n_vertices)
+        self.ctx.check(self.ctx.L.fb_export_charge_dens(self.ctx.h, _p(out)))
+        return out
+
+    def import_solution(self, phi_vertex):
+        phi = _f(phi_vertex)
+        assert len(phi) == self.n_vertices
+        self.ctx.check(self.ctx.L.fb_import_solution(self.ctx.h, _p(phi)))
+
+    def get_cell_volumes(self):
+        out = np.zeros(self.n_cells)
+        self.ctx.check(self.ctx.L.fb_get_cell_volumes(self.ctx.h, _p(out)))
+        return out
+
+    def get_cell_vol(self, i):
+        return float(self.get_cell_volumes()[i])
+
+    def to_str(self):
+        return "#elems=%d, #nodes=%d, #dofs=%d" % (self.n_cells, self.n_vertices, self.n_dofs)
+
+    # test hook: assembled system in DoF numbering
+    def get_system(self):
+        rowptr = np.zeros(self.n_dofs + 1, np.int32); col = np.zeros(self.nnz, np.int32)
+        val = np.zeros(self.nnz); save = np.zeros(self.nnz)
+        rhs = np.zeros(self.n_dofs); sol = np.zeros(self.n_dofs)
+        v2d = np.zeros(self.n_vertices, np.int32); v2n = np.zeros(self.n_vertices, np.int32)
+        self.ctx.check(self.ctx.L.fb_get_system(self.ctx.h, _p(rowptr), _p(col), _p(val), _p(save), _p(rhs), _p(sol), _p(v2d), _p(v2n)))
+        return dict(rowptr=rowptr, col=col, val=val, val_save=save, rhs=rhs, sol=sol, vertex2dof=v2d, vertex2node=v2n)
+
+
+class Interpolator:
+    """femocs::Interpolator: nodal solutions + cell tables on the device."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.n_nodes = 0
+
+    # Interpolator::initialize(mesh, 0, TYPES.VACUUM) (src/Interpolator.cpp:28-77); `mesh` is a dict of
+    # the TetgenMesh arrays (tests/golden/mesh_*.npz layout)
+    def initialize(self, mesh):
+        m = mesh
+        self.n_nodes = len(m["nodes"])
+        a = dict(nm=_i(m["node_markers"]), tets=_i(m["tets"]), nbr=_i(m["tet_nbrs"]), tm=_i(m["tet_markers"]),
+                 tris=_i(m["tris"]), t2t=_i(m["tri2tet"]), tn=_f(m["tri_norms"]), quads=_i(m["quads"]),
+                 q2h=_i(m["quad2hex"]), voff=_i(m["voro_off"]), vlist=_i(m["voro_list"]) if len(m["voro_list"]) else np.zeros(1, np.int32))
+        self.ctx.check(self.ctx.L.fb_interp_initialize(
+            self.ctx.h, _p(a["nm"]), _p(a["tets"]), _p(a["nbr"]), _p(a["tm"]), len(a["tets"]),
+            _p(a["tris"]), _p(a["t2t"]), _p(a["tn"]), len(a["tris"]), _p(a["quads"]), _p(a["q2h"]), len(a["quads"]),
+            float(m["edgemax"][0]), _p(a["voff"]), _p(a["vlist"]), len(a["voff"]) - 1))
+
+    # Interpolator::extract_solution(PoissonSolver<3>&, smoothen) (src/Interpolator.cpp:172-190)
+    def extract_solution(self, fem, smoothen=False):
+        assert fem.ctx is self.ctx
+        self.ctx.check(self.ctx.L.fb_extract_solution(self.ctx.h, int(smoothen)))
+
+    def get_solutions(self):
+        out = np.zeros((self.n_nodes, 5))
+        self.ctx.check(self.ctx.L.fb_get_nodal_solutions(self.ctx.h, _p(out)))
+        return out
+
+    def set_solutions(self, sol5):
+        s = _f(sol5)
+        assert s.shape == (self.n_nodes, 5)
+        self.ctx.check(self.ctx.L.fb_set_nodal_solutions(self.ctx.h, _p(s)))
+
+
+class SolutionReader:
+    """femocs::SolutionReader: points + interpolated Solutions + located cells (atom markers)."""
+
+    def __init__(self, interpolator):
+        self.interpolator = interpolator
+        self.ctx = interpolator.ctx
+        self.dim, self.rank = 3, 1
+        self.points = np.zeros((0, 3)); self.ids = np.zeros(0, np.int64)
+        self.markers = np.zeros(0, np.int32); self.interpolation = np.zeros((0, 5))
+        self.atoms_mapped_to_cells = False
+
+    # SolutionReader::set_preferences (include/SolutionReader.h:60-67); sorting is not used on the hot path
+    def set_preferences(self, sort_atoms, dim, rank, centroid=False):
+        if dim not in (2, 3) or rank not in (1, 2, 3):
+            raise ValueError("invalid interpolation dimension/rank")
+        if sort_atoms or centroid:
+            raise NotImplementedError("sort_atoms / interp_centroids are outside the hot path")
+        self.dim, self.rank = dim, rank
+
+    def size(self):
+        return len(self.points)
+
+    def reserve_points(self, xyz, ids=None):
+        self.points = _f(xyz).reshape(-1, 3)
+        self.ids = np.arange(len(self.points)) if ids is None else np.asarray(ids)
+        self.atoms_mapped_to_cells = False
+
+    # SolutionReader::calc_full_interpolation (src/SolutionReader.cpp:136-165)
+    def calc_full_interpolation(self):
+        n = len(self.points)
+        self.markers = np.zeros(n, np.int32); self.interpolation = np.zeros((n, 5))
+        if n:
+            x = self.points
+            self.ctx.check(self.ctx.L.fb_locate_interpolate(
+                self.ctx.h, self.dim, self.rank, n, x.ctypes.data, x.ctypes.data + 8, x.ctypes.data + 16, 3,
+                _p(self.markers), _p(self.interpolation)))
+        self.atoms_mapped_to_cells = True
+
+    # SolutionReader::calc_interpolation (src/SolutionReader.cpp:167-190)
+    def calc_interpolation(self):
+        if not self.atoms_mapped_to_cells:
+            return self.calc_full_interpolation()
+        n = len(self.points)
+        if n:
+            x = self.points
+            self.ctx.check(self.ctx.L.fb_interpolate(
+                self.ctx.h, self.dim, self.rank, n, x.ctypes.data, x.ctypes.data + 8, x.ctypes.data + 16, 3,
+                _p(self.markers), _p(self.interpolation)))
+
+    # SolutionReader::interpolate(n, x, y, z) (src/SolutionReader.cpp:428-436)
+    def interpolate(self, xyz, ids=None):
+        self.reserve_points(xyz, ids)
+        self.calc_interpolation()
+
+    def update_positions(self, xyz):
+        self.points = _f(xyz).reshape(-1, 3)
+
+    # SolutionReader::interpolate_results (src/SolutionReader.cpp:405-421): SoA x,y,z as in Femocs_wrap.h:36
+    def interpolate_results(self, x, y, z, data_type):
+        x = _f(x); y = _f(y); z = _f(z)
+        n = len(x)
+        cells = np.zeros(n, np.int32); sol = np.zeros((n, 5))
+        self.ctx.check(self.ctx.L.fb_locate_interpolate(self.ctx.h, self.dim, self.rank, n, _p(x), _p(y), _p(z), 1,
+                                                        _p(cells), _p(sol)))
+        tmp = SolutionReader(self.interpolator)
+        tmp.points = np.stack([x, y, z], 1); tmp.ids = np.arange(n); tmp.markers = cells; tmp.interpolation = sol
+        n_comp = 3 if data_type.lower() in ("elfield", "vec") else 1
+        data = np.zeros(n * n_comp)
+        tmp.export_results(n, data_type.upper(), data)
+        return data, cells
+
+    # SolutionReader::export_results (src/SolutionReader.cpp:303-398): exact-case label appends,
+    # upper-case label overwrites; scatter by atom id
+    LABELS = {"elfield": 1, "elfield_norm": 2, "charge_density": 3, "potential": 4}
+
+    def export_results(self, n_points, data_type, data):
+        if self.size() == 0:
+            return 1
+        append = data_type in self.LABELS
+        kind = self.LABELS.get(data_type.lower())
+        if kind is None:
+            raise ValueError("SolutionReader does not contain " + data_type)
+        ids = np.asarray(self.ids)
+        ok = (ids >= 0) & (ids < n_points)
+        ids = ids[ok]; sol = self.interpolation[ok]
+        if kind == 1:
+            if not append:
+                data[:3 * n_points] = 0
+            view = data[:3 * n_points].reshape(n_points, 3)
+            if append:
+                np.add.at(view, ids, sol[:, :3])
+            else:
+                view[ids] = sol[:, :3]
+        else:
+            vals = {2: np.sqrt((sol[:, :3] ** 2).sum(1)), 3: sol[:, 3], 4: sol[:, 4]}[kind]
+            if not append:
+                data[:n_points] = 0
+                data[:n_points][ids] = vals
+            else:
+                np.add.at(data[:n_points], ids, vals)
+        return 0
+
+
+class FieldReader(SolutionReader):
+    """femocs::FieldReader: adds field norms and E_max (src/SolutionReader.cpp:473-499)."""
+
+    def __init__(self, interpolator):
+        super().__init__(interpolator)
+        self.field_norm = np.zeros(0); self.E_max = -1e100
+
+    def calc_interpolation(self):
+        super().calc_interpolation()
+        self.field_norm = np.sqrt((self.interpolation[:, :3] ** 2).sum(1))
+        self.E_max = float(self.field_norm.max()) if len(self.field_norm) else -1e100
+
+    def get_elfield(self, i):
+        return self.interpolation[i, :3]
+
+    def get_potential(self, i):
+        return self.interpolation[i, 4]
+
+
+class Pic:
+    """The hot-path slice of femocs::Pic<3>: particle cell update and field look-up."""
+
+    def __init__(self, interpolator):
+        self.ctx = interpolator.ctx
+
+    # Pic::update_point_cell for all particles (src/Pic.cpp:186-196)
+    def update_point_cells(self, xyz, cells):
+        xyz = _f(xyz); cells = _i(cells).copy()
+        self.ctx.check(self.ctx.L.fb_particle_cells(self.ctx.h, len(cells), _p(xyz), _p(cells)))
+        return cells
+
+    # field look-up of Pic::update_velocities (src/Pic.cpp:198-209)
+    def fields(self, xyz, cells):
+        xyz = _f(xyz); cells = _i(cells)
+        E = np.zeros((len(cells), 3))
+        self.ctx.check(self.ctx.L.fb_particle_field(self.ctx.h, len(cells), _p(xyz), _p(cells), _p(E)))
+        return E

@@ -1,0 +1,201 @@
+/*
+ * femocs_b200.h -- C ABI of libfemocs_b200.so, the B200 (sm_100a) implementation of the
+ * per-step electrostatic hot path of FEMOCS (veskem/femocs).
+ *
+ * This is the drop-in boundary: the reference's C++ classes femocs::PoissonSolver<3> /
+ * DealSolver<3>, Interpolator::extract_solution, the SolutionReader interpolation loops and
+ * the Pic<3> locate / field look-ups are re-implemented as thin forwards to the entry
+ * points below (see INTEGRATION.md and femocs_b200/cxx/ for the seam).  Every entry point
+ * cites the reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C: opaque handle, plain pointers and sizes; no C++/torch types cross this line;
+ *   - every function returning int returns 0 on success and a non-zero FB_ERR_* code on
+ *     failure (fb_last_error gives the text); no exception ever crosses this boundary,
+ *     matching the reference's "return code, never throw across the ABI" protocol
+ *     (include/Femocs_wrap.h:17, src/DealSolver.cpp:193-205,446-457);
+ *   - host pointers unless the name ends in _dev; device work is ordered on the context's
+ *     stream and every non-_dev call is synchronous at return;
+ *   - all floating point data is IEEE binary64, all indices are 32-bit int (deal.II's
+ *     types::global_dof_index is 32-bit in the reference build);
+ *   - mesh arrays are exactly what the reference's TetgenMesh hands out (SURVEY.md 8a'):
+ *     hexahedron h = 4*tet + k belongs to tetrahedron `tet` (src/Tethex.cpp:1041-1096),
+ *     quadrangle q = 3*tri + k to triangle `tri`; hex marker > 0 = vacuum
+ *     (src/TetgenMesh.cpp:353-375); tet marker 3 = TYPES.VACUUM.
+ */
+#ifndef FEMOCS_B200_H_
+#define FEMOCS_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fb_ctx fb_ctx;
+
+enum {
+    FB_OK = 0,
+    FB_ERR_CUDA = 1,       /* a CUDA runtime call or kernel failed                       */
+    FB_ERR_ARG = 2,        /* invalid argument / call order                              */
+    FB_ERR_MESH = 3,       /* mesh could not be imported (import_mesh would return false) */
+    FB_ERR_NO_DEVICE = 4   /* no usable CUDA device: there is NO CPU fallback            */
+};
+
+/* preconditioners of fb_poisson_solve */
+enum {
+    FB_PRECOND_JACOBI = 1,     /* diagonal scaling                                        */
+    FB_PRECOND_CHEBYSHEV = 2   /* Chebyshev polynomial of the Jacobi-scaled operator      */
+};
+
+/* ---------------------------------------------------------------------------------------
+ * life cycle -- replaces the construction of PoissonSolver<3>/Interpolator members in
+ * ProjectRunaway (src/ProjectRunaway.cpp:19-53).  `device` is the CUDA ordinal.
+ * Returns NULL when no CUDA device can be initialised (fb_create_error() has the reason).
+ * ------------------------------------------------------------------------------------- */
+fb_ctx*     fb_create(int device);
+void        fb_destroy(fb_ctx* ctx);
+const char* fb_last_error(const fb_ctx* ctx);
+const char* fb_create_error(void);
+/* number of kernels launched by this context since creation (bench.py "gpu_launches") */
+long        fb_kernel_launches(const fb_ctx* ctx);
+/* tunables: "cg_graph_iters" (iterations per CUDA-graph launch), "cheb_degree",
+ * "dof_order" (0 = deal.II first-touch numbering, 1 = Morton order of vertex coordinates) */
+int         fb_set_option(fb_ctx* ctx, const char* key, double value);
+
+/* ---------------------------------------------------------------------------------------
+ * bool DealSolver<3>::import_mesh(vector<Point<3>> vertices, vector<CellData<3>> cells)
+ *   src/DealSolver.cpp:191-209 (+ mark_boundary :460-518, PoissonSolver::mark_mesh
+ *   src/PoissonSolver.cpp:52-55), fed by TetgenNodes::export_dealii and
+ *   Hexahedra::export_vacuum (src/TetgenCells.cpp:179-184,673-686) at
+ *   src/ProjectRunaway.cpp:216.
+ * Takes the FULL femocs node and hexahedron lists; hexahedra with hex_marker > 0 form the
+ * solver mesh (solver cell id = rank among them, solver vertex id = rank among the nodes
+ * they touch: src/InterpolatorCells.cpp:38-66,1247-1266).
+ * ------------------------------------------------------------------------------------- */
+int fb_import_mesh(fb_ctx* ctx, const double* xyz, int n_nodes,
+                   const int* hex8, const int* hex_marker, int n_hex);
+
+/* sizes after import: out[0]=n_dofs, [1]=n_cells, [2]=nnz, [3]=n_vertices,
+ * [4]=n_boundary_faces, [5]=n_top_faces, [6]=n_dirichlet_dofs (after assemble) */
+int fb_get_sizes(const fb_ctx* ctx, long* out7);
+
+/* void PoissonSolver<3>::setup(double field, double potential)  src/PoissonSolver.cpp:162-167
+ * (+ DealSolver::setup_system src/DealSolver.cpp:368-387: zero matrix/rhs, solution = 0).
+ * anode_is_dirichlet mirrors Config::Field::anode_BC == "dirichlet" (src/Config.cpp:68). */
+int fb_poisson_setup(fb_ctx* ctx, double field, double potential, int anode_is_dirichlet);
+
+/* void PoissonSolver<3>::assemble(bool first_time)              src/PoissonSolver.cpp:170-210
+ *   first_time: Q1 stiffness assembly (assemble_parallel :213-263); otherwise the saved
+ *   pre-BC matrix is restored (:157-159).  Then copper Dirichlet (0 V), Neumann top faces
+ *   (DealSolver::assemble_rhs src/DealSolver.cpp:389-430) or Dirichlet anode, the
+ *   space-charge RHS of assemble_space_charge_fast (:299-319) when particles are given,
+ *   and apply_dirichlet (src/DealSolver.cpp:437-440).
+ *   particle_xyz: 3*n doubles, particle_cell: solver cell index per particle (as
+ *   SuperParticle::cell), charge_factor = q_over_eps0 * Wsp.  n_particles = 0 -> Laplace. */
+int fb_poisson_assemble(fb_ctx* ctx, int first_time,
+                        const double* particle_xyz, const int* particle_cell,
+                        long n_particles, double charge_factor);
+
+/* int PoissonSolver<3>::solve() -> DealSolver::solve_cg(n_cg, cg_tolerance, ssor_param)
+ *   src/PoissonSolver.h:54, src/DealSolver.cpp:442-458.
+ * Preconditioned CG on K phi = b, warm-started from the current solution, stopping on the
+ * ABSOLUTE l2 residual <= abs_tol like deal.II's SolverControl.  Returns through *n_iter the
+ * reference's convention: +iterations when converged, -iterations when max_iter was hit. */
+int fb_poisson_solve(fb_ctx* ctx, int max_iter, double abs_tol, int precond,
+                     int* n_iter, double* final_residual);
+
+/* void DealSolver::export_solution(vector<double>&)             src/DealSolver.cpp:269-278
+ * void PoissonSolver::export_charge_dens(vector<double>&)       src/PoissonSolver.cpp:141-149
+ * both in solver-vertex order, n_vertices values. */
+int fb_export_solution(fb_ctx* ctx, double* phi_vertex);
+int fb_export_charge_dens(fb_ctx* ctx, double* rho_vertex);
+/* void DealSolver::import_solution(const vector<double>*)       src/DealSolver.cpp:303-315 */
+int fb_import_solution(fb_ctx* ctx, const double* phi_vertex);
+
+/* bool DealSolver::check_limits(lo, hi) + stat.sol_min/sol_max  src/DealSolver.cpp:157-167 */
+int fb_check_limits(fb_ctx* ctx, double lo, double hi, int* out_of_limits,
+                    double* sol_min, double* sol_max);
+
+/* double DealSolver::get_cell_vol(i) / int get_n_cells()        src/DealSolver.cpp:169-173 */
+int fb_get_cell_volumes(fb_ctx* ctx, double* vol_cells);
+
+/* test / integration hooks: the assembled system in DoF numbering (host copies).
+ * Any pointer may be NULL. */
+int fb_get_system(fb_ctx* ctx, int* rowptr, int* col, double* val, double* val_save,
+                  double* rhs, double* sol, int* vertex2dof, int* vertex2node);
+
+/* ---------------------------------------------------------------------------------------
+ * void Interpolator::initialize(const TetgenMesh*, double empty_val, int search_region)
+ *   src/Interpolator.cpp:28-77 with search_region = TYPES.VACUUM (src/ProjectRunaway.cpp:435)
+ *   and the precompute() of LinearTetrahedra / LinearHexahedra / LinearTriangles /
+ *   LinearQuadrangles / Quadratic* (src/InterpolatorCells.cpp:523-629,1205-1267,1585-1637,
+ *   1151-1173,1873-1895).  Must follow fb_import_mesh (uses its nodes and hexahedra).
+ *   voro_off/voro_list: CSR of TetgenMesh::calc_pseudo_3D_vorocells(vacuum=true)
+ *   (src/TetgenMesh.cpp:819-837), n_voro rows; tet_edgemax = tets.stat.edgemax.
+ * ------------------------------------------------------------------------------------- */
+int fb_interp_initialize(fb_ctx* ctx, const int* node_marker,
+                         const int* tet4, const int* tet_nbr4, const int* tet_marker, int n_tet,
+                         const int* tri3, const int* tri2tet, const double* tri_norm3, int n_tri,
+                         const int* quad4, const int* quad2hex, int n_quad,
+                         double tet_edgemax,
+                         const int* voro_off, const int* voro_list, int n_voro);
+
+/* void Interpolator::extract_solution(PoissonSolver<3>&, bool smoothen)
+ *   src/Interpolator.cpp:172-190 (store_solution :103-123, store_elfield :125-140,
+ *   average_nodal_fields :142-170).  The nodal Solution array stays on the device. */
+int fb_extract_solution(fb_ctx* ctx, int smoothen);
+
+/* InterpolatorNodes::solutions access (vector<Solution>, 5 doubles per femocs node:
+ * Ex, Ey, Ez, scalar1 (charge density), scalar2 (potential); include/Primitives.h:507-522) */
+int fb_get_nodal_solutions(fb_ctx* ctx, double* sol5);
+int fb_set_nodal_solutions(fb_ctx* ctx, const double* sol5);
+
+/* void SolutionReader::calc_full_interpolation()                src/SolutionReader.cpp:136-165
+ *   the chained-guess loop  cell = locate_interpolate(i, cell)  (:43-65,
+ *   src/InterpolatorCells.cpp:442-445,269-307) for dim in {2,3}, rank in {1,2,3}:
+ *     dim 2: lintri / quadtri / linquad, dim 3: lintet / quadtet / linhex.
+ *   Points are x[i*stride], y[i*stride], z[i*stride] (stride 1 = the three arrays of
+ *   femocs_interpolate_elfield, include/Femocs_wrap.h:36; stride 3 with y=x+1, z=x+2 = the
+ *   Atom/Point3 layout).  cells_out[i] is what the reference stores in atom.marker
+ *   (negative = outside, nearest cell), sol5_out the interpolated Solution.
+ *   Cell indices are bit-exact with the reference's sequential loop. */
+int fb_locate_interpolate(fb_ctx* ctx, int dim, int rank, long n,
+                          const double* x, const double* y, const double* z, int stride,
+                          int* cells_out, double* sol5_out);
+
+/* void SolutionReader::calc_interpolation() with atoms already mapped to cells
+ *   src/SolutionReader.cpp:167-190, :91-112 (interp_solution(i) with cell = abs(marker)) */
+int fb_interpolate(fb_ctx* ctx, int dim, int rank, long n,
+                   const double* x, const double* y, const double* z, int stride,
+                   const int* cells, double* sol5_out);
+
+/* int Pic<3>::update_point_cell(const SuperParticle&)           src/Pic.cpp:186-196
+ *   cell_inout: solver cell index guess in, located solver cell (or -1) out. */
+int fb_particle_cells(fb_ctx* ctx, long n, const double* xyz, int* cell_inout);
+
+/* field look-up of Pic<3>::update_velocities                    src/Pic.cpp:198-209, :38-39
+ *   E3[i] = linhex.interp_gradient(pos_i, deal2femocs(cell_i))
+ *   (src/InterpolatorCells.cpp:410-423,1363-1416) */
+int fb_particle_field(fb_ctx* ctx, long n, const double* xyz, const int* cells, double* E3);
+
+/* ---------------------------------------------------------------------------------------
+ * device-resident variants (inputs/outputs already in HBM; asynchronous on the context
+ * stream until fb_synchronize).  Used by the benchmark's "value" leg and by callers that
+ * keep atoms/particles on the GPU.
+ * ------------------------------------------------------------------------------------- */
+int fb_locate_interpolate_dev(fb_ctx* ctx, int dim, int rank, long n,
+                              const double* xyz_dev, int* cells_dev, double* sol5_dev);
+int fb_particle_cells_dev(fb_ctx* ctx, long n, const double* xyz_dev, int* cell_inout_dev);
+int fb_particle_field_dev(fb_ctx* ctx, long n, const double* xyz_dev, const int* cells_dev,
+                          double* E3_dev);
+int fb_poisson_assemble_dev(fb_ctx* ctx, int first_time, const double* particle_xyz_dev,
+                            const int* particle_cell_dev, long n_particles, double charge_factor);
+int fb_synchronize(fb_ctx* ctx);
+
+/* timing hooks for the roofline report: device time (ms, CUDA events on the context's
+ * stream) of the last fb_poisson_solve and its iteration count */
+int fb_last_solve_stats(const fb_ctx* ctx, double* solve_ms, int* iterations, long* spmv_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMOCS_B200_H_ */
