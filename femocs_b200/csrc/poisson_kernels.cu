@@ -211,12 +211,17 @@ __global__ void __launch_bounds__(256) k_apply_bc_matrix(int n, const int* __res
                                                          const int* __restrict__ flag, const double* __restrict__ bcval,
                                                          double* __restrict__ lift, double* __restrict__ dinv,
                                                          int* __restrict__ diagpos) {
+    // the row loop is warp-uniform (all 32 lanes take the same number of trips) so that the
+    // full-mask shuffles below are always executed by the whole warp
     const int lane = threadIdx.x % LANES;
-    const long row0 = ((long) blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const long gtid = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long warp_row0 = (gtid / 32) * (32 / LANES);
     const long stride = (long) gridDim.x * blockDim.x / LANES;
-    for (long r = row0; r < n; r += stride) {
-        const int lo = rowptr[r], hi = rowptr[r + 1];
-        const bool rc = flag[r] != 0;
+    for (long rb = warp_row0; rb < n; rb += stride) {
+        const long r = rb + (threadIdx.x % 32) / LANES;
+        const bool valid = r < n;
+        const int lo = valid ? rowptr[r] : 0, hi = valid ? rowptr[r + 1] : 0;
+        const bool rc = valid && flag[r] != 0;
         double l = 0;
         for (int k = lo + lane; k < hi; k += LANES) {
             const int c = col[k];
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(256) k_apply_bc_matrix(int n, const int* __res
         }
 #pragma unroll
         for (int o = LANES / 2; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o, LANES);
-        if (lane == 0) lift[r] = l;
+        if (lane == 0 && valid) lift[r] = l;
     }
 }
 
@@ -260,16 +265,19 @@ __global__ void __launch_bounds__(256) k_spmv_dot(int n, const int* __restrict__
                                                   CgScalars* __restrict__ cgs, double* __restrict__ alpha_out) {
     if (!INIT && cgs->done) return;
     const int lane = threadIdx.x % LANES;
-    const long row0 = ((long) blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const long gtid = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long warp_row0 = (gtid / 32) * (32 / LANES);       // warp-uniform trip count (full-mask shuffles)
     const long stride = (long) gridDim.x * blockDim.x / LANES;
     double acc[2] = {0, 0};
-    for (long r = row0; r < n; r += stride) {
-        const int lo = __ldg(&rowptr[r]), hi = __ldg(&rowptr[r + 1]);
+    for (long rb = warp_row0; rb < n; rb += stride) {
+        const long r = rb + (threadIdx.x % 32) / LANES;
+        const bool valid = r < n;
+        const int lo = valid ? __ldg(&rowptr[r]) : 0, hi = valid ? __ldg(&rowptr[r + 1]) : 0;
         double s = 0;
         for (int k = lo + lane; k < hi; k += LANES) s += __ldg(&val[k]) * xin[__ldg(&col[k])];
 #pragma unroll
         for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, LANES);
-        if (lane == 0) {
+        if (lane == 0 && valid) {
             if (INIT) {                      // g = A x - b ; accumulate g.(Dinv g) and g.g
                 const double g = s - rhs[r];
                 out[r] = g;
