@@ -63,6 +63,7 @@ void fb_destroy(fb_ctx* c) {
     drop_graph(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     if (c->stream) { cudaStreamSynchronize(c->stream); }
     cudaStream_t s = c->stream;
     delete c;                       // frees device buffers
@@ -77,11 +78,13 @@ int fb_set_option(fb_ctx* c, const char* key, double value) {
     if (k == "cg_graph_iters") { c->cg_graph_iters = std::max(1, (int) value); drop_graph(c); }
     else if (k == "cheb_degree") c->cheb_degree = (int) value;
     else if (k == "dof_order") c->dof_order = (int) value;
+    else if (k == "cg_profile") c->cg_profile = std::max(0, std::min(4096, (int) value));
     else return c->fail(FB_ERR_ARG, "unknown option %s", key);
     return FB_OK;
 }
 
 int fb_synchronize(fb_ctx* c) { return sync_check(c, "fb_synchronize"); }
+void* fb_get_stream(fb_ctx* c) { return (void*) c->stream; }
 
 // ------------------------------------------------------------------------------------------
 int fb_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {
@@ -166,7 +169,6 @@ static int assemble_impl(fb_ctx* c, int first_time, const double* d_pxyz, const 
     FB_CUDA(c, cudaMemsetAsync(c->d_rhs.p, 0, n * sizeof(double), s));
     if (!c->anode_dirichlet) fb::launch_neumann(c);
     if (n_parts > 0) {
-        FB_REQUIRE(c, c->interp_ok, "fb_poisson_assemble: space charge needs fb_interp_initialize (LinearHexahedra tables)");
         fb::launch_space_charge(c, n_parts, d_pxyz, d_pcell, charge_factor);
     }
     fb::launch_apply_bc_rhs(c);
@@ -222,8 +224,37 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
         cudaGraphDestroy(graph);
         c->cg_graph_n = c->cg_graph_iters; c->cg_graph_precond = lanes;
     }
+    // optional profile: the first cg_profile iterations run un-graphed, each bracketed by CUDA
+    // events on this stream (SpMV+dot | vector updates), for the live roofline figures of bench.py
+    int n_prof = 0;
+    if (c->cg_profile > 0) {
+        while ((int) c->prof_ev.size() < 3 * c->cg_profile) {
+            cudaEvent_t e; FB_CUDA(c, cudaEventCreate(&e)); c->prof_ev.push_back(e);
+        }
+        n_prof = std::min(c->cg_profile, std::max(0, max_iter));
+        for (int i = 0; i < n_prof; ++i) {
+            FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i], s));
+            fb::launch_cg_spmv(c, lanes);
+            FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i + 1], s));
+            fb::launch_cg_vectors(c);
+            FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i + 2], s));
+        }
+        spmv += n_prof;
+    }
     FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
     FB_CUDA(c, cudaStreamSynchronize(s));
+    c->prof_samples = 0; c->prof_spmv_ms = c->prof_vec_ms = 0;
+    if (n_prof > 0) {
+        const int live = std::min(n_prof, h->it);      // launches after convergence are no-ops: not sampled
+        for (int i = 0; i < live; ++i) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, c->prof_ev[3 * i], c->prof_ev[3 * i + 1]);
+            cudaEventElapsedTime(&b, c->prof_ev[3 * i + 1], c->prof_ev[3 * i + 2]);
+            c->prof_spmv_ms += a; c->prof_vec_ms += b;
+        }
+        c->prof_samples = live;
+        if (live > 0) { c->prof_spmv_ms /= live; c->prof_vec_ms /= live; }
+    }
     while (!h->done) {
         FB_CUDA(c, cudaGraphLaunch(c->cg_graph, s));
         c->launches += 3L * c->cg_graph_n;
@@ -242,6 +273,11 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
 
 int fb_last_solve_stats(const fb_ctx* c, double* ms, int* it, long* spmv) {
     if (ms) *ms = c->last_solve_ms; if (it) *it = c->last_iters; if (spmv) *spmv = c->last_spmv;
+    return FB_OK;
+}
+
+int fb_last_solve_profile(const fb_ctx* c, double* spmv_ms, double* vec_ms, int* n_samples) {
+    if (spmv_ms) *spmv_ms = c->prof_spmv_ms; if (vec_ms) *vec_ms = c->prof_vec_ms; if (n_samples) *n_samples = c->prof_samples;
     return FB_OK;
 }
 

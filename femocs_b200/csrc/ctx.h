@@ -82,6 +82,7 @@ struct fb_ctx {
     int cg_graph_iters = 32;
     int cheb_degree = 2;
     int dof_order = 0;
+    int cg_profile = 0;                      // iterations per solve bracketed with CUDA events (0 = off)
 
     // ---- host copies of the mesh (femocs numbering) ----
     int n_nodes = 0, n_hex = 0;
@@ -120,6 +121,8 @@ struct fb_ctx {
     double last_solve_ms = 0; int last_iters = 0; long last_spmv = 0;
     double cheb_lmax = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> prof_ev;        // 3 events per profiled iteration
+    double prof_spmv_ms = 0, prof_vec_ms = 0; int prof_samples = 0;
 
     // ---- interpolator ----
     bool interp_ok = false;

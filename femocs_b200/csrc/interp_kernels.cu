@@ -512,16 +512,41 @@ __global__ void __launch_bounds__(128) k_particle_field(Tables T, long n, const 
     E3[3 * i] = E.x; E3[3 * i + 1] = E.y; E3[3 * i + 2] = E.z;
 }
 
-// PoissonSolver<3>::assemble_space_charge_fast (PoissonSolver.cpp:299-319): 8 scatter-adds per particle
+// PoissonSolver<3>::assemble_space_charge_fast (PoissonSolver.cpp:299-319): 8 scatter-adds per particle.
+// FROM_VERTS = false reads the LinearHexahedra coefficient table of the interpolator (192 B/hex);
+// FROM_VERTS = true rebuilds f0..f7 (InterpolatorCells.cpp:1205-1245) from the 8 cell vertices, for
+// solver-only meshes that have no tetrahedral tables (the refined benchmark meshes).
+template <bool FROM_VERTS>
 __global__ void __launch_bounds__(128) k_space_charge(const HexRec* __restrict__ hexrec, long n, const double* __restrict__ pts,
                                                       const int* __restrict__ pcell, int n_cells, const int* __restrict__ cell2hex,
-                                                      const int* __restrict__ cells_dof, double charge_factor, double* __restrict__ rhs) {
+                                                      const int* __restrict__ cells_dof, const double* __restrict__ vxyz,
+                                                      double charge_factor, double* __restrict__ rhs) {
     const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int cell = pcell[i];
     if (cell < 0 || cell >= n_cells) return;
     double sf[8];
-    hex_sf(hexrec[cell2hex[cell]], ldp(pts, i), sf);
+    if (FROM_VERTS) {
+        const int lex[8] = {0, 1, 5, 4, 2, 3, 7, 6};   // femocs/UCD local vertex k sits at lexicographic position lex[k]
+        P3 x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = ldp(vxyz, cells_dof[8 * (long) cell + lex[k]]);
+        HexRec H;
+        const P3 f0 = (x[0] + x[1] + x[2] + x[3] + x[4] + x[5] + x[6] + x[7]) * 0.125;
+        const P3 f1 = ((x[0] * -1.0) + x[1] + x[2] - x[3] - x[4] + x[5] + x[6] - x[7]) * 0.125;
+        const P3 f2 = ((x[0] * -1.0) - x[1] + x[2] + x[3] - x[4] - x[5] + x[6] + x[7]) * 0.125;
+        const P3 f3 = ((x[0] * -1.0) - x[1] - x[2] - x[3] + x[4] + x[5] + x[6] + x[7]) * 0.125;
+        const P3 f4 = (x[0] - x[1] + x[2] - x[3] + x[4] - x[5] + x[6] - x[7]) * 0.125;
+        const P3 f5 = (x[0] - x[1] - x[2] + x[3] - x[4] + x[5] + x[6] - x[7]) * 0.125;
+        const P3 f6 = (x[0] + x[1] - x[2] - x[3] - x[4] - x[5] + x[6] + x[7]) * 0.125;
+        const P3 f7 = ((x[0] * -1.0) + x[1] - x[2] + x[3] + x[4] - x[5] + x[6] - x[7]) * 0.125;
+        const P3 f[8] = {f0, f1, f2, f3, f4, f5, f6, f7};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { H.f[k][0] = f[k].x; H.f[k][1] = f[k].y; H.f[k][2] = f[k].z; }
+        hex_sf(H, ldp(pts, i), sf);
+    } else {
+        hex_sf(hexrec[cell2hex[cell]], ldp(pts, i), sf);
+    }
     const int perm[8] = {0, 1, 4, 5, 3, 2, 7, 6};       // shape_funs_dealii (:1355-1358)
 #pragma unroll
     for (int k = 0; k < 8; ++k) atomicAdd(&rhs[cells_dof[8 * (long) cell + k]], sf[perm[k]] * charge_factor);
@@ -618,8 +643,13 @@ void launch_particle_field(fb_ctx* c, long n, const double* d_pts, const int* d_
 
 void launch_space_charge(fb_ctx* c, long n, const double* d_pts, const int* d_pcell, double charge_factor) {
     if (n <= 0) return;
-    k_space_charge<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(c->d_hex.p, n, d_pts, d_pcell, c->n_cells, c->d_cell2hex.p,
-                                                                     c->d_cells.p, charge_factor, c->d_rhs.p);
+    const unsigned g = (unsigned) ((n + 127) / 128);
+    if (c->interp_ok)
+        k_space_charge<false><<<g, 128, 0, c->stream>>>(c->d_hex.p, n, d_pts, d_pcell, c->n_cells, c->d_cell2hex.p, c->d_cells.p,
+                                                         c->d_vxyz.p, charge_factor, c->d_rhs.p);
+    else
+        k_space_charge<true><<<g, 128, 0, c->stream>>>(nullptr, n, d_pts, d_pcell, c->n_cells, c->d_cell2hex.p, c->d_cells.p,
+                                                        c->d_vxyz.p, charge_factor, c->d_rhs.p);
     c->launches++;
 }
 

@@ -15,6 +15,8 @@ void launch_apply_bc_matrix(fb_ctx* c);
 void launch_apply_bc_rhs(fb_ctx* c);
 void launch_cg_init(fb_ctx* c, int lanes);
 void launch_cg_iteration(fb_ctx* c, int lanes);
+void launch_cg_spmv(fb_ctx* c, int lanes);
+void launch_cg_vectors(fb_ctx* c);
 void launch_minmax(fb_ctx* c);
 void launch_gather(fb_ctx* c, int n, const int* idx, const double* src, double* dst);
 void launch_scatter(fb_ctx* c, int n, const int* idx, const double* src, double* dst);

@@ -451,14 +451,22 @@ void launch_cg_init(fb_ctx* c, int lanes) {
     c->launches++;
 }
 
-void launch_cg_iteration(fb_ctx* c, int lanes) {
-    unsigned* counter = (unsigned*) (c->d_partial.p + c->d_partial.n - 8);
+void launch_cg_spmv(fb_ctx* c, int lanes) {       // h = A d, alpha = gh / (d.h)
     spmv_dispatch<false>(c, lanes, c->d_d.p, c->d_h.p, alpha_ptr(c));
+}
+
+void launch_cg_vectors(fb_ctx* c) {               // x, g update + dots + convergence test, then new direction
+    unsigned* counter = (unsigned*) (c->d_partial.p + c->d_partial.n - 8);
     const int g = grid_for(c, c->n_dofs, 256);
     k_update<<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_d.p, c->d_h.p, c->d_dinv.p, c->d_x.p, c->d_g.p, c->d_partial.p, counter,
                                        c->d_cg.p, alpha_ptr(c), beta_ptr(c));
     k_direction<false><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_g.p, c->d_dinv.p, c->d_d.p, c->d_cg.p, beta_ptr(c));
     c->launches += 2;
+}
+
+void launch_cg_iteration(fb_ctx* c, int lanes) {
+    launch_cg_spmv(c, lanes);
+    launch_cg_vectors(c);
 }
 
 void launch_minmax(fb_ctx* c) {

@@ -47,6 +47,8 @@ SIGNATURES = {
     "fb_poisson_assemble_dev": (C.c_int, [vp, C.c_int, vp, vp, C.c_long, C.c_double]),
     "fb_synchronize": (C.c_int, [vp]),
     "fb_last_solve_stats": (C.c_int, [vp, c_double_p, c_int_p, c_long_p]),
+    "fb_last_solve_profile": (C.c_int, [vp, c_double_p, c_double_p, c_int_p]),
+    "fb_get_stream": (vp, [vp]),
 }
 
 _lib = None

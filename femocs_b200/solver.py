@@ -78,6 +78,11 @@ class Context:
     def synchronize(self):
         self.check(self.L.fb_synchronize(self.h))
 
+    @property
+    def stream(self):
+        """cudaStream_t of the context (integer address)."""
+        return int(self.L.fb_get_stream(self.h))
+
 
 @dataclass
 class FieldConfig:
@@ -140,6 +145,11 @@ class PoissonSolver:
         else:
             self.ctx.check(self.ctx.L.fb_poisson_assemble(self.ctx.h, int(first_time), None, None, 0, 0.0))
 
+    # same, with the particle arrays already in HBM (raw device addresses; asynchronous on the context stream)
+    def assemble_dev(self, first_time, xyz_dev_ptr, cells_dev_ptr, n_particles, charge_factor):
+        self.ctx.check(self.ctx.L.fb_poisson_assemble_dev(self.ctx.h, int(first_time), xyz_dev_ptr, cells_dev_ptr,
+                                                          int(n_particles), float(charge_factor)))
+
     # PoissonSolver::solve (include/PoissonSolver.h:54): +#CG on success, -#CG when n_cg was hit
     def solve(self, n_cg=None, cg_tolerance=None):
         it = C.c_int(0); res = C.c_double(0)
@@ -155,6 +165,13 @@ class PoissonSolver:
         self.ctx.L.fb_last_solve_stats(self.ctx.h, C.byref(ms), C.byref(it), C.byref(sp))
         return ms.value, it.value, sp.value
 
+    # (avg ms of the SpMV+dot kernel, avg ms of the vector kernels, samples) of the last solve; needs
+    # ctx.set_option("cg_profile", k)
+    def solve_profile(self):
+        a = C.c_double(0); b = C.c_double(0); n = C.c_int(0)
+        self.ctx.L.fb_last_solve_profile(self.ctx.h, C.byref(a), C.byref(b), C.byref(n))
+        return a.value, b.value, n.value
+
     # DealSolver::check_limits (src/DealSolver.cpp:157-167)
     def check_limits(self, low_limit, high_limit):
         bad = C.c_int(0); a = C.c_double(0); b = C.c_double(0)
@@ -163,8 +180,10 @@ class PoissonSolver:
         return bool(bad.value)
 
     # DealSolver::export_solution / PoissonSolver::export_charge_dens (vertex order)
-    def export_solution(self):
-        out = np.zeros(self.n_vertices)
+    def export_solution(self, out=None):
+        if out is None:
+            out = np.zeros(self.n_vertices)
+        assert out.dtype == np.float64 and out.size >= self.n_vertices
         self.ctx.check(self.ctx.L.fb_export_solution(self.ctx.h, _p(out)))
         return out
 

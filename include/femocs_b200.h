@@ -58,7 +58,8 @@ const char* fb_create_error(void);
 /* number of kernels launched by this context since creation (bench.py "gpu_launches") */
 long        fb_kernel_launches(const fb_ctx* ctx);
 /* tunables: "cg_graph_iters" (iterations per CUDA-graph launch), "cheb_degree",
- * "dof_order" (0 = deal.II first-touch numbering, 1 = Morton order of vertex coordinates) */
+ * "dof_order" (0 = deal.II first-touch numbering, 1 = Morton order of vertex coordinates),
+ * "cg_profile" (see fb_last_solve_profile) */
 int         fb_set_option(fb_ctx* ctx, const char* key, double value);
 
 /* ---------------------------------------------------------------------------------------
@@ -194,6 +195,12 @@ int fb_synchronize(fb_ctx* ctx);
 /* timing hooks for the roofline report: device time (ms, CUDA events on the context's
  * stream) of the last fb_poisson_solve and its iteration count */
 int fb_last_solve_stats(const fb_ctx* ctx, double* solve_ms, int* iterations, long* spmv_launches);
+/* with option "cg_profile" = k > 0 the first k iterations of every solve are bracketed by CUDA
+ * events on the context's stream: average device time (ms) of the SpMV+dot kernel and of the
+ * vector-update kernels over the sampled (live) iterations */
+int fb_last_solve_profile(const fb_ctx* ctx, double* spmv_ms_avg, double* vector_ms_avg, int* n_samples);
+/* the context's cudaStream_t (for callers that record their own events around fb_*_dev calls) */
+void* fb_get_stream(fb_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -469,7 +469,10 @@ void assemble(Oracle& o, int first_time, const double* pxyz, const int* pcell, l
     apply_dirichlet(o);
 }
 
+// SparseMatrix::vmult -- deal.II runs it TBB-parallel over row ranges; here OpenMP over rows
+// (row sums keep their serial order, so the result does not depend on the thread count)
 void spmv(const Oracle& o, const std::vector<double>& x, std::vector<double>& y) {
+#pragma omp parallel for schedule(static)
     for (int r = 0; r < o.n_dofs; ++r) {
         double s = 0;
         for (int k = o.rowptr[r]; k < o.rowptr[r + 1]; ++k) s += o.val[k] * x[o.col[k]];
