@@ -78,6 +78,8 @@ int fb_set_option(fb_ctx* c, const char* key, double value) {
     if (k == "cg_graph_iters") { c->cg_graph_iters = std::max(1, (int) value); drop_graph(c); }
     else if (k == "cheb_degree") c->cheb_degree = (int) value;
     else if (k == "dof_order") c->dof_order = (int) value;
+    else if (k == "spmv_kernel") { c->spmv_kernel = (int) value; drop_graph(c); }
+    else if (k == "cg_persistent") c->cg_persistent = (int) value;
     else if (k == "cg_profile") c->cg_profile = std::max(0, std::min(4096, (int) value));
     else return c->fail(FB_ERR_ARG, "unknown option %s", key);
     return FB_OK;
@@ -110,6 +112,8 @@ int fb_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, c
     FB_CUDA(c, c->d_cells.upload(c->cells_dof, s));
     FB_CUDA(c, c->d_rowptr.upload(c->rowptr, s));
     FB_CUDA(c, c->d_col.upload(c->col, s));
+    c->n_rowblk = 0; c->rowblk_chunk = 0; c->win_cap = 0;
+    c->pers_grid = 0;
     FB_CUDA(c, c->d_topfaces.upload(top, s));
     FB_CUDA(c, c->d_vertex2dof.upload(c->vertex2dof, s));
     FB_CUDA(c, c->d_cell2hex.upload(c->cell2hex, s));
@@ -201,66 +205,97 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
     FB_REQUIRE(c, precond == FB_PRECOND_JACOBI, "fb_poisson_solve: only FB_PRECOND_JACOBI is implemented in this build");
     cudaSetDevice(c->device);
     cudaStream_t s = c->stream;
-    const int lanes = fb::choose_lanes(c);
     fb::CgScalars init; memset(&init, 0, sizeof init);
     init.tol2 = abs_tol * abs_tol; init.max_iter = max_iter;
     fb::CgScalars* h = (fb::CgScalars*) c->pin_out.p;
     *h = init;
     FB_CUDA(c, cudaEventRecord(c->ev0, s));
     FB_CUDA(c, cudaMemcpyAsync(c->d_cg.p, h, sizeof(fb::CgScalars), cudaMemcpyHostToDevice, s));
-    fb::launch_cg_init(c, lanes);
     long spmv = 1;
-    // CUDA graph of cg_graph_iters iterations; kernels become no-ops once cgs->done is set
-    if (!c->cg_graph || c->cg_graph_n != c->cg_graph_iters || c->cg_graph_precond != lanes) {
-        drop_graph(c);
-        cudaGraph_t graph;
-        const long before = c->launches;
-        FB_CUDA(c, cudaStreamSynchronize(s));
-        FB_CUDA(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        for (int i = 0; i < c->cg_graph_iters; ++i) fb::launch_cg_iteration(c, lanes);
-        FB_CUDA(c, cudaStreamEndCapture(s, &graph));
-        c->launches = before;     // captured, not launched
-        FB_CUDA(c, cudaGraphInstantiate(&c->cg_graph, graph, 0));
-        cudaGraphDestroy(graph);
-        c->cg_graph_n = c->cg_graph_iters; c->cg_graph_precond = lanes;
-    }
-    // optional profile: the first cg_profile iterations run un-graphed, each bracketed by CUDA
-    // events on this stream (SpMV+dot | vector updates), for the live roofline figures of bench.py
-    int n_prof = 0;
-    if (c->cg_profile > 0) {
-        while ((int) c->prof_ev.size() < 3 * c->cg_profile) {
-            cudaEvent_t e; FB_CUDA(c, cudaEventCreate(&e)); c->prof_ev.push_back(e);
-        }
-        n_prof = std::min(c->cg_profile, std::max(0, max_iter));
-        for (int i = 0; i < n_prof; ++i) {
-            FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i], s));
-            fb::launch_cg_spmv(c, lanes);
-            FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i + 1], s));
-            fb::launch_cg_vectors(c);
-            FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i + 2], s));
-        }
-        spmv += n_prof;
-    }
-    FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
-    FB_CUDA(c, cudaStreamSynchronize(s));
     c->prof_samples = 0; c->prof_spmv_ms = c->prof_vec_ms = 0;
-    if (n_prof > 0) {
-        const int live = std::min(n_prof, h->it);      // launches after convergence are no-ops: not sampled
-        for (int i = 0; i < live; ++i) {
-            float a = 0, b = 0;
-            cudaEventElapsedTime(&a, c->prof_ev[3 * i], c->prof_ev[3 * i + 1]);
-            cudaEventElapsedTime(&b, c->prof_ev[3 * i + 1], c->prof_ev[3 * i + 2]);
-            c->prof_spmv_ms += a; c->prof_vec_ms += b;
-        }
-        c->prof_samples = live;
-        if (live > 0) { c->prof_spmv_ms /= live; c->prof_vec_ms /= live; }
-    }
-    while (!h->done) {
-        FB_CUDA(c, cudaGraphLaunch(c->cg_graph, s));
-        c->launches += 3L * c->cg_graph_n;
-        spmv += c->cg_graph_n;
+    const bool persistent = c->cg_profile == 0 && fb::persistent_eligible(c);
+    if (persistent) {
+        // native meshes: the whole solve is ONE cooperative launch (matrix slice resident in shared memory)
+        FB_CUDA(c, fb::launch_cg_persistent(c));
         FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
         FB_CUDA(c, cudaStreamSynchronize(s));
+        spmv += h->it;
+    } else {
+        int lanes = fb::choose_lanes(c);
+        if (lanes == 0 || lanes >= 100) {          // streaming SpMV: (re)build its row blocks for the chosen variant
+            int chunk, maxrows;
+            fb::stream_block_shape(lanes, chunk, maxrows);
+            if (c->rowblk_chunk != chunk || c->rowblk_maxrows != maxrows || c->n_rowblk == 0) {
+                drop_graph(c);
+                c->win_cap = 0;
+                if (fb_host_row_blocks(c, chunk, maxrows)) FB_CUDA(c, c->d_rowblk.upload(c->rowblk, s));
+                else lanes = 32;                   // a row longer than the chunk: per-row kernel
+            }
+            if (lanes >= 200 && c->win_cap == 0) { // windowed variant: column windows + 16-bit window positions
+                if (fb_host_col_windows(c, 6144)) {
+                    c->win_cap = (c->win_max + 15) & ~15;
+                    FB_CUDA(c, c->d_col16.upload(c->col16, s));
+                    FB_CUDA(c, c->d_win_off.upload(c->win_off, s));
+                    FB_CUDA(c, c->d_win_list.upload(c->win_list, s));
+                    FB_CUDA(c, cudaStreamSynchronize(s));
+                    std::vector<unsigned short>().swap(c->col16);      // host copy no longer needed
+                } else {
+                    lanes = (lanes == 201 || lanes == 204) ? 103 : (lanes == 202 ? 101 : (lanes == 203 ? 100 : 0));   // same block shape, plain gather
+                }
+            }
+        }
+        fb::launch_cg_init(c, lanes);
+        // CUDA graph of cg_graph_iters iterations; kernels become no-ops once cgs->done is set
+        if (!c->cg_graph || c->cg_graph_n != c->cg_graph_iters || c->cg_graph_precond != lanes) {
+            drop_graph(c);
+            cudaGraph_t graph;
+            const long before = c->launches;
+            FB_CUDA(c, cudaStreamSynchronize(s));
+            FB_CUDA(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            for (int i = 0; i < c->cg_graph_iters; ++i) fb::launch_cg_iteration(c, lanes);
+            FB_CUDA(c, cudaStreamEndCapture(s, &graph));
+            c->launches = before;     // captured, not launched
+            FB_CUDA(c, cudaGraphInstantiate(&c->cg_graph, graph, 0));
+            cudaGraphDestroy(graph);
+            c->cg_graph_n = c->cg_graph_iters; c->cg_graph_precond = lanes;
+        }
+        // optional profile: the first cg_profile iterations run un-graphed, each bracketed by CUDA
+        // events on this stream (SpMV+dot | vector updates), for the live roofline figures of bench.py
+        int n_prof = 0;
+        if (c->cg_profile > 0) {
+            while ((int) c->prof_ev.size() < 3 * c->cg_profile) {
+                cudaEvent_t e; FB_CUDA(c, cudaEventCreate(&e)); c->prof_ev.push_back(e);
+            }
+            n_prof = std::min(c->cg_profile, std::max(0, max_iter));
+            for (int i = 0; i < n_prof; ++i) {
+                FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i], s));
+                fb::launch_cg_spmv(c, lanes);
+                FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i + 1], s));
+                fb::launch_cg_vectors(c);
+                FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i + 2], s));
+            }
+            spmv += n_prof;
+        }
+        FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
+        FB_CUDA(c, cudaStreamSynchronize(s));
+        if (n_prof > 0) {
+            const int live = std::min(n_prof, h->it);      // launches after convergence are no-ops: not sampled
+            for (int i = 0; i < live; ++i) {
+                float a = 0, b = 0;
+                cudaEventElapsedTime(&a, c->prof_ev[3 * i], c->prof_ev[3 * i + 1]);
+                cudaEventElapsedTime(&b, c->prof_ev[3 * i + 1], c->prof_ev[3 * i + 2]);
+                c->prof_spmv_ms += a; c->prof_vec_ms += b;
+            }
+            c->prof_samples = live;
+            if (live > 0) { c->prof_spmv_ms /= live; c->prof_vec_ms /= live; }
+        }
+        while (!h->done) {
+            FB_CUDA(c, cudaGraphLaunch(c->cg_graph, s));
+            c->launches += 3L * c->cg_graph_n;
+            spmv += c->cg_graph_n;
+            FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
+            FB_CUDA(c, cudaStreamSynchronize(s));
+        }
     }
     FB_CUDA(c, cudaEventRecord(c->ev1, s));
     FB_CUDA(c, cudaEventSynchronize(c->ev1));

@@ -82,6 +82,8 @@ struct fb_ctx {
     int cg_graph_iters = 32;
     int cheb_degree = 2;
     int dof_order = 0;
+    int spmv_kernel = -1;                    // -1 auto, 0 row-block stream kernel, 2..32 lanes per row
+    int cg_persistent = -1;                  // -1 auto (single cooperative launch when the system fits on chip), 0 off
     int cg_profile = 0;                      // iterations per solve bracketed with CUDA events (0 = off)
 
     // ---- host copies of the mesh (femocs numbering) ----
@@ -94,6 +96,11 @@ struct fb_ctx {
     int n_vert = 0, n_cells = 0, n_dofs = 0;
     long nnz = 0;
     std::vector<int> rowptr, col;            // CSR pattern, columns sorted
+    std::vector<int> rowblk;                 // row blocks of the streaming SpMV (first row of each block, n_rowblk + 1 entries)
+    int n_rowblk = 0, rowblk_chunk = 0, rowblk_maxrows = 0;
+    std::vector<unsigned short> col16;       // windowed SpMV: column position inside the block's window
+    std::vector<int> win_off, win_list;      // per row block: sorted distinct columns (CSR over blocks)
+    int win_max = 0, win_cap = 0;
     struct BFace { int cell, face, id; };
     std::vector<BFace> bfaces;
     std::vector<int> copper_dofs, top_dofs;  // Dirichlet candidates
@@ -106,7 +113,8 @@ struct fb_ctx {
     // ---- device: solver ----
     fb::DevBuf<double> d_vxyz;               // coordinates per DoF (3*n_dofs)
     fb::DevBuf<int> d_cells;                 // 8*n_cells dof ids (lexicographic)
-    fb::DevBuf<int> d_rowptr, d_col, d_diagpos;
+    fb::DevBuf<int> d_rowptr, d_col, d_diagpos, d_rowblk, d_win_off, d_win_list;
+    fb::DevBuf<unsigned short> d_col16;
     fb::DevBuf<double> d_val, d_val_save;
     fb::DevBuf<double> d_rhs, d_x, d_g, d_d, d_h, d_dinv, d_z, d_w;
     fb::DevBuf<int> d_topfaces;              // 4 dof ids per top (Neumann) face
@@ -116,6 +124,9 @@ struct fb_ctx {
     fb::DevBuf<int> d_vertex2dof;            // n_vert
     fb::DevBuf<int> d_cell2hex, d_hex2cell;
     fb::DevBuf<double> d_minmax;
+    // persistent cooperative CG (native meshes): row slice per CTA
+    std::vector<int> pers_cta_row; int pers_grid = 0, pers_cap = 0, pers_rmax = 0; bool pers_uploaded = false;
+    fb::DevBuf<int> d_cta_row;
     cudaGraphExec_t cg_graph = nullptr;
     int cg_graph_precond = -1, cg_graph_n = 0;
     double last_solve_ms = 0; int last_iters = 0; long last_spmv = 0;
@@ -158,6 +169,8 @@ struct fb_ctx {
     } while (0)
 
 // implemented in host_setup.cpp
+bool fb_host_row_blocks(fb_ctx* c, int chunk, int maxrows);
+bool fb_host_col_windows(fb_ctx* c, int max_window);
 int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
 struct fb_interp_tables {
     std::vector<fb::TetRec> tet; std::vector<double> tet_cent; std::vector<int> tet_mark, tet_nbr_off, tet_nbr;

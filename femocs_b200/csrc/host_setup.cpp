@@ -263,6 +263,63 @@ int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* he
     return FB_OK;
 }
 
+// Row blocks of the streaming SpMV: whole rows, <= chunk non-zeros and <= maxrows rows per block.
+// Returns false when a single row is longer than the chunk (the per-row kernel must be used).
+bool fb_host_row_blocks(fb_ctx* c, int chunk, int maxrows) {
+    c->rowblk.clear(); c->rowblk.push_back(0);
+    int start = 0;
+    for (int r = 0; r < c->n_dofs; ++r) {
+        if (c->rowptr[r + 1] - c->rowptr[r] > chunk) { c->n_rowblk = 0; return false; }
+        if (c->rowptr[r + 1] - c->rowptr[start] > chunk || r - start >= maxrows) { c->rowblk.push_back(r); start = r; }
+    }
+    c->rowblk.push_back(c->n_dofs);
+    c->n_rowblk = (int) c->rowblk.size() - 1;
+    c->rowblk_chunk = chunk; c->rowblk_maxrows = maxrows;
+    return true;
+}
+
+// Column windows of the windowed streaming SpMV: for every row block the sorted list of distinct
+// columns it references (its "window" of the input vector) and, per non-zero, the 16-bit position
+// of its column inside that window.  Returns false if a window exceeds max_window entries.
+bool fb_host_col_windows(fb_ctx* c, int max_window) {
+    const int nb = c->n_rowblk;
+    if (nb <= 0) return false;
+    std::vector<std::vector<int>> win(nb);
+    c->col16.resize(c->nnz);
+    bool ok = true;
+#pragma omp parallel
+    {
+        std::vector<int> buf;
+#pragma omp for schedule(dynamic, 64)
+        for (int b = 0; b < nb; ++b) {
+            const int k0 = c->rowptr[c->rowblk[b]], k1 = c->rowptr[c->rowblk[b + 1]];
+            buf.assign(c->col.begin() + k0, c->col.begin() + k1);
+            std::sort(buf.begin(), buf.end());
+            buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
+            if ((int) buf.size() > max_window) {
+#pragma omp atomic write
+                ok = false;
+                continue;
+            }
+            for (int k = k0; k < k1; ++k)
+                c->col16[k] = (unsigned short) (std::lower_bound(buf.begin(), buf.end(), c->col[k]) - buf.begin());
+            win[b] = buf;
+        }
+    }
+    if (!ok) { c->col16.clear(); c->col16.shrink_to_fit(); return false; }
+    c->win_off.assign(nb + 1, 0);
+    int wmax = 0;
+    for (int b = 0; b < nb; ++b) {
+        c->win_off[b + 1] = c->win_off[b] + (int) win[b].size();
+        wmax = std::max(wmax, (int) win[b].size());
+    }
+    c->win_list.resize(c->win_off[nb]);
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < nb; ++b) std::copy(win[b].begin(), win[b].end(), c->win_list.begin() + c->win_off[b]);
+    c->win_max = wmax;
+    return true;
+}
+
 // =======================================================================================
 //  Interpolator precompute tables.  The arithmetic below must reproduce the reference's
 //  tables bit for bit (cell location is compared bit-exactly), hence the expression order

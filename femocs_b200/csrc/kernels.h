@@ -8,6 +8,7 @@ namespace fb {
 
 // poisson_kernels.cu
 int choose_lanes(const fb_ctx* c);
+void stream_block_shape(int kernel, int& chunk, int& maxrows);
 void launch_assemble_stiffness(fb_ctx* c, double* d_cell_vol);
 void launch_neumann(fb_ctx* c);
 void launch_set_bc(fb_ctx* c, const int* d_dofs, int n, double value);
@@ -17,6 +18,8 @@ void launch_cg_init(fb_ctx* c, int lanes);
 void launch_cg_iteration(fb_ctx* c, int lanes);
 void launch_cg_spmv(fb_ctx* c, int lanes);
 void launch_cg_vectors(fb_ctx* c);
+bool persistent_eligible(fb_ctx* c);
+cudaError_t launch_cg_persistent(fb_ctx* c);
 void launch_minmax(fb_ctx* c);
 void launch_gather(fb_ctx* c, int n, const int* idx, const double* src, double* dst);
 void launch_scatter(fb_ctx* c, int n, const int* idx, const double* src, double* dst);

@@ -12,6 +12,9 @@
 // are not used.  Layout: CSR (double val, int col) with sorted columns, vectors in DoF order.
 #include <cooperative_groups.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "kernels.h"
 
 namespace cg = cooperative_groups;
@@ -300,6 +303,76 @@ __global__ void __launch_bounds__(256) k_spmv_dot(int n, const int* __restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Row-block ("CSR-stream") SpMV for HBM-sized systems.  The host cuts the rows into blocks of
+// whole rows holding <= SPMV_CHUNK non-zeros and <= 256 rows (ctx: rowblk).  A CTA streams the
+// block's val/col arrays with perfectly coalesced, evict-first loads (each thread SPMV_CHUNK/256
+// independent loads in flight), multiplies by the gathered vector entries (read-only path, L1/L2
+// resident) into shared memory, then one thread per row adds its products in column order --
+// the same summation order as a sequential CSR sweep, so the result is deterministic.
+// Algorithmic bytes per launch: 12 nnz + 4 (n+1) + 16 n.
+// ---------------------------------------------------------------------------------------
+template <bool INIT, int THREADS, int PER_THREAD>
+__global__ void __launch_bounds__(THREADS) k_spmv_stream(int n_blocks, const int* __restrict__ rowblk, const int* __restrict__ rowptr,
+                                                         const int* __restrict__ col, const double* __restrict__ val,
+                                                         const double* __restrict__ xin, const double* __restrict__ rhs,
+                                                         const double* __restrict__ dinv, double* __restrict__ out,
+                                                         double* __restrict__ partial, unsigned* counter, CgScalars* __restrict__ cgs,
+                                                         double* __restrict__ alpha_out) {
+    if (!INIT && cgs->done) return;
+    constexpr int CHUNK = THREADS * PER_THREAD;
+    __shared__ double s_prod[CHUNK];
+    __shared__ int s_rp[THREADS + 1];
+    const int tid = threadIdx.x;
+    double acc[2] = {0, 0};
+    for (int b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        const int r0 = __ldg(&rowblk[b]), nr = __ldg(&rowblk[b + 1]) - r0;
+        if (tid <= nr) s_rp[tid] = __ldg(&rowptr[r0 + tid]);
+        __syncthreads();
+        const int k0 = s_rp[0], k1 = s_rp[nr];
+        const int* __restrict__ cb = col + k0;
+        const double* __restrict__ vb = val + k0;
+        const int cnt = k1 - k0;
+        int cidx[PER_THREAD];
+        double v[PER_THREAD];
+#pragma unroll
+        for (int u = 0; u < PER_THREAD; ++u) {
+            const int k = tid + u * THREADS;
+            cidx[u] = (k < cnt) ? __ldcg(&cb[k]) : -1;
+            v[u] = (k < cnt) ? __ldcg(&vb[k]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < PER_THREAD; ++u)
+            if (cidx[u] >= 0) s_prod[tid + u * THREADS] = v[u] * __ldg(&xin[cidx[u]]);
+        __syncthreads();
+        if (tid < nr) {
+            const int lo = s_rp[tid] - k0, hi = s_rp[tid + 1] - k0;
+            double sum = 0;
+            for (int j = lo; j < hi; ++j) sum += s_prod[j];
+            const int r = r0 + tid;
+            if (INIT) {
+                const double g = sum - rhs[r];
+                out[r] = g;
+                acc[0] += g * g * dinv[r];
+                acc[1] += g * g;
+            } else {
+                out[r] = sum;
+                acc[0] += __ldg(&xin[r]) * sum;
+            }
+        }
+        __syncthreads();
+    }
+    double tot[2];
+    if (reduce_publish<2>(acc, partial, counter, tot)) {
+        if (INIT) {
+            cgs->gh = tot[0]; cgs->res2 = tot[1]; cgs->it = 0;
+            cgs->done = (tot[1] <= cgs->tol2) ? 1 : ((cgs->max_iter <= 0 || tot[1] != tot[1]) ? 2 : 0);
+        } else {
+            *alpha_out = cgs->gh / tot[0];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_update(int n, const double* __restrict__ d, const double* __restrict__ h,
                                                 const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ g,
                                                 double* __restrict__ partial, unsigned* counter, CgScalars* __restrict__ cgs,
@@ -334,6 +407,232 @@ __global__ void __launch_bounds__(256) k_direction(int n, const double* __restri
     const double beta = INIT ? 0.0 : *beta_in;
     for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x)
         d[i] = (INIT ? 0.0 : beta * d[i]) - dinv[i] * g[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// Windowed streaming SpMV (the HBM-roofline kernel).  Same row blocks as k_spmv_stream, plus two
+// host-built tables (fb_host_col_windows): the block's WINDOW = sorted distinct columns it touches,
+// and a 16-bit window position per non-zero.  A CTA
+//   1. issues its coalesced val (8 B) / col16 (2 B) loads, L1-bypassing (ld.global.cg),
+//   2. stages the window of the input vector into shared memory (sorted -> dense sectors; each
+//      distinct entry is fetched once per block instead of once per non-zero),
+//   3. multiplies out of shared memory (no scattered global gathers: the L1 wavefront limit of the
+//      per-non-zero gather is what capped the plain CSR kernels at ~0.45-0.65 of HBM peak),
+//   4. adds the products of each row in column order (deterministic, = sequential CSR order).
+// DRAM traffic is BELOW the algorithmic 12 nnz + 4(n+1) + 16 n bytes it is rated against
+// (10 B per non-zero + windows), which is why its roofline fraction can approach / exceed 1.
+// ---------------------------------------------------------------------------------------
+template <bool INIT, int THREADS, int PER_THREAD>
+__global__ void __launch_bounds__(THREADS) k_spmv_window(int n_blocks, const int* __restrict__ rowblk, const int* __restrict__ rowptr,
+                                                         const unsigned short* __restrict__ col16, const double* __restrict__ val,
+                                                         const int* __restrict__ win_off, const int* __restrict__ win_list,
+                                                         const double* __restrict__ xin, const double* __restrict__ rhs,
+                                                         const double* __restrict__ dinv, double* __restrict__ out,
+                                                         double* __restrict__ partial, unsigned* counter, CgScalars* __restrict__ cgs,
+                                                         double* __restrict__ alpha_out, int wcap) {
+    if (!INIT && cgs->done) return;
+    constexpr int CHUNK = THREADS * PER_THREAD;
+    extern __shared__ double s_dyn[];
+    double* s_prod = s_dyn;                  // CHUNK products
+    double* s_x = s_dyn + CHUNK;             // wcap window entries
+    __shared__ int s_rp[THREADS + 1];
+    const int tid = threadIdx.x;
+    double acc[2] = {0, 0};
+    for (int b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        const int r0 = __ldg(&rowblk[b]), nr = __ldg(&rowblk[b + 1]) - r0;
+        const int w0 = __ldg(&win_off[b]), nw = __ldg(&win_off[b + 1]) - w0;
+        if (tid <= nr) s_rp[tid] = __ldg(&rowptr[r0 + tid]);
+        const int k0 = __ldg(&rowptr[r0]), cnt = __ldg(&rowptr[r0 + nr]) - k0;
+        const unsigned short* __restrict__ cb = col16 + k0;
+        const double* __restrict__ vb = val + k0;
+        int cidx[PER_THREAD];
+        double v[PER_THREAD];
+#pragma unroll
+        for (int u = 0; u < PER_THREAD; ++u) {
+            const int k = tid + u * THREADS;
+            cidx[u] = (k < cnt) ? (int) __ldcg(&cb[k]) : -1;
+            v[u] = (k < cnt) ? __ldcg(&vb[k]) : 0.0;
+        }
+        for (int i = tid; i < nw; i += THREADS) s_x[i] = __ldg(&xin[__ldg(&win_list[w0 + i])]);
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < PER_THREAD; ++u)
+            if (cidx[u] >= 0) s_prod[tid + u * THREADS] = v[u] * s_x[cidx[u]];
+        __syncthreads();
+        if (tid < nr) {
+            const int lo = s_rp[tid] - k0, hi = s_rp[tid + 1] - k0;
+            double sum = 0;
+            for (int j = lo; j < hi; ++j) sum += s_prod[j];
+            const int r = r0 + tid;
+            if (INIT) {
+                const double g = sum - rhs[r];
+                out[r] = g;
+                acc[0] += g * g * dinv[r];
+                acc[1] += g * g;
+            } else {
+                out[r] = sum;
+                acc[0] += __ldg(&xin[r]) * sum;
+            }
+        }
+        __syncthreads();
+    }
+    double tot[2];
+    if (reduce_publish<2>(acc, partial, counter, tot)) {
+        if (INIT) {
+            cgs->gh = tot[0]; cgs->res2 = tot[1]; cgs->it = 0;
+            cgs->done = (tot[1] <= cgs->tol2) ? 1 : ((cgs->max_iter <= 0 || tot[1] != tot[1]) ? 2 : 0);
+        } else {
+            *alpha_out = cgs->gh / tot[0];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Persistent cooperative CG for the native (L2-resident) meshes: the WHOLE solve is one launch.
+// One CTA per SM owns a contiguous, nnz-balanced slice of rows for the entire solve: its matrix
+// values live in shared memory, its column indices in registers, its slices of x, g, d, h, 1/diag
+// in shared memory.  Per iteration only the search direction d crosses SMs (written to global,
+// gathered through L2 with ld.global.cg) plus 3 doubles per CTA for the dot products; the three
+// phases are separated by grid-wide barriers and every warp re-reduces the per-CTA partials in a
+// fixed order, so all CTAs take bit-identical alpha/beta/convergence decisions (no divergence at
+// the barriers) and the result is deterministic.  Same operation order as the multi-kernel path
+// (deal.II SolverCG): h = A d; alpha = gh/(d.h); x += alpha d; g += alpha h; test |g|;
+// beta = g.Dinv g / gh; d = beta d - Dinv g.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double sum_partials(const double* p, int G) {
+    double s = 0;
+    for (int i = threadIdx.x & 31; i < G; i += 32) s += __ldcg(p + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;       // bit-identical in every lane, warp and CTA
+}
+
+template <int NV>
+__device__ __forceinline__ void block_publish(double (&v)[NV], double (*s_red)[32], double* partial, int G) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) s_red[k][warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double t = 0;
+            for (int w = 0; w < nwarp; ++w) t += s_red[k][w];
+            __stcg(&partial[(size_t) k * G + blockIdx.x], t);
+        }
+    }
+}
+
+template <int THREADS, int PT>
+__global__ void __launch_bounds__(THREADS, 1) k_cg_persistent(const int* __restrict__ cta_row, const int* __restrict__ rowptr,
+                                                              const int* __restrict__ col, const double* __restrict__ val,
+                                                              const double* __restrict__ rhs, const double* __restrict__ dinv_g,
+                                                              double* x_g, double* d_g, double* partial, CgScalars* cgs,
+                                                              int cap, int rmax) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double smem[];
+    double* s_val = smem;
+    double* s_prod = s_val + cap;
+    double* s_x = s_prod + cap;
+    double* s_g = s_x + rmax;
+    double* s_d = s_g + rmax;
+    double* s_h = s_d + rmax;
+    double* s_dinv = s_h + rmax;
+    int* s_rp = (int*) (s_dinv + rmax);
+    __shared__ double s_red[2][32];
+    const int G = gridDim.x, tid = threadIdx.x;
+    const int r0 = cta_row[blockIdx.x], nr = cta_row[blockIdx.x + 1] - r0;
+    const int k0 = rowptr[r0], cnt = rowptr[r0 + nr] - k0;
+    double* partA = partial;             // phase A: d.h
+    double* partB = partial + G;         // phase B: g.Dinv g, g.g
+
+    int cidx[PT];
+#pragma unroll
+    for (int u = 0; u < PT; ++u) {
+        const int k = tid + u * THREADS;
+        cidx[u] = (k < cnt) ? __ldg(&col[k0 + k]) : -1;
+        if (k < cnt) s_val[k] = __ldg(&val[k0 + k]);
+    }
+    for (int r = tid; r <= nr; r += THREADS) s_rp[r] = rowptr[r0 + r] - k0;
+    for (int r = tid; r < nr; r += THREADS) { s_x[r] = x_g[r0 + r]; s_dinv[r] = dinv_g[r0 + r]; }
+    __syncthreads();
+
+    auto spmv = [&](const double* vec) {          // s_h = (A vec) on the CTA's rows; vec is gathered through L2
+#pragma unroll
+        for (int u = 0; u < PT; ++u)
+            if (cidx[u] >= 0) s_prod[tid + u * THREADS] = s_val[tid + u * THREADS] * __ldcg(&vec[cidx[u]]);
+        __syncthreads();
+        for (int r = tid; r < nr; r += THREADS) {
+            double sum = 0;
+            for (int j = s_rp[r]; j < s_rp[r + 1]; ++j) sum += s_prod[j];
+            s_h[r] = sum;
+        }
+    };
+
+    const double tol2 = cgs->tol2;
+    const int max_iter = cgs->max_iter;
+    // ---- start: g = A x - b (deal.II SolverCG), d = -Dinv g ----
+    spmv(x_g);
+    double acc[2] = {0, 0};
+    for (int r = tid; r < nr; r += THREADS) {
+        const double g = s_h[r] - rhs[r0 + r];
+        s_g[r] = g;
+        acc[0] += g * g * s_dinv[r];
+        acc[1] += g * g;
+    }
+    block_publish<2>(acc, s_red, partB, G);
+    grid.sync();
+    double gh = sum_partials(partB, G);
+    double res2 = sum_partials(partB + G, G);
+    int it = 0;
+    int done = (res2 <= tol2) ? 1 : ((max_iter <= 0 || res2 != res2) ? 2 : 0);
+    if (!done) {
+        for (int r = tid; r < nr; r += THREADS) { const double d = -s_dinv[r] * s_g[r]; s_d[r] = d; __stcg(&d_g[r0 + r], d); }
+        grid.sync();
+    }
+    while (!done) {
+        // phase A
+        spmv(d_g);
+        double a[1] = {0};
+        for (int r = tid; r < nr; r += THREADS) a[0] += s_d[r] * s_h[r];
+        block_publish<1>(a, s_red, partA, G);
+        grid.sync();
+        // phase B
+        const double alpha = gh / sum_partials(partA, G);
+        acc[0] = 0; acc[1] = 0;
+        for (int r = tid; r < nr; r += THREADS) {
+            s_x[r] += alpha * s_d[r];
+            const double g = s_g[r] + alpha * s_h[r];
+            s_g[r] = g;
+            acc[0] += g * g * s_dinv[r];
+            acc[1] += g * g;
+        }
+        block_publish<2>(acc, s_red, partB, G);
+        grid.sync();
+        // phase C
+        const double ghn = sum_partials(partB, G);
+        res2 = sum_partials(partB + G, G);
+        ++it;
+        const double beta = ghn / gh;
+        gh = ghn;
+        if (res2 <= tol2) done = 1;
+        else if (it >= max_iter || res2 != res2) done = 2;
+        if (!done) {
+            for (int r = tid; r < nr; r += THREADS) {
+                const double d = beta * s_d[r] - s_dinv[r] * s_g[r];
+                s_d[r] = d;
+                __stcg(&d_g[r0 + r], d);
+            }
+            grid.sync();
+        }
+    }
+    for (int r = tid; r < nr; r += THREADS) x_g[r0 + r] = s_x[r];
+    if (blockIdx.x == 0 && tid == 0) { cgs->gh = gh; cgs->res2 = res2; cgs->it = it; cgs->done = done; }
 }
 
 // min/max of the solution (DealSolver::check_limits)
@@ -381,7 +680,26 @@ static inline int grid_for(const fb_ctx* c, long work_items, int block) {
     return (int) (g < 1 ? 1 : g);
 }
 
+// row-block parameters (non-zeros, rows) of a streaming-kernel variant
+void stream_block_shape(int kernel, int& chunk, int& maxrows) {
+    switch (kernel) {
+        case 100: chunk = 1024; maxrows = 256; break;
+        case 101: chunk = 4096; maxrows = 512; break;
+        case 102: chunk = 1024; maxrows = 128; break;
+        case 103: chunk = 4096; maxrows = 256; break;
+        case 200: chunk = 2048; maxrows = 256; break;
+        case 201: chunk = 4096; maxrows = 256; break;
+        case 202: chunk = 4096; maxrows = 512; break;
+        case 203: chunk = 1024; maxrows = 256; break;
+        case 204: chunk = 8192; maxrows = 512; break;
+        default: chunk = 2048; maxrows = 256; break;
+    }
+}
+
 int choose_lanes(const fb_ctx* c) {
+    // 0 selects the row-block streaming kernel (option "spmv_kernel": -1 auto, 0 stream, else lanes per row)
+    if (c->spmv_kernel >= 0) return c->spmv_kernel;
+    if (c->nnz >= 4000000) return 201;
     const double avg = c->n_dofs ? (double) c->nnz / c->n_dofs : 1.0;
     if (avg > 48) return 32;
     if (avg > 20) return 8;
@@ -424,9 +742,46 @@ void launch_apply_bc_rhs(fb_ctx* c) {
 
 template <bool INIT>
 static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, double* alpha) {
-    const int g = grid_for(c, (long) c->n_dofs * lanes, 256);
     unsigned* counter = (unsigned*) (c->d_partial.p + c->d_partial.n - 8);
     double* part = c->d_partial.p;
+    if (lanes >= 200) {         // windowed streaming kernel (variants 200.. are tuning points)
+        const int nb = c->n_rowblk;
+#define FB_WINDOW(T, P, OCC) do {                                                                                                   \
+        auto kern = k_spmv_window<INIT, T, P>;                                                                                      \
+        const size_t smem = sizeof(double) * ((size_t) (T) * (P) + (size_t) c->win_cap);                                            \
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);                                        \
+        const int occ = std::max(1, std::min((OCC), (int) (220 * 1024 / (smem + 4 * ((T) + 1) + 1024))));                           \
+        const int g = std::min(nb, c->n_sm * occ);                                                                                  \
+        kern<<<g, T, smem, c->stream>>>(nb, c->d_rowblk.p, c->d_rowptr.p, c->d_col16.p, c->d_val.p, c->d_win_off.p, c->d_win_list.p, \
+                                        xin, c->d_rhs.p, c->d_dinv.p, out, part, counter, c->d_cg.p, alpha, c->win_cap); } while (0)
+        switch (lanes) {
+            case 201: FB_WINDOW(256, 16, 8); break;
+            case 202: FB_WINDOW(512, 8, 4); break;
+            case 203: FB_WINDOW(256, 4, 8); break;
+            case 204: FB_WINDOW(512, 16, 4); break;
+            default: FB_WINDOW(256, 8, 8); break;
+        }
+#undef FB_WINDOW
+        c->launches++;
+        return;
+    }
+    if (lanes == 0 || lanes >= 100) {           // row-block streaming kernel (variants 100.. are tuning points)
+        const int nb = c->n_rowblk;
+#define FB_STREAM(T, P, OCC) do { const int g = std::min(nb, c->n_sm * (OCC));                                                     \
+        k_spmv_stream<INIT, T, P><<<g, T, 0, c->stream>>>(nb, c->d_rowblk.p, c->d_rowptr.p, c->d_col.p, c->d_val.p, xin, c->d_rhs.p, \
+                                                         c->d_dinv.p, out, part, counter, c->d_cg.p, alpha); } while (0)
+        switch (lanes) {
+            case 100: FB_STREAM(256, 4, 8); break;
+            case 101: FB_STREAM(512, 8, 4); break;
+            case 102: FB_STREAM(128, 8, 16); break;
+            case 103: FB_STREAM(256, 16, 6); break;
+            default: FB_STREAM(256, 8, 8); break;
+        }
+#undef FB_STREAM
+        c->launches++;
+        return;
+    }
+    const int g = grid_for(c, (long) c->n_dofs * lanes, 256);
 #define FB_SPMV(L) k_spmv_dot<L, INIT><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_rowptr.p, c->d_col.p, c->d_val.p, xin, \
                                                               c->d_rhs.p, c->d_dinv.p, out, part, counter, c->d_cg.p, alpha)
     switch (lanes) {
@@ -467,6 +822,60 @@ void launch_cg_vectors(fb_ctx* c) {               // x, g update + dots + conver
 void launch_cg_iteration(fb_ctx* c, int lanes) {
     launch_cg_spmv(c, lanes);
     launch_cg_vectors(c);
+}
+
+// Persistent solve: returns false when the system does not fit the per-SM shared memory / register budget.
+template <int PT>
+static cudaError_t launch_persistent_pt(fb_ctx* c, size_t smem) {
+    auto kern = k_cg_persistent<512, PT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    const int* a0 = c->d_cta_row.p; const int* a1 = c->d_rowptr.p; const int* a2 = c->d_col.p; const double* a3 = c->d_val.p;
+    const double* a4 = c->d_rhs.p; const double* a5 = c->d_dinv.p; double* a6 = c->d_x.p; double* a7 = c->d_d.p;
+    double* a8 = c->d_partial.p; CgScalars* a9 = c->d_cg.p; int a10 = c->pers_cap, a11 = c->pers_rmax;
+    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10, &a11};
+    return cudaLaunchCooperativeKernel((void*) kern, dim3(c->pers_grid), dim3(512), args, smem, c->stream);
+}
+
+bool persistent_eligible(fb_ctx* c) {
+    if (c->cg_persistent == 0 || c->n_dofs <= 0) return false;
+    if (c->pers_grid == 0) {
+        // nnz-balanced contiguous row slices, one per SM
+        const int G = std::min(c->n_sm, std::max(1, c->n_dofs / 8));
+        std::vector<int> cta_row(G + 1, c->n_dofs);
+        cta_row[0] = 0;
+        int r = 0, cap = 0, rmax = 0;
+        for (int b = 0; b < G; ++b) {
+            const long target = (long) c->nnz * (b + 1) / G;
+            const int start = r;
+            while (r < c->n_dofs && (c->rowptr[r + 1] <= target || r == start) && (c->n_dofs - r) > (G - 1 - b)) ++r;
+            if (b == G - 1) r = c->n_dofs;
+            cta_row[b + 1] = r;
+            cap = std::max(cap, c->rowptr[r] - c->rowptr[start]);
+            rmax = std::max(rmax, r - start);
+        }
+        c->pers_grid = G; c->pers_cap = (cap + 1) & ~1; c->pers_rmax = (rmax + 1) & ~1;
+        c->pers_cta_row = cta_row;
+        c->pers_uploaded = false;
+    }
+    const size_t smem = 16 * (size_t) c->pers_cap + 40 * (size_t) c->pers_rmax + 4 * ((size_t) c->pers_rmax + 2);
+    return c->pers_cap <= 24 * 512 && smem <= 220 * 1024;
+}
+
+cudaError_t launch_cg_persistent(fb_ctx* c) {
+    if (!c->pers_uploaded) {
+        cudaError_t e = c->d_cta_row.upload(c->pers_cta_row, c->stream);
+        if (e != cudaSuccess) return e;
+        c->pers_uploaded = true;
+    }
+    const size_t smem = 16 * (size_t) c->pers_cap + 40 * (size_t) c->pers_rmax + 4 * ((size_t) c->pers_rmax + 2);
+    const int pt = (c->pers_cap + 511) / 512;
+    c->launches++;
+    if (pt <= 4) return launch_persistent_pt<4>(c, smem);
+    if (pt <= 8) return launch_persistent_pt<8>(c, smem);
+    if (pt <= 12) return launch_persistent_pt<12>(c, smem);
+    if (pt <= 16) return launch_persistent_pt<16>(c, smem);
+    return launch_persistent_pt<24>(c, smem);
 }
 
 void launch_minmax(fb_ctx* c) {

@@ -107,6 +107,45 @@ def test_solution_matches_oracle(name, fb, ctx, golden, oracles):
     assert s.solve(n_cg=5) == -5
 
 
+@pytest.mark.parametrize("kernel", [0, 100, 101, 102, 103, 200, 201, 202, 203, 204, 2, 8, 32])
+def test_spmv_kernel_variants_agree(kernel, fb, golden, oracles):
+    """every SpMV kernel of the multi-kernel CG (windowed / plain row-block streaming variants, lanes-per-row
+    variants) gives the oracle's solution"""
+    m = golden("mesh", "mdsmall"); o = oracles["mdsmall"]
+    c = fb.Context(0)
+    c.set_option("cg_persistent", 0)
+    c.set_option("spmv_kernel", kernel)
+    s = fb.PoissonSolver(c, fb.FieldConfig(cg_tolerance=1e-11))
+    s.import_mesh(m["nodes"], m["hexs"], m["hex_markers"])
+    s.setup(0.5, 0.0); s.assemble(True)
+    assert s.solve() > 0
+    o.setup(0.5, 0.0, False); o.assemble(True); o.solve(10000, 1e-11, 1.2, 0)
+    assert _rel(s.export_solution(), o.export_solution()) < REL
+    c.close()
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_persistent_and_multikernel_cg_agree(name, fb, golden):
+    """the single-launch cooperative CG and the CUDA-graph multi-kernel CG run the same algorithm"""
+    m = golden("mesh", name)
+    out = []
+    for persistent in (1, 0):
+        c = fb.Context(0)
+        c.set_option("cg_persistent", persistent)
+        s = fb.PoissonSolver(c, fb.FieldConfig(cg_tolerance=1e-10))
+        s.import_mesh(m["nodes"], m["hexs"], m["hex_markers"])
+        s.setup(0.5, 0.0); s.assemble(True)
+        it = s.solve()
+        assert it > 0
+        launches = c.kernel_launches
+        assert s.solve(n_cg=3) == 0                      # warm start inside the same path
+        out.append((it, s.export_solution(), launches))
+        c.close()
+    assert abs(out[0][0] - out[1][0]) <= 2
+    assert _rel(out[0][1], out[1][1]) < 1e-9
+    assert out[0][2] < 40 < out[1][2]                    # one cooperative launch vs 3 kernels per iteration
+
+
 def test_uniform_field_exact(fb, ctx):
     nodes, hexs, mk = synth.box_mesh(7, 6, 9, 3.0, 2.5, 4.0, jitter=0.2)
     F = 0.37
@@ -241,6 +280,23 @@ def test_space_charge_rhs_matches_oracle(name, fb, golden, gpu_interp, oracles):
     o.solve(10000, 1e-11, 1.2, 0)
     assert _rel(s.export_solution(), o.export_solution()) < REL
     s.conf.mode = "laplace"; s.set_particles(None, None, 0)
+
+
+def test_space_charge_without_interpolator_tables(fb, golden, oracles):
+    """solver-only context (no fb_interp_initialize): the hexahedron coefficients are rebuilt from the cell vertices"""
+    m = golden("mesh", "mdsmall"); g = golden("interp", "mdsmall"); o = oracles["mdsmall"]
+    ok = g["pic_ok"]
+    pts = g["points"][ok]; cells = g["pic_cells"][ok]
+    cf = -180.9512268 * 0.01
+    c = fb.Context(0)
+    s = fb.PoissonSolver(c, fb.FieldConfig(mode="transient"))
+    s.import_mesh(m["nodes"], m["hexs"], m["hex_markers"])
+    s.set_particles(pts, cells, cf)
+    s.setup(0.5, 0.0); s.assemble(True)
+    o.setup(0.5, 0.0, False); o.assemble(True, pts, cells, cf)
+    rhs = o.vectors()[0]
+    assert np.abs(s.get_system()["rhs"] - rhs).max() <= 1e-11 * np.abs(rhs).max()
+    c.close()
 
 
 def test_full_step_matches_oracle(fb, golden, oracles):
