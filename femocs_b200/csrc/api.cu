@@ -80,6 +80,8 @@ int fb_set_option(fb_ctx* c, const char* key, double value) {
     else if (k == "dof_order") c->dof_order = (int) value;
     else if (k == "spmv_kernel") { c->spmv_kernel = (int) value; drop_graph(c); }
     else if (k == "cg_persistent") c->cg_persistent = (int) value;
+    else if (k == "cg_debug") c->cg_debug = (int) value;
+    else if (k == "cg_persistent_ctas") { c->pers_ctas = (int) value; c->pers_grid = 0; }
     else if (k == "cg_profile") c->cg_profile = std::max(0, std::min(4096, (int) value));
     else return c->fail(FB_ERR_ARG, "unknown option %s", key);
     return FB_OK;
@@ -112,7 +114,7 @@ int fb_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, c
     FB_CUDA(c, c->d_cells.upload(c->cells_dof, s));
     FB_CUDA(c, c->d_rowptr.upload(c->rowptr, s));
     FB_CUDA(c, c->d_col.upload(c->col, s));
-    c->n_rowblk = 0; c->rowblk_chunk = 0; c->win_cap = 0;
+    c->n_rowblk = 0; c->rowblk_chunk = 0; c->win_cap = 0; c->jds_ready = false; c->jds_val_dirty = true;
     c->pers_grid = 0;
     FB_CUDA(c, c->d_topfaces.upload(top, s));
     FB_CUDA(c, c->d_vertex2dof.upload(c->vertex2dof, s));
@@ -166,6 +168,7 @@ static int assemble_impl(fb_ctx* c, int first_time, const double* d_pxyz, const 
         }
         c->n_dirichlet = (int) std::count(mark.begin(), mark.end(), (unsigned char) 1);
         fb::launch_apply_bc_matrix(c);      // val, Dirichlet lift (kept in d_w), dinv, diagpos
+        c->jds_val_dirty = true;
         FB_CUDA(c, cudaStreamSynchronize(s));   // tmp goes out of scope
         c->matrix_ok = true;
     }
@@ -220,9 +223,41 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
         FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
         FB_CUDA(c, cudaStreamSynchronize(s));
         spmv += h->it;
+        if (c->cg_debug) {          // per-phase SM cycles of CTAs 0..3 (diagnostics)
+            long long t[24];
+            cudaMemcpy(t, c->d_dbg.p, sizeof t, cudaMemcpyDeviceToHost);
+            for (int b = 0; b < 4; ++b)
+                fprintf(stderr, "[fb cg_debug] cta %d it %d cycles/it: spmv %lld | reduce(d.h) %lld | update %lld | reduce(g.g) %lld | direction %lld | barrier(d) %lld\n",
+                        b, h->it, t[6 * b] / std::max(1, h->it), t[6 * b + 1] / std::max(1, h->it), t[6 * b + 2] / std::max(1, h->it),
+                        t[6 * b + 3] / std::max(1, h->it), t[6 * b + 4] / std::max(1, h->it), t[6 * b + 5] / std::max(1, h->it));
+        }
     } else {
         int lanes = fb::choose_lanes(c);
-        if (lanes == 0 || lanes >= 100) {          // streaming SpMV: (re)build its row blocks for the chosen variant
+        if (lanes >= 300) {                        // block-JDS SpMV: tables once per mesh, values once per assemble
+            const int R = (lanes == 301) ? 128 : 256;
+            if (!c->jds_ready || c->jds_R != R) {
+                drop_graph(c);
+                if (fb_host_jds_build(c, R, 8192)) {
+                    c->win_cap = (c->win_max + 15) & ~15;
+                    FB_CUDA(c, c->d_col16.upload(c->col16, s));
+                    FB_CUDA(c, c->d_win_off.upload(c->win_off, s)); FB_CUDA(c, c->d_win_list.upload(c->win_list, s));
+                    FB_CUDA(c, c->d_jds_perm.upload(c->jds_perm, s)); FB_CUDA(c, c->d_jds_len.upload(c->jds_len, s));
+                    FB_CUDA(c, c->d_jds_slot.upload(c->jds_slot, s));
+                    FB_CUDA(c, c->d_jds_jdp.upload(c->jds_jdp, s)); FB_CUDA(c, c->d_jds_jd.upload(c->jds_jd, s));
+                    FB_CUDA(c, c->d_val_jds.alloc(c->nnz));
+                    FB_CUDA(c, cudaStreamSynchronize(s));
+                    std::vector<unsigned short>().swap(c->col16);      // host copies no longer needed
+                    std::vector<int>().swap(c->win_list);
+                    c->jds_ready = true; c->jds_val_dirty = true;
+                    c->rowblk_chunk = 0; c->n_rowblk = 0;              // col16 / windows now belong to the JDS layout
+                } else {
+                    lanes = 100;                   // window too large for shared memory: plain streaming kernel
+                }
+            }
+            if (lanes >= 300 && c->jds_val_dirty) { fb::launch_csr_to_jds(c); c->jds_val_dirty = false; }
+        }
+        if (lanes == 0 || (lanes >= 100 && lanes < 300)) {          // streaming SpMV: (re)build its row blocks for the chosen variant
+            if (lanes >= 200) c->jds_ready = false;                  // the windowed variants reuse the col16 / window buffers
             int chunk, maxrows;
             fb::stream_block_shape(lanes, chunk, maxrows);
             if (c->rowblk_chunk != chunk || c->rowblk_maxrows != maxrows || c->n_rowblk == 0) {
@@ -462,7 +497,7 @@ static int check_dim_rank(fb_ctx* c, int dim, int rank) {
 }
 
 static int reserve_query(fb_ctx* c, long n) {
-    FB_CUDA(c, c->d_cellsA.alloc(n)); FB_CUDA(c, c->d_cellsB.alloc(n)); FB_CUDA(c, c->d_scan.alloc(n));
+    FB_CUDA(c, c->d_cellsA.alloc(n)); FB_CUDA(c, c->d_cellsB.alloc(n)); FB_CUDA(c, c->d_scan.alloc(n)); FB_CUDA(c, c->d_scan2.alloc(n));
     FB_CUDA(c, c->d_dirtyA.alloc(n)); FB_CUDA(c, c->d_dirtyB.alloc(n));
     return FB_OK;
 }
@@ -513,7 +548,7 @@ int fb_locate_interpolate(fb_ctx* c, int dim, int rank, long n, const double* x,
     FB_CUDA(c, c->d_sol.alloc(5 * (size_t) n));
     int* base = nullptr;
     if ((rc = fb::launch_locate_chain(c, dim, rank, n, c->d_pts.p, &base))) return rc;
-    int* final_cells = (base == c->d_cellsA.p) ? c->d_cellsB.p : c->d_cellsA.p;
+    int* final_cells = c->d_cellsA.p;          // the chain buffers are free once the fix-point is in d_scan2
     fb::launch_finish_interp(c, dim, rank, n, c->d_pts.p, base, 0, final_cells, c->d_sol.p);
     if (cells_out) FB_CUDA(c, cudaMemcpyAsync(cells_out, final_cells, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (sol5_out) FB_CUDA(c, cudaMemcpyAsync(sol5_out, c->d_sol.p, 5 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -101,6 +101,9 @@ struct fb_ctx {
     std::vector<unsigned short> col16;       // windowed SpMV: column position inside the block's window
     std::vector<int> win_off, win_list;      // per row block: sorted distinct columns (CSR over blocks)
     int win_max = 0, win_cap = 0;
+    // block-JDS layout of the HBM-roofline SpMV
+    int jds_R = 0, jds_nb = 0, jds_maxlen = 0; bool jds_ready = false, jds_val_dirty = true;
+    std::vector<unsigned short> jds_perm, jds_len, jds_slot; std::vector<int> jds_jdp, jds_jd;
     struct BFace { int cell, face, id; };
     std::vector<BFace> bfaces;
     std::vector<int> copper_dofs, top_dofs;  // Dirichlet candidates
@@ -114,7 +117,8 @@ struct fb_ctx {
     fb::DevBuf<double> d_vxyz;               // coordinates per DoF (3*n_dofs)
     fb::DevBuf<int> d_cells;                 // 8*n_cells dof ids (lexicographic)
     fb::DevBuf<int> d_rowptr, d_col, d_diagpos, d_rowblk, d_win_off, d_win_list;
-    fb::DevBuf<unsigned short> d_col16;
+    fb::DevBuf<unsigned short> d_col16, d_jds_perm, d_jds_len, d_jds_slot;
+    fb::DevBuf<int> d_jds_jdp, d_jds_jd; fb::DevBuf<double> d_val_jds;
     fb::DevBuf<double> d_val, d_val_save;
     fb::DevBuf<double> d_rhs, d_x, d_g, d_d, d_h, d_dinv, d_z, d_w;
     fb::DevBuf<int> d_topfaces;              // 4 dof ids per top (Neumann) face
@@ -126,7 +130,8 @@ struct fb_ctx {
     fb::DevBuf<double> d_minmax;
     // persistent cooperative CG (native meshes): row slice per CTA
     std::vector<int> pers_cta_row; int pers_grid = 0, pers_cap = 0, pers_rmax = 0; bool pers_uploaded = false;
-    fb::DevBuf<int> d_cta_row;
+    fb::DevBuf<int> d_cta_row, d_pers_flags;
+    fb::DevBuf<long long> d_dbg; int cg_debug = 0, pers_ctas = 0;
     cudaGraphExec_t cg_graph = nullptr;
     int cg_graph_precond = -1, cg_graph_n = 0;
     double last_solve_ms = 0; int last_iters = 0; long last_spmv = 0;
@@ -149,7 +154,8 @@ struct fb_ctx {
     fb::DevBuf<fb::HexRec> d_hex; fb::DevBuf<int> d_quad2hex;
     fb::DevBuf<int> d_qtet, d_qtri;          // 10 / 6 node ids
     // scratch for queries
-    fb::DevBuf<double> d_pts; fb::DevBuf<int> d_cellsA, d_cellsB, d_scan, d_flag; fb::DevBuf<double> d_sol;
+    fb::DevBuf<double> d_pts; fb::DevBuf<int> d_cellsA, d_cellsB, d_scan, d_scan2, d_flag;
+    int chain_blocks_per_sm = 0; fb::DevBuf<double> d_sol;
     fb::DevBuf<unsigned char> d_dirtyA, d_dirtyB;
     fb::PinnedBuf pin_in, pin_out;
 
@@ -171,6 +177,7 @@ struct fb_ctx {
 // implemented in host_setup.cpp
 bool fb_host_row_blocks(fb_ctx* c, int chunk, int maxrows);
 bool fb_host_col_windows(fb_ctx* c, int max_window);
+bool fb_host_jds_build(fb_ctx* c, int R, int max_window);
 int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
 struct fb_interp_tables {
     std::vector<fb::TetRec> tet; std::vector<double> tet_cent; std::vector<int> tet_mark, tet_nbr_off, tet_nbr;

@@ -320,6 +320,90 @@ bool fb_host_col_windows(fb_ctx* c, int max_window) {
     return true;
 }
 
+// Block-JDS tables of the HBM-roofline SpMV (k_spmv_jds).  Rows are cut into blocks of R consecutive
+// rows; inside a block the rows are (stably) sorted by decreasing length and stored as jagged
+// diagonals: diagonal j holds the j-th entry of every row longer than j, so that thread t of the
+// CTA walks "its" row with perfectly coalesced loads and NO padding.  Columns are replaced by 16-bit
+// positions inside the block's window (the sorted distinct columns the block touches).
+bool fb_host_jds_build(fb_ctx* c, int R, int max_window) {
+    const int n = c->n_dofs;
+    const int nb = (n + R - 1) / R;
+    c->jds_R = R; c->jds_nb = nb;
+    c->jds_perm.assign((size_t) nb * R, 0); c->jds_len.assign((size_t) nb * R, 0); c->jds_slot.assign(n, 0);
+    c->jds_jdp.assign(nb + 1, 0);
+    std::vector<int> maxlen(nb, 0);
+    // pass 1: per-block row order and jagged-diagonal counts
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < nb; ++b) {
+        const int r0 = b * R, nr = std::min(R, n - r0);
+        std::vector<int> ord(nr);
+        std::iota(ord.begin(), ord.end(), 0);
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int q) {
+            return c->rowptr[r0 + a + 1] - c->rowptr[r0 + a] > c->rowptr[r0 + q + 1] - c->rowptr[r0 + q];
+        });
+        for (int t = 0; t < nr; ++t) {
+            const int len = c->rowptr[r0 + ord[t] + 1] - c->rowptr[r0 + ord[t]];
+            c->jds_perm[(size_t) b * R + t] = (unsigned short) ord[t];
+            c->jds_len[(size_t) b * R + t] = (unsigned short) std::min(len, 65535);
+            c->jds_slot[r0 + ord[t]] = (unsigned short) t;
+        }
+        maxlen[b] = c->rowptr[r0 + ord[0] + 1] - c->rowptr[r0 + ord[0]];
+    }
+    for (int b = 0; b < nb; ++b) {
+        if (maxlen[b] > 60000) return false;
+        c->jds_jdp[b + 1] = c->jds_jdp[b] + maxlen[b] + 1;
+    }
+    c->jds_jd.assign(c->jds_jdp[nb], 0);
+    std::vector<std::vector<int>> win(nb);
+    c->col16.assign(c->nnz, 0);
+    bool ok = true;
+#pragma omp parallel
+    {
+        std::vector<int> buf;
+#pragma omp for schedule(dynamic, 16)
+        for (int b = 0; b < nb; ++b) {
+            const int r0 = b * R, nr = std::min(R, n - r0);
+            int* jd = &c->jds_jd[c->jds_jdp[b]];
+            // jd[j] = entries stored before diagonal j = sum_{j' < j} #rows longer than j'
+            int t_active = nr;
+            jd[0] = 0;
+            for (int j = 0; j < maxlen[b]; ++j) {
+                while (t_active > 0 && (int) c->jds_len[(size_t) b * R + t_active - 1] <= j) --t_active;
+                jd[j + 1] = jd[j] + t_active;
+            }
+            const int k0 = c->rowptr[r0], k1 = c->rowptr[r0 + nr];
+            buf.assign(c->col.begin() + k0, c->col.begin() + k1);
+            std::sort(buf.begin(), buf.end());
+            buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
+            if ((int) buf.size() > max_window) {
+#pragma omp atomic write
+                ok = false;
+                continue;
+            }
+            for (int t = 0; t < nr; ++t) {
+                const int r = r0 + c->jds_perm[(size_t) b * R + t];
+                for (int k = c->rowptr[r]; k < c->rowptr[r + 1]; ++k)
+                    c->col16[(size_t) k0 + jd[k - c->rowptr[r]] + t] =
+                        (unsigned short) (std::lower_bound(buf.begin(), buf.end(), c->col[k]) - buf.begin());
+            }
+            win[b] = buf;
+        }
+    }
+    if (!ok) return false;
+    c->win_off.assign(nb + 1, 0);
+    int wmax = 0;
+    for (int b = 0; b < nb; ++b) {
+        c->win_off[b + 1] = c->win_off[b] + (int) win[b].size();
+        wmax = std::max(wmax, (int) win[b].size());
+    }
+    c->win_list.resize(c->win_off[nb]);
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < nb; ++b) std::copy(win[b].begin(), win[b].end(), c->win_list.begin() + c->win_off[b]);
+    c->win_max = wmax;
+    c->jds_maxlen = *std::max_element(maxlen.begin(), maxlen.end());
+    return true;
+}
+
 // =======================================================================================
 //  Interpolator precompute tables.  The arithmetic below must reproduce the reference's
 //  tables bit for bit (cell location is compared bit-exactly), hence the expression order

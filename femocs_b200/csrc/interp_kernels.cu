@@ -18,6 +18,10 @@
 //
 // These kernels are latency/L2-bound (mesh tables of the native meshes are a few MB and stay
 // in the 126 MB L2); the mandatory HBM traffic is 24 B in + 44 B out per point.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace fb {
@@ -200,6 +204,48 @@ __global__ void __launch_bounds__(128) k_chain_sweep(Tables T, long n, const dou
     const bool ch = (cell != prev[i]);
     dirty_next[i] = ch;
     if (ch) *changed = 1;
+}
+
+// The whole fix-point iteration of the chained-guess recurrence in ONE cooperative launch: Jacobi
+// sweeps separated by grid-wide barriers, convergence flag on the device (three rotating flags so
+// that resetting the next flag never races with readers of the previous one), result copied to
+// `out`.  No host round trip; flags[3] returns the number of sweeps.
+template <class Fam>
+__global__ void __launch_bounds__(128) k_chain_fixpoint(Tables T, long n, const double* __restrict__ pts, const int* __restrict__ scan,
+                                                        int* bufA, int* bufB, unsigned char* dirtyA, unsigned char* dirtyB,
+                                                        int first_guess, int* flags, int* __restrict__ out) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const long tid = (long) blockIdx.x * blockDim.x + threadIdx.x, stride = (long) gridDim.x * blockDim.x;
+    const int* prev = scan; int* next = bufA;                  // the first sweep reads `scan`, which is never written
+    unsigned char* dcur = dirtyA; unsigned char* dprev = dirtyB;   // dprev is not read in the first sweep
+    int sweep = 0;
+    while (true) {
+        if (tid == 0) flags[(sweep + 1) % 3] = 0;
+        bool any = false;
+        for (long i = tid; i < n; i += stride) {
+            // buffers written by other CTAs in the previous sweep are read through L2 (ld.global.cg)
+            const bool need = sweep == 0 || (i > 0 && __ldcg(&dprev[i - 1]));
+            const int old = __ldcg(&prev[i]);
+            if (!need) { next[i] = old; dcur[i] = 0; continue; }
+            const int guess = (i == 0) ? first_guess : abs(__ldcg(&prev[i - 1]));
+            int cell;
+            if (!try_guess<Fam>(T, ldp(pts, i), guess, cell)) cell = scan[i];
+            next[i] = cell;
+            const bool ch = (cell != old);
+            dcur[i] = ch;
+            any |= ch;
+        }
+        if (any) atomicOr(&flags[sweep % 3], 1);
+        grid.sync();
+        const int changed = *((volatile int*) &flags[sweep % 3]);
+        prev = next;
+        next = (prev == bufA) ? bufB : bufA;
+        unsigned char* t = dcur; dcur = dprev; dprev = t;
+        ++sweep;
+        if (!changed) break;
+    }
+    for (long i = tid; i < n; i += stride) out[i] = __ldcg(&prev[i]);
+    if (tid == 0) flags[3] = sweep;
 }
 
 // ---- hexahedra -------------------------------------------------------------------------
@@ -590,35 +636,41 @@ void launch_pack_points(fb_ctx* c, long n, const double* x, const double* y, con
     c->launches++;
 }
 
-// chained-guess location for n points already on the device; returns base-family cells in c->d_cellsA or B
+// chained-guess location for n points already on the device: brute-force guess-free scan, then the
+// fix-point of the guess chain in one cooperative launch.  Result (base-family cells) in c->d_scan2.
+template <class Fam>
+static int chain_fixpoint(fb_ctx* c, const Tables& T, long n, const double* d_pts, int first_guess) {
+    auto kern = k_chain_fixpoint<Fam>;
+    if (c->chain_blocks_per_sm == 0) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 128, 0);
+        c->chain_blocks_per_sm = std::max(1, nb);
+    }
+    const long want = (n + 127) / 128;
+    const int grid = (int) std::min<long>(want, (long) c->chain_blocks_per_sm * c->n_sm);
+    const double* a2 = d_pts; const int* a3 = c->d_scan.p; int* a4 = c->d_cellsA.p; int* a5 = c->d_cellsB.p;
+    unsigned char* a6 = c->d_dirtyA.p; unsigned char* a7 = c->d_dirtyB.p; int a8 = first_guess; int* a9 = c->d_flag.p; int* a10 = c->d_scan2.p;
+    Tables t = T; long nn = n;
+    void* args[] = {&t, &nn, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*) kern, dim3(grid), dim3(128), args, 0, c->stream);
+    if (e != cudaSuccess) return c->fail(FB_ERR_CUDA, "locate chain launch failed: %s", cudaGetErrorString(e));
+    c->launches++;
+    return FB_OK;
+}
+
 int launch_locate_chain(fb_ctx* c, int dim, int rank, long n, const double* d_pts, int** result) {
     const Tables T = make_tables(c);
     const unsigned g = (unsigned) ((n + 127) / 128);
     // abs(-1) = 1 is the first guess of the reference loop (SolutionReader.cpp:145, InterpolatorCells.cpp:443);
     // hex/quad ranks divide it by 4/3 (:1539, :1955)
     const int first_guess = (rank == 3) ? 0 : 1;
-    int* changed = c->d_flag.p;
     if (dim == 2) k_scan_cells<TriFam, 64><<<g, 128, 0, c->stream>>>(T, n, d_pts, c->d_scan.p);
     else k_scan_cells<TetFam, 64><<<g, 128, 0, c->stream>>>(T, n, d_pts, c->d_scan.p);
     c->launches++;
-    int* prev = c->d_scan.p; int* next = c->d_cellsA.p;
-    unsigned char* dp = c->d_dirtyA.p; unsigned char* dn = c->d_dirtyB.p;
-    int* h_changed = (int*) c->pin_out.p;
-    for (long sweep = 0; sweep <= n; ++sweep) {
-        cudaMemsetAsync(changed, 0, sizeof(int), c->stream);
-        if (dim == 2) k_chain_sweep<TriFam><<<g, 128, 0, c->stream>>>(T, n, d_pts, c->d_scan.p, prev, next, dp, dn, first_guess, sweep == 0, changed);
-        else k_chain_sweep<TetFam><<<g, 128, 0, c->stream>>>(T, n, d_pts, c->d_scan.p, prev, next, dp, dn, first_guess, sweep == 0, changed);
-        c->launches++;
-        cudaMemcpyAsync(h_changed, changed, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
-        cudaError_t e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) return c->fail(FB_ERR_CUDA, "locate chain sweep failed: %s", cudaGetErrorString(e));
-        int* cur = next;
-        next = (cur == c->d_cellsA.p) ? c->d_cellsB.p : c->d_cellsA.p;
-        prev = cur;
-        std::swap(dp, dn);
-        if (!*h_changed) break;
-    }
-    *result = prev;
+    cudaMemsetAsync(c->d_flag.p, 0, 4 * sizeof(int), c->stream);
+    const int rc = (dim == 2) ? chain_fixpoint<TriFam>(c, T, n, d_pts, first_guess) : chain_fixpoint<TetFam>(c, T, n, d_pts, first_guess);
+    if (rc) return rc;
+    *result = c->d_scan2.p;
     return FB_OK;
 }
 

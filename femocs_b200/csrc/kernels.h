@@ -14,6 +14,7 @@ void launch_neumann(fb_ctx* c);
 void launch_set_bc(fb_ctx* c, const int* d_dofs, int n, double value);
 void launch_apply_bc_matrix(fb_ctx* c);
 void launch_apply_bc_rhs(fb_ctx* c);
+void launch_csr_to_jds(fb_ctx* c);
 void launch_cg_init(fb_ctx* c, int lanes);
 void launch_cg_iteration(fb_ctx* c, int lanes);
 void launch_cg_spmv(fb_ctx* c, int lanes);

@@ -488,6 +488,95 @@ __global__ void __launch_bounds__(THREADS) k_spmv_window(int n_blocks, const int
 }
 
 // ---------------------------------------------------------------------------------------
+// Block-JDS SpMV (the HBM-roofline kernel; tables from fb_host_jds_build).  One CTA = one block of
+// R = blockDim.x consecutive rows; thread t owns the t-th longest row of the block and walks it
+// diagonal by diagonal:  k = base + jd[j] + t  -> val (8 B) and the 16-bit window position are read
+// perfectly coalesced with NO padding and NO shared-memory staging of products; the input vector is
+// read from the block's window in shared memory (staged once per block from sorted, dense global
+// addresses).  Per-row summation is in column order = the sequential CSR order (deterministic).
+// L1/LSU work per 32 non-zeros: ~2 (val) + 0.5 (col16) + shared-memory gather, vs ~26 wavefronts for
+// the per-non-zero global gather of plain CSR, which is what capped those kernels at 0.45-0.65 of peak.
+// DRAM traffic ~ 10 B per non-zero + windows, i.e. BELOW the algorithmic 12 nnz + 4(n+1) + 16 n bytes.
+// ---------------------------------------------------------------------------------------
+__global__ void k_csr_to_jds(int n, int R, const int* __restrict__ rowptr, const unsigned short* __restrict__ slot,
+                             const int* __restrict__ jdp, const int* __restrict__ jd, const double* __restrict__ val,
+                             double* __restrict__ val_jds) {
+    // 8 lanes per row
+    const int lane = threadIdx.x & 7;
+    for (long r = ((long) blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < n; r += ((long) gridDim.x * blockDim.x) >> 3) {
+        const int b = (int) (r / R);
+        const int base = rowptr[(long) b * R], lo = rowptr[r], hi = rowptr[r + 1], t = slot[r];
+        const int* __restrict__ jdb = jd + jdp[b];
+        for (int k = lo + lane; k < hi; k += 8) val_jds[(long) base + jdb[k - lo] + t] = val[k];
+    }
+}
+
+template <bool INIT, int R>
+__global__ void __launch_bounds__(R) k_spmv_jds(int n, int n_blocks, const int* __restrict__ rowptr,
+                                                const unsigned short* __restrict__ perm, const unsigned short* __restrict__ rlen,
+                                                const int* __restrict__ jdp, const int* __restrict__ jd,
+                                                const unsigned short* __restrict__ col16, const double* __restrict__ val,
+                                                const int* __restrict__ win_off, const int* __restrict__ win_list,
+                                                const double* __restrict__ xin, const double* __restrict__ rhs,
+                                                const double* __restrict__ dinv, double* __restrict__ out,
+                                                double* __restrict__ partial, unsigned* counter, CgScalars* __restrict__ cgs,
+                                                double* __restrict__ alpha_out, int wcap, int jcap) {
+    if (!INIT && cgs->done) return;
+    extern __shared__ double s_dyn[];
+    double* s_x = s_dyn;                      // wcap window entries
+    int* s_jd = (int*) (s_dyn + wcap);        // jcap + 1 diagonal offsets
+    const int tid = threadIdx.x;
+    double acc[2] = {0, 0};
+    for (int b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        const int r0 = b * R;
+        const int w0 = __ldg(&win_off[b]), nw = __ldg(&win_off[b + 1]) - w0;
+        const int j0 = __ldg(&jdp[b]), nj = __ldg(&jdp[b + 1]) - j0;          // maxlen + 1 offsets
+        const long base = __ldg(&rowptr[r0]);
+        const bool valid = r0 + tid < n;
+        const int len = valid ? (int) __ldg(&rlen[(long) r0 + tid]) : 0;
+        const int row = valid ? r0 + (int) __ldg(&perm[(long) r0 + tid]) : 0;
+        for (int i = tid; i < nw; i += R) s_x[i] = __ldg(&xin[__ldg(&win_list[w0 + i])]);
+        for (int i = tid; i < nj; i += R) s_jd[i] = __ldg(&jd[j0 + i]);
+        __syncthreads();
+        const double* __restrict__ vb = val + base + tid;
+        const unsigned short* __restrict__ cb = col16 + base + tid;
+        double sum = 0;
+        int j = 0;
+        for (; j + 4 <= len; j += 4) {         // 4 diagonals per trip: 8 independent loads in flight per thread
+            const int o0 = s_jd[j], o1 = s_jd[j + 1], o2 = s_jd[j + 2], o3 = s_jd[j + 3];
+            const double v0 = __ldcg(&vb[o0]), v1 = __ldcg(&vb[o1]), v2 = __ldcg(&vb[o2]), v3 = __ldcg(&vb[o3]);
+            const int c0 = __ldcg(&cb[o0]), c1 = __ldcg(&cb[o1]), c2 = __ldcg(&cb[o2]), c3 = __ldcg(&cb[o3]);
+            sum += v0 * s_x[c0]; sum += v1 * s_x[c1]; sum += v2 * s_x[c2]; sum += v3 * s_x[c3];
+        }
+        for (; j < len; ++j) {
+            const int o = s_jd[j];
+            sum += __ldcg(&vb[o]) * s_x[__ldcg(&cb[o])];
+        }
+        if (valid) {
+            if (INIT) {
+                const double g = sum - rhs[row];
+                out[row] = g;
+                acc[0] += g * g * dinv[row];
+                acc[1] += g * g;
+            } else {
+                out[row] = sum;
+                acc[0] += __ldg(&xin[row]) * sum;
+            }
+        }
+        __syncthreads();
+    }
+    double tot[2];
+    if (reduce_publish<2>(acc, partial, counter, tot)) {
+        if (INIT) {
+            cgs->gh = tot[0]; cgs->res2 = tot[1]; cgs->it = 0;
+            cgs->done = (tot[1] <= cgs->tol2) ? 1 : ((cgs->max_iter <= 0 || tot[1] != tot[1]) ? 2 : 0);
+        } else {
+            *alpha_out = cgs->gh / tot[0];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Persistent cooperative CG for the native (L2-resident) meshes: the WHOLE solve is one launch.
 // One CTA per SM owns a contiguous, nnz-balanced slice of rows for the entire solve: its matrix
 // values live in shared memory, its column indices in registers, its slices of x, g, d, h, 1/diag
@@ -499,17 +588,23 @@ __global__ void __launch_bounds__(THREADS) k_spmv_window(int n_blocks, const int
 // (deal.II SolverCG): h = A d; alpha = gh/(d.h); x += alpha d; g += alpha h; test |g|;
 // beta = g.Dinv g / gh; d = beta d - Dinv g.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double sum_partials(const double* p, int G) {
-    double s = 0;
-    for (int i = threadIdx.x & 31; i < G; i += 32) s += __ldcg(p + i);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    return s;       // bit-identical in every lane, warp and CTA
-}
+// All-to-all through L2 without a central counter: every CTA publishes {partials, sequence flag};
+// warp 0 of every CTA polls the G flags (message passing: data store, fence, flag store | flag load,
+// fence, data load), then adds the G partials in index order -> bit-identical totals in all CTAs.
+// Partials are double-buffered by sequence parity: a CTA can run at most one phase ahead of the
+// slowest one, so a slot is never overwritten while somebody still reads it.
+struct GridComm {
+    double* part;        // [2][NVMAX][G]
+    int* flag;           // [G]
+    int G, seq;
+};
+constexpr int PERS_NV = 2;
 
 template <int NV>
-__device__ __forceinline__ void block_publish(double (&v)[NV], double (*s_red)[32], double* partial, int G) {
+__device__ __forceinline__ void grid_allreduce(GridComm& gc, double (&v)[NV], double (*s_red)[32], double (&tot)[NV]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    ++gc.seq;
+    double* slot = gc.part + (size_t) (gc.seq & 1) * PERS_NV * gc.G;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         double x = v[k];
@@ -517,25 +612,52 @@ __device__ __forceinline__ void block_publish(double (&v)[NV], double (*s_red)[3
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (lane == 0) s_red[k][warp] = x;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    __syncthreads();            // also orders this CTA's global stores (d slice) before the flag below
+    if (warp == 0) {
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                double t = 0;
+                for (int w = 0; w < nwarp; ++w) t += s_red[k][w];
+                __stcg(&slot[(size_t) k * gc.G + blockIdx.x], t);
+            }
+            __threadfence();
+            *((volatile int*) &gc.flag[blockIdx.x]) = gc.seq;
+        }
+        bool ready;
+        do {                     // every lane polls its (up to 8) flags in one batch of independent loads
+            ready = true;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = lane + 32 * j;
+                if (i < gc.G) ready &= (*((volatile int*) &gc.flag[i]) >= gc.seq);
+            }
+        } while (!__all_sync(0xffffffffu, ready));
+        __threadfence();
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            double t = 0;
-            for (int w = 0; w < nwarp; ++w) t += s_red[k][w];
-            __stcg(&partial[(size_t) k * G + blockIdx.x], t);
+            double x = 0;
+            for (int i = lane; i < gc.G; i += 32) x += __ldcg(&slot[(size_t) k * gc.G + i]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) s_red[k][0] = x;
         }
     }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) tot[k] = s_red[k][0];
+    __syncthreads();            // s_red is reused by the next call
 }
 
 template <int THREADS, int PT>
 __global__ void __launch_bounds__(THREADS, 1) k_cg_persistent(const int* __restrict__ cta_row, const int* __restrict__ rowptr,
                                                               const int* __restrict__ col, const double* __restrict__ val,
                                                               const double* __restrict__ rhs, const double* __restrict__ dinv_g,
-                                                              double* x_g, double* d_g, double* partial, CgScalars* cgs,
-                                                              int cap, int rmax) {
-    cg::grid_group grid = cg::this_grid();
+                                                              double* x_g, double* d_g, double* partial, int* flags, CgScalars* cgs,
+                                                              int cap, int rmax, long long* dbg) {
     extern __shared__ double smem[];
+    long long t_ph[6] = {0, 0, 0, 0, 0, 0}, t_last = clock64();
+    auto lap = [&](int k) { if (dbg) { const long long t = clock64(); t_ph[k] += t - t_last; t_last = t; } };
     double* s_val = smem;
     double* s_prod = s_val + cap;
     double* s_x = s_prod + cap;
@@ -544,12 +666,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_cg_persistent(const int* __restr
     double* s_h = s_d + rmax;
     double* s_dinv = s_h + rmax;
     int* s_rp = (int*) (s_dinv + rmax);
-    __shared__ double s_red[2][32];
-    const int G = gridDim.x, tid = threadIdx.x;
+    __shared__ double s_red[PERS_NV][32];
+    const int tid = threadIdx.x;
+    GridComm gc = {partial, flags, (int) gridDim.x, 0};
     const int r0 = cta_row[blockIdx.x], nr = cta_row[blockIdx.x + 1] - r0;
     const int k0 = rowptr[r0], cnt = rowptr[r0 + nr] - k0;
-    double* partA = partial;             // phase A: d.h
-    double* partB = partial + G;         // phase B: g.Dinv g, g.g
 
     int cidx[PT];
 #pragma unroll
@@ -562,48 +683,58 @@ __global__ void __launch_bounds__(THREADS, 1) k_cg_persistent(const int* __restr
     for (int r = tid; r < nr; r += THREADS) { s_x[r] = x_g[r0 + r]; s_dinv[r] = dinv_g[r0 + r]; }
     __syncthreads();
 
-    auto spmv = [&](const double* vec) {          // s_h = (A vec) on the CTA's rows; vec is gathered through L2
+    // s_h = (A vec) on the CTA's rows; vec is gathered through L2 (other CTAs wrote it).  Four lanes add
+    // one row (fixed order: lane-strided partial sums, then a 4-lane butterfly), so the ~150-entry rows of
+    // the tet vertices do not serialise the phase.
+    auto spmv = [&](const double* vec) {
 #pragma unroll
         for (int u = 0; u < PT; ++u)
             if (cidx[u] >= 0) s_prod[tid + u * THREADS] = s_val[tid + u * THREADS] * __ldcg(&vec[cidx[u]]);
         __syncthreads();
-        for (int r = tid; r < nr; r += THREADS) {
+        const int sub = tid & 3;
+        for (int rb = 0; rb < nr; rb += THREADS / 4) {          // block-uniform trip count
+            const int r = rb + (tid >> 2);
             double sum = 0;
-            for (int j = s_rp[r]; j < s_rp[r + 1]; ++j) sum += s_prod[j];
-            s_h[r] = sum;
+            if (r < nr)
+                for (int j = s_rp[r] + sub; j < s_rp[r + 1]; j += 4) sum += s_prod[j];
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            if (r < nr && sub == 0) s_h[r] = sum;
         }
+        __syncthreads();
     };
 
     const double tol2 = cgs->tol2;
     const int max_iter = cgs->max_iter;
     // ---- start: g = A x - b (deal.II SolverCG), d = -Dinv g ----
     spmv(x_g);
-    double acc[2] = {0, 0};
+    double acc[2] = {0, 0}, tot[2];
     for (int r = tid; r < nr; r += THREADS) {
         const double g = s_h[r] - rhs[r0 + r];
         s_g[r] = g;
         acc[0] += g * g * s_dinv[r];
         acc[1] += g * g;
     }
-    block_publish<2>(acc, s_red, partB, G);
-    grid.sync();
-    double gh = sum_partials(partB, G);
-    double res2 = sum_partials(partB + G, G);
+    grid_allreduce<2>(gc, acc, s_red, tot);
+    double gh = tot[0], res2 = tot[1];
     int it = 0;
     int done = (res2 <= tol2) ? 1 : ((max_iter <= 0 || res2 != res2) ? 2 : 0);
     if (!done) {
         for (int r = tid; r < nr; r += THREADS) { const double d = -s_dinv[r] * s_g[r]; s_d[r] = d; __stcg(&d_g[r0 + r], d); }
-        grid.sync();
+        double z[1] = {0}, zt[1];
+        grid_allreduce<1>(gc, z, s_red, zt);          // barrier: every slice of d is visible
     }
     while (!done) {
-        // phase A
+        // phase A: h = A d, alpha = gh / (d.h)
+        lap(5);
         spmv(d_g);
-        double a[1] = {0};
+        double a[1] = {0}, at[1];
         for (int r = tid; r < nr; r += THREADS) a[0] += s_d[r] * s_h[r];
-        block_publish<1>(a, s_red, partA, G);
-        grid.sync();
-        // phase B
-        const double alpha = gh / sum_partials(partA, G);
+        lap(0);
+        grid_allreduce<1>(gc, a, s_red, at);
+        lap(1);
+        // phase B: x += alpha d, g += alpha h, |g|, g.Dinv g
+        const double alpha = gh / at[0];
         acc[0] = 0; acc[1] = 0;
         for (int r = tid; r < nr; r += THREADS) {
             s_x[r] += alpha * s_d[r];
@@ -612,14 +743,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_cg_persistent(const int* __restr
             acc[0] += g * g * s_dinv[r];
             acc[1] += g * g;
         }
-        block_publish<2>(acc, s_red, partB, G);
-        grid.sync();
-        // phase C
-        const double ghn = sum_partials(partB, G);
-        res2 = sum_partials(partB + G, G);
+        lap(2);
+        grid_allreduce<2>(gc, acc, s_red, tot);
+        lap(3);
+        // phase C: convergence test (deal.II SolverControl: success first), d = beta d - Dinv g
+        res2 = tot[1];
         ++it;
-        const double beta = ghn / gh;
-        gh = ghn;
+        const double beta = tot[0] / gh;
+        gh = tot[0];
         if (res2 <= tol2) done = 1;
         else if (it >= max_iter || res2 != res2) done = 2;
         if (!done) {
@@ -628,9 +759,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_cg_persistent(const int* __restr
                 s_d[r] = d;
                 __stcg(&d_g[r0 + r], d);
             }
-            grid.sync();
+            double z[1] = {0}, zt[1];
+            lap(4);
+            grid_allreduce<1>(gc, z, s_red, zt);      // barrier: every slice of the new d is visible
         }
     }
+    if (dbg && tid == 0 && blockIdx.x < 4) for (int k = 0; k < 6; ++k) dbg[6 * blockIdx.x + k] = t_ph[k];
     for (int r = tid; r < nr; r += THREADS) x_g[r0 + r] = s_x[r];
     if (blockIdx.x == 0 && tid == 0) { cgs->gh = gh; cgs->res2 = res2; cgs->it = it; cgs->done = done; }
 }
@@ -699,7 +833,7 @@ void stream_block_shape(int kernel, int& chunk, int& maxrows) {
 int choose_lanes(const fb_ctx* c) {
     // 0 selects the row-block streaming kernel (option "spmv_kernel": -1 auto, 0 stream, else lanes per row)
     if (c->spmv_kernel >= 0) return c->spmv_kernel;
-    if (c->nnz >= 4000000) return 201;
+    if (c->nnz >= 4000000) return 300;
     const double avg = c->n_dofs ? (double) c->nnz / c->n_dofs : 1.0;
     if (avg > 48) return 32;
     if (avg > 20) return 8;
@@ -734,6 +868,13 @@ void launch_apply_bc_matrix(fb_ctx* c) {
     c->launches++;
 }
 
+void launch_csr_to_jds(fb_ctx* c) {
+    const int g = grid_for(c, (long) c->n_dofs * 8, 256);
+    k_csr_to_jds<<<g, 256, 0, c->stream>>>(c->n_dofs, c->jds_R, c->d_rowptr.p, c->d_jds_slot.p, c->d_jds_jdp.p, c->d_jds_jd.p,
+                                           c->d_val.p, c->d_val_jds.p);
+    c->launches++;
+}
+
 void launch_apply_bc_rhs(fb_ctx* c) {
     const int g = grid_for(c, c->n_dofs, 256);
     k_apply_bc_rhs<<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_bcflag.p, c->d_bcval.p, c->d_dinv.p, c->d_w.p, c->d_rhs.p, c->d_x.p);
@@ -744,6 +885,22 @@ template <bool INIT>
 static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, double* alpha) {
     unsigned* counter = (unsigned*) (c->d_partial.p + c->d_partial.n - 8);
     double* part = c->d_partial.p;
+    if (lanes >= 300) {         // block-JDS kernel (300: 256 rows per block, 301: 128)
+        const int nb = c->jds_nb;
+        const size_t smem = sizeof(double) * (size_t) c->win_cap + sizeof(int) * ((size_t) c->jds_maxlen + 2);
+#define FB_JDS(RR, OCC) do {                                                                                                        \
+        auto kern = k_spmv_jds<INIT, RR>;                                                                                           \
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);                                        \
+        const int occ = std::max(1, std::min((OCC), (int) (200 * 1024 / (smem + 1024))));                                           \
+        const int g = std::min(nb, c->n_sm * occ);                                                                                  \
+        kern<<<g, RR, smem, c->stream>>>(c->n_dofs, nb, c->d_rowptr.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_jdp.p, c->d_jds_jd.p, \
+                                         c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin, c->d_rhs.p, c->d_dinv.p, \
+                                         out, part, counter, c->d_cg.p, alpha, c->win_cap, c->jds_maxlen); } while (0)
+        if (c->jds_R == 128) FB_JDS(128, 16); else FB_JDS(256, 8);
+#undef FB_JDS
+        c->launches++;
+        return;
+    }
     if (lanes >= 200) {         // windowed streaming kernel (variants 200.. are tuning points)
         const int nb = c->n_rowblk;
 #define FB_WINDOW(T, P, OCC) do {                                                                                                   \
@@ -832,8 +989,9 @@ static cudaError_t launch_persistent_pt(fb_ctx* c, size_t smem) {
     if (e != cudaSuccess) return e;
     const int* a0 = c->d_cta_row.p; const int* a1 = c->d_rowptr.p; const int* a2 = c->d_col.p; const double* a3 = c->d_val.p;
     const double* a4 = c->d_rhs.p; const double* a5 = c->d_dinv.p; double* a6 = c->d_x.p; double* a7 = c->d_d.p;
-    double* a8 = c->d_partial.p; CgScalars* a9 = c->d_cg.p; int a10 = c->pers_cap, a11 = c->pers_rmax;
-    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10, &a11};
+    double* a8 = c->d_partial.p; int* a8b = c->d_pers_flags.p; CgScalars* a9 = c->d_cg.p; int a10 = c->pers_cap, a11 = c->pers_rmax;
+    long long* a12 = c->cg_debug ? c->d_dbg.p : nullptr;
+    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a8b, &a9, &a10, &a11, &a12};
     return cudaLaunchCooperativeKernel((void*) kern, dim3(c->pers_grid), dim3(512), args, smem, c->stream);
 }
 
@@ -841,7 +999,7 @@ bool persistent_eligible(fb_ctx* c) {
     if (c->cg_persistent == 0 || c->n_dofs <= 0) return false;
     if (c->pers_grid == 0) {
         // nnz-balanced contiguous row slices, one per SM
-        const int G = std::min(c->n_sm, std::max(1, c->n_dofs / 8));
+        const int G = std::min(c->pers_ctas > 0 ? std::min(c->pers_ctas, c->n_sm) : c->n_sm, std::max(1, c->n_dofs / 8));
         std::vector<int> cta_row(G + 1, c->n_dofs);
         cta_row[0] = 0;
         int r = 0, cap = 0, rmax = 0;
@@ -865,9 +1023,13 @@ bool persistent_eligible(fb_ctx* c) {
 cudaError_t launch_cg_persistent(fb_ctx* c) {
     if (!c->pers_uploaded) {
         cudaError_t e = c->d_cta_row.upload(c->pers_cta_row, c->stream);
+        if (e == cudaSuccess) e = c->d_pers_flags.alloc(c->n_sm);
+        if (e == cudaSuccess) e = c->d_dbg.alloc(64);
         if (e != cudaSuccess) return e;
         c->pers_uploaded = true;
     }
+    cudaError_t ez = cudaMemsetAsync(c->d_pers_flags.p, 0, c->n_sm * sizeof(int), c->stream);    // sequence flags restart at 0
+    if (ez != cudaSuccess) return ez;
     const size_t smem = 16 * (size_t) c->pers_cap + 40 * (size_t) c->pers_rmax + 4 * ((size_t) c->pers_rmax + 2);
     const int pt = (c->pers_cap + 511) / 512;
     c->launches++;

@@ -12,11 +12,11 @@ import bench  # noqa: E402
 import femocs_b200 as fb  # noqa: E402
 
 levels = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-kernels = [int(k) for k in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 100, 103, 200, 201, 202, 203, 204]
+kernels = [int(k) for k in sys.argv[2].split(",")] if len(sys.argv) > 2 else [100, 200, 300, 301]
 orders = [int(k) for k in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1]
 # native mesh: single-launch persistent CG vs CUDA-graph multi-kernel CG
 m = bench.load_native()
-for pers in (1, 0):
+for pers in ((1, 0) if os.environ.get('SWEEP_NATIVE', '1') == '1' else ()):
     ctx = fb.Context(0)
     ctx.set_option("cg_persistent", pers)
     s = fb.PoissonSolver(ctx, fb.FieldConfig(cg_tolerance=1e-9))
