@@ -16,6 +16,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-ccbin", "/usr/bin/g++",
 # compared bit-for-bit with the reference, which is built for baseline x86-64.
 UNITS = [
     ("host_setup.cpp", []),
+    ("partition.cpp", []),
     ("poisson_kernels.cu", []),
     ("interp_kernels.cu", ["-fmad=false"]),
     ("api.cu", []),

@@ -46,8 +46,8 @@ fb_ctx* fb_create(int device) {
         g_create_error = cudaGetErrorString(e); delete c; return nullptr;
     }
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
-    // partials: 2 values x max grid (n_sm * 16 blocks) + counter slot, zero-initialised once
-    const size_t np = 2 * (size_t) c->n_sm * 16 + 8;
+    // partials: 2 values x max grid (n_sm * 32 blocks) + counter slot, zero-initialised once
+    const size_t np = 2 * (size_t) c->n_sm * 32 + 8;
     if (c->d_partial.alloc(np) != cudaSuccess || c->d_cg.alloc(2) != cudaSuccess || c->d_minmax.alloc(2) != cudaSuccess ||
         c->d_flag.alloc(4) != cudaSuccess || c->pin_out.reserve(4096) != cudaSuccess) {
         g_create_error = "device allocation failed"; fb_destroy(c); return nullptr;
@@ -224,8 +224,11 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
         FB_CUDA(c, cudaStreamSynchronize(s));
         spmv += h->it;
         if (c->cg_debug) {          // per-phase SM cycles of CTAs 0..3 (diagnostics)
-            long long t[24];
+            long long t[32];
             cudaMemcpy(t, c->d_dbg.p, sizeof t, cudaMemcpyDeviceToHost);
+            const long long na = std::max(1LL, t[29]);
+            fprintf(stderr, "[fb cg_debug] allreduce on cta 0 (avg cycles over %lld calls): block-reduce+sync %lld | publish+release %lld | poll %lld | fence+read %lld | exit syncs %lld\n",
+                    t[29], t[24] / na, t[25] / na, t[26] / na, t[27] / na, t[28] / na);
             for (int b = 0; b < 4; ++b)
                 fprintf(stderr, "[fb cg_debug] cta %d it %d cycles/it: spmv %lld | reduce(d.h) %lld | update %lld | reduce(g.g) %lld | direction %lld | barrier(d) %lld\n",
                         b, h->it, t[6 * b] / std::max(1, h->it), t[6 * b + 1] / std::max(1, h->it), t[6 * b + 2] / std::max(1, h->it),
@@ -234,7 +237,7 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
     } else {
         int lanes = fb::choose_lanes(c);
         if (lanes >= 300) {                        // block-JDS SpMV: tables once per mesh, values once per assemble
-            const int R = (lanes == 301) ? 128 : 256;
+            const int R = (lanes == 301) ? 128 : (lanes == 302 ? 512 : 256);
             if (!c->jds_ready || c->jds_R != R) {
                 drop_graph(c);
                 if (fb_host_jds_build(c, R, 8192)) {
@@ -244,7 +247,9 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
                     FB_CUDA(c, c->d_jds_perm.upload(c->jds_perm, s)); FB_CUDA(c, c->d_jds_len.upload(c->jds_len, s));
                     FB_CUDA(c, c->d_jds_slot.upload(c->jds_slot, s));
                     FB_CUDA(c, c->d_jds_jdp.upload(c->jds_jdp, s)); FB_CUDA(c, c->d_jds_jd.upload(c->jds_jd, s));
-                    FB_CUDA(c, c->d_val_jds.alloc(c->nnz));
+                    FB_CUDA(c, c->d_jds_base.upload(c->jds_base, s));
+                    FB_CUDA(c, c->d_val_jds.alloc((size_t) c->jds_size + 8));
+                    FB_CUDA(c, c->d_val_jds.zero(s));                  // padding entries stay 0
                     FB_CUDA(c, cudaStreamSynchronize(s));
                     std::vector<unsigned short>().swap(c->col16);      // host copies no longer needed
                     std::vector<int>().swap(c->win_list);

@@ -86,6 +86,23 @@ struct fb_ctx {
     int cg_persistent = -1;                  // -1 auto (single cooperative launch when the system fits on chip), 0 off
     int cg_profile = 0;                      // iterations per solve bracketed with CUDA events (0 = off)
 
+    // ---- multi-GPU partition (one process per GPU; see partition.cpp) ----
+    int rank = 0, world = 1;
+    void* nccl_comm = nullptr;               // ncclComm_t
+    bool host_only = false;                  // plan-only context for CPU tests of the partition logic (no CUDA)
+    int n_cols = 0;                          // local columns = owned rows + ghosts (== n_dofs on one GPU)
+    int part_n_owned = -1;                   // >= 0: partitioned import, local vertices [0, part_n_owned) are owned
+    long n_dofs_global = 0; int n_vert_global = 0, n_cells_global = 0;
+    std::vector<int> part_l2g;               // local vertex (= local dof) -> global solver vertex id
+    std::vector<int> part_owner;             // owner rank of every local vertex
+    std::vector<int> part_cell_g;            // local cell -> global solver cell id
+    std::vector<int> send_off, send_idx, recv_off;   // halo plan: per peer, owned dofs to send / ghost segment to receive
+    fb::DevBuf<int> d_send_idx, d_l2g, d_gcell2local;
+    fb::DevBuf<double> d_sendbuf, d_red;
+    // import intermediates (phase 1 -> phase 2)
+    std::vector<int> h_cv, h_v2c_off, h_v2c; std::vector<unsigned char> h_isb;
+    double bb_mn[3] = {0, 0, 0}, bb_mx[3] = {0, 0, 0};
+
     // ---- host copies of the mesh (femocs numbering) ----
     int n_nodes = 0, n_hex = 0;
     std::vector<double> xyz;
@@ -103,7 +120,7 @@ struct fb_ctx {
     int win_max = 0, win_cap = 0;
     // block-JDS layout of the HBM-roofline SpMV
     int jds_R = 0, jds_nb = 0, jds_maxlen = 0; bool jds_ready = false, jds_val_dirty = true;
-    std::vector<unsigned short> jds_perm, jds_len, jds_slot; std::vector<int> jds_jdp, jds_jd;
+    std::vector<unsigned short> jds_perm, jds_len, jds_slot; std::vector<int> jds_jdp, jds_jd, jds_base; int jds_size = 0;
     struct BFace { int cell, face, id; };
     std::vector<BFace> bfaces;
     std::vector<int> copper_dofs, top_dofs;  // Dirichlet candidates
@@ -118,7 +135,7 @@ struct fb_ctx {
     fb::DevBuf<int> d_cells;                 // 8*n_cells dof ids (lexicographic)
     fb::DevBuf<int> d_rowptr, d_col, d_diagpos, d_rowblk, d_win_off, d_win_list;
     fb::DevBuf<unsigned short> d_col16, d_jds_perm, d_jds_len, d_jds_slot;
-    fb::DevBuf<int> d_jds_jdp, d_jds_jd; fb::DevBuf<double> d_val_jds;
+    fb::DevBuf<int> d_jds_jdp, d_jds_jd, d_jds_base; fb::DevBuf<double> d_val_jds;
     fb::DevBuf<double> d_val, d_val_save;
     fb::DevBuf<double> d_rhs, d_x, d_g, d_d, d_h, d_dinv, d_z, d_w;
     fb::DevBuf<int> d_topfaces;              // 4 dof ids per top (Neumann) face
@@ -179,6 +196,10 @@ bool fb_host_row_blocks(fb_ctx* c, int chunk, int maxrows);
 bool fb_host_col_windows(fb_ctx* c, int max_window);
 bool fb_host_jds_build(fb_ctx* c, int R, int max_window);
 int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
+int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
+int fb_host_import_phase2(fb_ctx* c);
+// partition.cpp: cuts the mesh for c->rank of c->world and runs phase 1 on the local sub-mesh
+int fb_host_partition_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
 struct fb_interp_tables {
     std::vector<fb::TetRec> tet; std::vector<double> tet_cent; std::vector<int> tet_mark, tet_nbr_off, tet_nbr;
     std::vector<fb::TriRec> tri; std::vector<double> tri_cent; std::vector<int> tri_nbr_off, tri_nbr;

@@ -68,7 +68,11 @@ inline uint64_t spread21(uint64_t v) {          // interleave helper for 63-bit 
 
 }  // namespace
 
-int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {
+// Phase 1: vertex compaction, orientation, boundary faces and the extremes of their centres (c->bb_mn/bb_mx).
+// On one GPU phase 2 follows directly; with a partitioned mesh the extremes are first reduced over the ranks
+// (mark_boundary of the reference works on the global mesh).  c->part_n_owned >= 0 marks a partition: the
+// local vertices [0, part_n_owned) are owned, the rest are ghosts, and only faces touching an owned vertex count.
+int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {
     c->mesh_ok = false;
     c->n_nodes = n_nodes; c->n_hex = n_hex;
     c->xyz.assign(xyz, xyz + 3 * (size_t) n_nodes);
@@ -93,7 +97,8 @@ int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* he
         if (c->node2vert[i] == 0) { c->node2vert[i] = (int) c->vert2node.size(); c->vert2node.push_back(i); }
     const int n_vert = c->n_vert = (int) c->vert2node.size();
 
-    std::vector<int> cv(8 * (size_t) n_cells);       // lexicographic vertex ids
+    std::vector<int>& cv = c->h_cv;                  // lexicographic vertex ids
+    cv.assign(8 * (size_t) n_cells, 0);
 #pragma omp parallel for schedule(static)
     for (int ce = 0; ce < n_cells; ++ce) {
         const int* h = &hex8[8 * (size_t) c->cell2hex[ce]];
@@ -120,15 +125,19 @@ int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* he
     }
 
     // ---- vertex -> cells adjacency (CSR) ----
-    std::vector<int> v2c_off(n_vert + 1, 0);
+    std::vector<int>& v2c_off = c->h_v2c_off; std::vector<int>& v2c = c->h_v2c;
+    v2c_off.assign(n_vert + 1, 0);
     for (size_t i = 0; i < cv.size(); ++i) v2c_off[cv[i] + 1]++;
     for (int v = 0; v < n_vert; ++v) v2c_off[v + 1] += v2c_off[v];
-    std::vector<int> v2c(cv.size()), fill(v2c_off.begin(), v2c_off.end() - 1);
+    v2c.assign(cv.size(), 0);
+    std::vector<int> fill(v2c_off.begin(), v2c_off.end() - 1);
     for (int ce = 0; ce < n_cells; ++ce)
         for (int k = 0; k < 8; ++k) v2c[fill[cv[8 * (size_t) ce + k]]++] = ce;     // ascending cell ids per vertex
 
     // ---- boundary faces: a face is interior iff another cell holds all 4 of its vertices ----
-    std::vector<unsigned char> is_b(6 * (size_t) n_cells, 0);
+    std::vector<unsigned char>& is_b = c->h_isb;
+    is_b.assign(6 * (size_t) n_cells, 0);
+    const int n_owned_v = c->part_n_owned >= 0 ? c->part_n_owned : n_vert;
 #pragma omp parallel for schedule(dynamic, 4096)
     for (int ce = 0; ce < n_cells; ++ce)
         for (int f = 0; f < 6; ++f) {
@@ -148,7 +157,9 @@ int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* he
                 }
                 interior = (hit == 4);
             }
-            is_b[6 * (size_t) ce + f] = !interior;
+            // partition: a face without an owned vertex may border a cell this rank does not hold -> not ours to judge
+            const bool ours = fv[0] < n_owned_v || fv[1] < n_owned_v || fv[2] < n_owned_v || fv[3] < n_owned_v;
+            is_b[6 * (size_t) ce + f] = !interior && ours;
         }
     auto face_centre = [&](int ce, int f, double ctr[3]) {      // TriaAccessor::center: vertex mean
         double s[3] = {0, 0, 0};
@@ -167,6 +178,24 @@ int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* he
                 double p[3]; face_centre(ce, f, p);
                 for (int d = 0; d < 3; ++d) { mx[d] = std::max(mx[d], p[d]); mn[d] = std::min(mn[d], p[d]); }
             }
+    for (int d = 0; d < 3; ++d) { c->bb_mn[d] = mn[d]; c->bb_mx[d] = mx[d]; }
+    return FB_OK;
+}
+
+// Phase 2: boundary ids from the (global) extremes, DoF numbering, sparsity of the owned rows, Dirichlet candidates.
+int fb_host_import_phase2(fb_ctx* c) {
+    const double* xyz = c->xyz.data();
+    const int n_vert = c->n_vert, n_cells = c->n_cells;
+    std::vector<int>& cv = c->h_cv; std::vector<int>& v2c_off = c->h_v2c_off; std::vector<int>& v2c = c->h_v2c;
+    const double* mn = c->bb_mn; const double* mx = c->bb_mx;
+    auto face_centre = [&](int ce, int f, double ctr[3]) {      // TriaAccessor::center: vertex mean
+        double s[3] = {0, 0, 0};
+        for (int k = 0; k < 4; ++k) {
+            const double* p = &xyz[3 * (size_t) c->vert2node[cv[8 * (size_t) ce + FACE_VERTS[f][k]]]];
+            s[0] += p[0]; s[1] += p[1]; s[2] += p[2];
+        }
+        ctr[0] = s[0] / 4.0; ctr[1] = s[1] / 4.0; ctr[2] = s[2] / 4.0;
+    };
     const double eps = 1e-6;
     c->n_top_faces = 0;
     for (auto& bf : c->bfaces) {
@@ -180,7 +209,11 @@ int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* he
     // ---- DoF numbering ----
     c->vertex2dof.assign(n_vert, -1);
     int n_dofs = 0;
-    if (c->dof_order == 1) {
+    if (c->part_n_owned >= 0) {
+        // partition: the local vertex order (owned first, ghosts grouped by owner) IS the numbering
+        for (int v = 0; v < n_vert; ++v) c->vertex2dof[v] = v;
+        n_dofs = n_vert;
+    } else if (c->dof_order == 1) {
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
         for (int v = 0; v < n_vert; ++v)
             for (int d = 0; d < 3; ++d) {
@@ -205,8 +238,11 @@ int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* he
         for (size_t i = 0; i < cv.size(); ++i)
             if (c->vertex2dof[cv[i]] < 0) c->vertex2dof[cv[i]] = n_dofs++;
     }
+    c->n_cols = n_dofs;
+    const int n_all = n_dofs;
+    if (c->part_n_owned >= 0) n_dofs = c->part_n_owned;       // rows = owned dofs only
     c->n_dofs = n_dofs;
-    c->dof2vertex.assign(n_dofs, -1);
+    c->dof2vertex.assign(n_all, -1);
     for (int v = 0; v < n_vert; ++v) c->dof2vertex[c->vertex2dof[v]] = v;
     c->cells_dof.resize(cv.size());
 #pragma omp parallel for schedule(static)
@@ -250,7 +286,7 @@ int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* he
     }
 
     // ---- Dirichlet candidate dofs per boundary id (interpolate_boundary_values) ----
-    std::vector<unsigned char> on_cu(n_dofs, 0), on_top(n_dofs, 0);
+    std::vector<unsigned char> on_cu(n_all, 0), on_top(n_all, 0);
     for (const auto& bf : c->bfaces)
         for (int k = 0; k < 4; ++k) {
             const int d = c->cells_dof[8 * (size_t) bf.cell + FACE_VERTS[bf.face][k]];
@@ -258,9 +294,17 @@ int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* he
             if (bf.id == 8) on_top[d] = 1;
         }
     c->copper_dofs.clear(); c->top_dofs.clear();
-    for (int d = 0; d < n_dofs; ++d) { if (on_cu[d]) c->copper_dofs.push_back(d); if (on_top[d]) c->top_dofs.push_back(d); }
+    for (int d = 0; d < n_all; ++d) { if (on_cu[d]) c->copper_dofs.push_back(d); if (on_top[d]) c->top_dofs.push_back(d); }
+    std::vector<int>().swap(c->h_cv); std::vector<int>().swap(c->h_v2c_off); std::vector<int>().swap(c->h_v2c);
+    std::vector<unsigned char>().swap(c->h_isb);
     c->mesh_ok = true;
     return FB_OK;
+}
+
+int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {
+    c->part_n_owned = -1;
+    const int rc = fb_host_import_phase1(c, xyz, n_nodes, hex8, hex_marker, n_hex);
+    return rc ? rc : fb_host_import_phase2(c);
 }
 
 // Row blocks of the streaming SpMV: whole rows, <= chunk non-zeros and <= maxrows rows per block.
@@ -330,7 +374,7 @@ bool fb_host_jds_build(fb_ctx* c, int R, int max_window) {
     const int nb = (n + R - 1) / R;
     c->jds_R = R; c->jds_nb = nb;
     c->jds_perm.assign((size_t) nb * R, 0); c->jds_len.assign((size_t) nb * R, 0); c->jds_slot.assign(n, 0);
-    c->jds_jdp.assign(nb + 1, 0);
+    c->jds_jdp.assign(nb + 1, 0); c->jds_base.assign(nb + 1, 0);
     std::vector<int> maxlen(nb, 0);
     // pass 1: per-block row order and jagged-diagonal counts
 #pragma omp parallel for schedule(static)
@@ -354,8 +398,27 @@ bool fb_host_jds_build(fb_ctx* c, int R, int max_window) {
         c->jds_jdp[b + 1] = c->jds_jdp[b] + maxlen[b] + 1;
     }
     c->jds_jd.assign(c->jds_jdp[nb], 0);
+    // every diagonal is padded to an even number of entries (zero value, window position 0) so that a
+    // thread can fetch the entries of two neighbouring rows with one 16-byte load
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < nb; ++b) {
+        const int nr = std::min(R, n - b * R);
+        int* jd = &c->jds_jd[c->jds_jdp[b]];
+        int t_active = nr;
+        jd[0] = 0;
+        for (int j = 0; j < maxlen[b]; ++j) {
+            while (t_active > 0 && (int) c->jds_len[(size_t) b * R + t_active - 1] <= j) --t_active;
+            jd[j + 1] = jd[j] + ((t_active + 1) & ~1);
+        }
+    }
+    for (int b = 0; b < nb; ++b) {
+        const long next = (long) c->jds_base[b] + c->jds_jd[c->jds_jdp[b + 1] - 1];
+        if (next > 2147483000L) return false;
+        c->jds_base[b + 1] = (int) next;
+    }
+    c->jds_size = c->jds_base[nb];
     std::vector<std::vector<int>> win(nb);
-    c->col16.assign(c->nnz, 0);
+    c->col16.assign((size_t) c->jds_size + 8, 0);
     bool ok = true;
 #pragma omp parallel
     {
@@ -363,15 +426,9 @@ bool fb_host_jds_build(fb_ctx* c, int R, int max_window) {
 #pragma omp for schedule(dynamic, 16)
         for (int b = 0; b < nb; ++b) {
             const int r0 = b * R, nr = std::min(R, n - r0);
-            int* jd = &c->jds_jd[c->jds_jdp[b]];
-            // jd[j] = entries stored before diagonal j = sum_{j' < j} #rows longer than j'
-            int t_active = nr;
-            jd[0] = 0;
-            for (int j = 0; j < maxlen[b]; ++j) {
-                while (t_active > 0 && (int) c->jds_len[(size_t) b * R + t_active - 1] <= j) --t_active;
-                jd[j + 1] = jd[j] + t_active;
-            }
+            const int* jd = &c->jds_jd[c->jds_jdp[b]];      // jd[j] = (padded) entries stored before diagonal j
             const int k0 = c->rowptr[r0], k1 = c->rowptr[r0 + nr];
+            const size_t base = (size_t) c->jds_base[b];
             buf.assign(c->col.begin() + k0, c->col.begin() + k1);
             std::sort(buf.begin(), buf.end());
             buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
@@ -383,7 +440,7 @@ bool fb_host_jds_build(fb_ctx* c, int R, int max_window) {
             for (int t = 0; t < nr; ++t) {
                 const int r = r0 + c->jds_perm[(size_t) b * R + t];
                 for (int k = c->rowptr[r]; k < c->rowptr[r + 1]; ++k)
-                    c->col16[(size_t) k0 + jd[k - c->rowptr[r]] + t] =
+                    c->col16[base + jd[k - c->rowptr[r]] + t] =
                         (unsigned short) (std::lower_bound(buf.begin(), buf.end(), c->col[k]) - buf.begin());
             }
             win[b] = buf;

@@ -499,69 +499,78 @@ __global__ void __launch_bounds__(THREADS) k_spmv_window(int n_blocks, const int
 // DRAM traffic ~ 10 B per non-zero + windows, i.e. BELOW the algorithmic 12 nnz + 4(n+1) + 16 n bytes.
 // ---------------------------------------------------------------------------------------
 __global__ void k_csr_to_jds(int n, int R, const int* __restrict__ rowptr, const unsigned short* __restrict__ slot,
-                             const int* __restrict__ jdp, const int* __restrict__ jd, const double* __restrict__ val,
-                             double* __restrict__ val_jds) {
+                             const int* __restrict__ jbase, const int* __restrict__ jdp, const int* __restrict__ jd,
+                             const double* __restrict__ val, double* __restrict__ val_jds) {
     // 8 lanes per row
     const int lane = threadIdx.x & 7;
     for (long r = ((long) blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < n; r += ((long) gridDim.x * blockDim.x) >> 3) {
         const int b = (int) (r / R);
-        const int base = rowptr[(long) b * R], lo = rowptr[r], hi = rowptr[r + 1], t = slot[r];
+        const int base = jbase[b], lo = rowptr[r], hi = rowptr[r + 1], t = slot[r];
         const int* __restrict__ jdb = jd + jdp[b];
         for (int k = lo + lane; k < hi; k += 8) val_jds[(long) base + jdb[k - lo] + t] = val[k];
     }
 }
 
+// R rows per block, R / 2 threads: thread t owns the rows in slots 2t and 2t+1 (len0 >= len1) and fetches
+// their entries of a diagonal with ONE 16-byte value load and ONE 4-byte window-position load.
 template <bool INIT, int R>
-__global__ void __launch_bounds__(R) k_spmv_jds(int n, int n_blocks, const int* __restrict__ rowptr,
-                                                const unsigned short* __restrict__ perm, const unsigned short* __restrict__ rlen,
-                                                const int* __restrict__ jdp, const int* __restrict__ jd,
-                                                const unsigned short* __restrict__ col16, const double* __restrict__ val,
-                                                const int* __restrict__ win_off, const int* __restrict__ win_list,
-                                                const double* __restrict__ xin, const double* __restrict__ rhs,
-                                                const double* __restrict__ dinv, double* __restrict__ out,
-                                                double* __restrict__ partial, unsigned* counter, CgScalars* __restrict__ cgs,
-                                                double* __restrict__ alpha_out, int wcap, int jcap) {
+__global__ void __launch_bounds__(R / 2) k_spmv_jds(int n, int n_blocks, const int* __restrict__ jbase,
+                                                    const unsigned short* __restrict__ perm, const unsigned short* __restrict__ rlen,
+                                                    const int* __restrict__ jdp, const int* __restrict__ jd,
+                                                    const unsigned short* __restrict__ col16, const double* __restrict__ val,
+                                                    const int* __restrict__ win_off, const int* __restrict__ win_list,
+                                                    const double* __restrict__ xin, const double* __restrict__ rhs,
+                                                    const double* __restrict__ dinv, double* __restrict__ out,
+                                                    double* __restrict__ partial, unsigned* counter, CgScalars* __restrict__ cgs,
+                                                    double* __restrict__ alpha_out, int wcap, int jcap) {
     if (!INIT && cgs->done) return;
+    constexpr int T = R / 2;
     extern __shared__ double s_dyn[];
     double* s_x = s_dyn;                      // wcap window entries
-    int* s_jd = (int*) (s_dyn + wcap);        // jcap + 1 diagonal offsets
+    int* s_jd = (int*) (s_dyn + wcap);        // jcap + 1 diagonal offsets (in 2-entry units)
     const int tid = threadIdx.x;
     double acc[2] = {0, 0};
     for (int b = blockIdx.x; b < n_blocks; b += gridDim.x) {
         const int r0 = b * R;
         const int w0 = __ldg(&win_off[b]), nw = __ldg(&win_off[b + 1]) - w0;
         const int j0 = __ldg(&jdp[b]), nj = __ldg(&jdp[b + 1]) - j0;          // maxlen + 1 offsets
-        const long base = __ldg(&rowptr[r0]);
-        const bool valid = r0 + tid < n;
-        const int len = valid ? (int) __ldg(&rlen[(long) r0 + tid]) : 0;
-        const int row = valid ? r0 + (int) __ldg(&perm[(long) r0 + tid]) : 0;
-        for (int i = tid; i < nw; i += R) s_x[i] = __ldg(&xin[__ldg(&win_list[w0 + i])]);
-        for (int i = tid; i < nj; i += R) s_jd[i] = __ldg(&jd[j0 + i]);
+        const long base = __ldg(&jbase[b]);
+        const int sl0 = r0 + 2 * tid, sl1 = sl0 + 1;
+        const int len0 = sl0 < n ? (int) __ldg(&rlen[sl0]) : 0, len1 = sl1 < n ? (int) __ldg(&rlen[sl1]) : 0;
+        const int row0 = sl0 < n ? r0 + (int) __ldg(&perm[sl0]) : 0, row1 = sl1 < n ? r0 + (int) __ldg(&perm[sl1]) : 0;
+        for (int i = tid; i < nw; i += T) s_x[i] = __ldg(&xin[__ldg(&win_list[w0 + i])]);
+        for (int i = tid; i < nj; i += T) s_jd[i] = __ldg(&jd[j0 + i]) >> 1;
         __syncthreads();
-        const double* __restrict__ vb = val + base + tid;
-        const unsigned short* __restrict__ cb = col16 + base + tid;
-        double sum = 0;
-        int j = 0;
-        for (; j + 4 <= len; j += 4) {         // 4 diagonals per trip: 8 independent loads in flight per thread
-            const int o0 = s_jd[j], o1 = s_jd[j + 1], o2 = s_jd[j + 2], o3 = s_jd[j + 3];
-            const double v0 = __ldcg(&vb[o0]), v1 = __ldcg(&vb[o1]), v2 = __ldcg(&vb[o2]), v3 = __ldcg(&vb[o3]);
-            const int c0 = __ldcg(&cb[o0]), c1 = __ldcg(&cb[o1]), c2 = __ldcg(&cb[o2]), c3 = __ldcg(&cb[o3]);
-            sum += v0 * s_x[c0]; sum += v1 * s_x[c1]; sum += v2 * s_x[c2]; sum += v3 * s_x[c3];
+        const double2* __restrict__ vb = reinterpret_cast<const double2*>(val + base) + tid;
+        const ushort2* __restrict__ cb = reinterpret_cast<const ushort2*>(col16 + base) + tid;
+        double sum0 = 0, sum1 = 0;
+        // register double-buffered pipeline: the loads of the next 4 diagonals are issued before the current
+        // 4 are consumed, so every thread keeps 4-8 x (16 B + 4 B) loads in flight without draining
+        double2 va[4], vb2[4];
+        ushort2 ca[4], cb2[4];
+#define FB_ISSUE(JJ, V, C)                                                                     \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u)                                          \
+            if ((JJ) + u < len0) { const int o = s_jd[(JJ) + u]; V[u] = __ldcg(&vb[o]); C[u] = __ldcg(&cb[o]); }
+#define FB_CONSUME(JJ, V, C)                                                                   \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                        \
+            if ((JJ) + u < len0) sum0 += V[u].x * s_x[C[u].x];                                 \
+            if ((JJ) + u < len1) sum1 += V[u].y * s_x[C[u].y];                                 \
         }
-        for (; j < len; ++j) {
-            const int o = s_jd[j];
-            sum += __ldcg(&vb[o]) * s_x[__ldcg(&cb[o])];
+        FB_ISSUE(0, va, ca)
+        for (int j = 0; j < len0; j += 8) {
+            FB_ISSUE(j + 4, vb2, cb2)
+            FB_CONSUME(j, va, ca)
+            FB_ISSUE(j + 8, va, ca)
+            FB_CONSUME(j + 4, vb2, cb2)
         }
-        if (valid) {
-            if (INIT) {
-                const double g = sum - rhs[row];
-                out[row] = g;
-                acc[0] += g * g * dinv[row];
-                acc[1] += g * g;
-            } else {
-                out[row] = sum;
-                acc[0] += __ldg(&xin[row]) * sum;
-            }
+#undef FB_ISSUE
+#undef FB_CONSUME
+        if (INIT) {
+            if (sl0 < n) { const double g = sum0 - rhs[row0]; out[row0] = g; acc[0] += g * g * dinv[row0]; acc[1] += g * g; }
+            if (sl1 < n) { const double g = sum1 - rhs[row1]; out[row1] = g; acc[0] += g * g * dinv[row1]; acc[1] += g * g; }
+        } else {
+            if (sl0 < n) { out[row0] = sum0; acc[0] += __ldg(&xin[row0]) * sum0; }
+            if (sl1 < n) { out[row1] = sum1; acc[0] += __ldg(&xin[row1]) * sum1; }
         }
         __syncthreads();
     }
@@ -593,10 +602,15 @@ __global__ void __launch_bounds__(R) k_spmv_jds(int n, int n_blocks, const int* 
 // fence, data load), then adds the G partials in index order -> bit-identical totals in all CTAs.
 // Partials are double-buffered by sequence parity: a CTA can run at most one phase ahead of the
 // slowest one, so a slot is never overwritten while somebody still reads it.
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) { int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 struct GridComm {
     double* part;        // [2][NVMAX][G]
     int* flag;           // [G]
     int G, seq;
+    long long* dbg;
 };
 constexpr int PERS_NV = 2;
 
@@ -605,6 +619,8 @@ __device__ __forceinline__ void grid_allreduce(GridComm& gc, double (&v)[NV], do
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     ++gc.seq;
     double* slot = gc.part + (size_t) (gc.seq & 1) * PERS_NV * gc.G;
+    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+    if (gc.dbg) t0 = clock64();
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         double x = v[k];
@@ -614,26 +630,29 @@ __device__ __forceinline__ void grid_allreduce(GridComm& gc, double (&v)[NV], do
     }
     __syncthreads();            // also orders this CTA's global stores (d slice) before the flag below
     if (warp == 0) {
-        if (lane == 0) {
+        if (gc.dbg) t1 = clock64();
 #pragma unroll
-            for (int k = 0; k < NV; ++k) {
-                double t = 0;
-                for (int w = 0; w < nwarp; ++w) t += s_red[k][w];
-                __stcg(&slot[(size_t) k * gc.G + blockIdx.x], t);
-            }
-            __threadfence();
-            *((volatile int*) &gc.flag[blockIdx.x]) = gc.seq;
+        for (int k = 0; k < NV; ++k) {       // warp 0 adds the per-warp partials (fixed order)
+            double t = (lane < nwarp) ? s_red[k][lane] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) __stcg(&slot[(size_t) k * gc.G + blockIdx.x], t);
         }
+        // release store: the partials above and (through the bar.sync) the d slice written by the other
+        // threads of this CTA are visible to whoever observes the flag
+        if (lane == 0) st_release_gpu(&gc.flag[blockIdx.x], gc.seq);
+        if (gc.dbg) t2 = clock64();
         bool ready;
         do {                     // every lane polls its (up to 8) flags in one batch of independent loads
             ready = true;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int i = lane + 32 * j;
-                if (i < gc.G) ready &= (*((volatile int*) &gc.flag[i]) >= gc.seq);
+                if (i < gc.G) ready &= (ld_relaxed_gpu(&gc.flag[i]) >= gc.seq);
             }
         } while (!__all_sync(0xffffffffu, ready));
-        __threadfence();
+        if (gc.dbg) t3 = clock64();
+        fence_acq_rel_gpu();     // acquire side of the message passing
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             double x = 0;
@@ -642,11 +661,16 @@ __device__ __forceinline__ void grid_allreduce(GridComm& gc, double (&v)[NV], do
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
             if (lane == 0) s_red[k][0] = x;
         }
+        if (gc.dbg) t4 = clock64();
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < NV; ++k) tot[k] = s_red[k][0];
     __syncthreads();            // s_red is reused by the next call
+    if (gc.dbg && threadIdx.x == 0 && blockIdx.x == 0) {
+        const long long t5 = clock64();
+        gc.dbg[24] += t1 - t0; gc.dbg[25] += t2 - t1; gc.dbg[26] += t3 - t2; gc.dbg[27] += t4 - t3; gc.dbg[28] += t5 - t4; gc.dbg[29] += 1;
+    }
 }
 
 template <int THREADS, int PT>
@@ -668,7 +692,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_cg_persistent(const int* __restr
     int* s_rp = (int*) (s_dinv + rmax);
     __shared__ double s_red[PERS_NV][32];
     const int tid = threadIdx.x;
-    GridComm gc = {partial, flags, (int) gridDim.x, 0};
+    GridComm gc = {partial, flags, (int) gridDim.x, 0, dbg};
     const int r0 = cta_row[blockIdx.x], nr = cta_row[blockIdx.x + 1] - r0;
     const int k0 = rowptr[r0], cnt = rowptr[r0 + nr] - k0;
 
@@ -833,7 +857,7 @@ void stream_block_shape(int kernel, int& chunk, int& maxrows) {
 int choose_lanes(const fb_ctx* c) {
     // 0 selects the row-block streaming kernel (option "spmv_kernel": -1 auto, 0 stream, else lanes per row)
     if (c->spmv_kernel >= 0) return c->spmv_kernel;
-    if (c->nnz >= 4000000) return 300;
+    if (c->nnz >= 4000000) return 302;
     const double avg = c->n_dofs ? (double) c->nnz / c->n_dofs : 1.0;
     if (avg > 48) return 32;
     if (avg > 20) return 8;
@@ -870,7 +894,7 @@ void launch_apply_bc_matrix(fb_ctx* c) {
 
 void launch_csr_to_jds(fb_ctx* c) {
     const int g = grid_for(c, (long) c->n_dofs * 8, 256);
-    k_csr_to_jds<<<g, 256, 0, c->stream>>>(c->n_dofs, c->jds_R, c->d_rowptr.p, c->d_jds_slot.p, c->d_jds_jdp.p, c->d_jds_jd.p,
+    k_csr_to_jds<<<g, 256, 0, c->stream>>>(c->n_dofs, c->jds_R, c->d_rowptr.p, c->d_jds_slot.p, c->d_jds_base.p, c->d_jds_jdp.p, c->d_jds_jd.p,
                                            c->d_val.p, c->d_val_jds.p);
     c->launches++;
 }
@@ -893,10 +917,10 @@ static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, 
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);                                        \
         const int occ = std::max(1, std::min((OCC), (int) (200 * 1024 / (smem + 1024))));                                           \
         const int g = std::min(nb, c->n_sm * occ);                                                                                  \
-        kern<<<g, RR, smem, c->stream>>>(c->n_dofs, nb, c->d_rowptr.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_jdp.p, c->d_jds_jd.p, \
+        kern<<<g, (RR) / 2, smem, c->stream>>>(c->n_dofs, nb, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_jdp.p, c->d_jds_jd.p, \
                                          c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin, c->d_rhs.p, c->d_dinv.p, \
                                          out, part, counter, c->d_cg.p, alpha, c->win_cap, c->jds_maxlen); } while (0)
-        if (c->jds_R == 128) FB_JDS(128, 16); else FB_JDS(256, 8);
+        if (c->jds_R == 128) FB_JDS(128, 24); else if (c->jds_R == 512) FB_JDS(512, 6); else FB_JDS(256, 12);
 #undef FB_JDS
         c->launches++;
         return;
@@ -1029,6 +1053,7 @@ cudaError_t launch_cg_persistent(fb_ctx* c) {
         c->pers_uploaded = true;
     }
     cudaError_t ez = cudaMemsetAsync(c->d_pers_flags.p, 0, c->n_sm * sizeof(int), c->stream);    // sequence flags restart at 0
+    if (ez == cudaSuccess) ez = cudaMemsetAsync(c->d_dbg.p, 0, 64 * sizeof(long long), c->stream);
     if (ez != cudaSuccess) return ez;
     const size_t smem = 16 * (size_t) c->pers_cap + 40 * (size_t) c->pers_rmax + 4 * ((size_t) c->pers_rmax + 2);
     const int pt = (c->pers_cap + 511) / 512;

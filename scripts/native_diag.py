@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 import femocs_b200 as fb
 m = bench.load_native()
-for ctas in (148, 74, 37):
+for ctas in (148, 74):
     ctx = fb.Context(0)
     ctx.set_option("cg_persistent_ctas", ctas)
     s = fb.PoissonSolver(ctx, fb.FieldConfig(cg_tolerance=1e-9))

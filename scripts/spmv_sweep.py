@@ -12,7 +12,7 @@ import bench  # noqa: E402
 import femocs_b200 as fb  # noqa: E402
 
 levels = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-kernels = [int(k) for k in sys.argv[2].split(",")] if len(sys.argv) > 2 else [100, 200, 300, 301]
+kernels = [int(k) for k in sys.argv[2].split(",")] if len(sys.argv) > 2 else [100, 300, 301, 302]
 orders = [int(k) for k in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1]
 # native mesh: single-launch persistent CG vs CUDA-graph multi-kernel CG
 m = bench.load_native()
