@@ -256,15 +256,20 @@ def run_b200(args):
     log("[rank %d] X mesh: %d hexahedra, %d nodes (%.1f s)" % (rank, len(hexs), len(nodes), time.perf_counter() - t_setup))
 
     ctx = fb.Context(local)
+    if world > 1:
+        ctx.init_comm_torch(dist)                 # element-partitioned CG: one rank per GPU, NCCL inside the library
     ctx.set_option("cg_profile", 32)
     if args.dof_order is not None:
         ctx.set_option("dof_order", args.dof_order)
     solver = fb.PoissonSolver(ctx, fb.FieldConfig(E0=E0, cg_tolerance=CG_TOL, n_cg=N_CG, mode="transient"))
     t0 = time.perf_counter()
     assert solver.import_mesh(nodes, hexs, mk), "import_mesh failed"
-    log("[rank %d] import_mesh: %d DoF, nnz %d (%.1f s host setup + upload)" % (rank, solver.n_dofs, solver.nnz, time.perf_counter() - t0))
+    part = ctx.partition()
+    log("[rank %d] import_mesh: %d rows (+%d ghosts) of %d DoF, local nnz %d (%.1f s host setup + upload)"
+        % (rank, part["n_rows"], part["n_ghost"], solver.n_dofs_global, solver.nnz, time.perf_counter() - t0))
     del nodes, hexs, mk
-    n, nnz = solver.n_dofs, solver.nnz
+    n, nnz = solver.n_dofs_global, solver.nnz          # global DoF, rank-local non-zeros
+    n_loc = part["n_rows"]
     cf = Q_OVER_EPS0 * WSP
 
     # device-resident inputs (value leg) and pinned host buffers (e2e leg)
@@ -313,13 +318,13 @@ def run_b200(args):
     solve_ms, last_it, _ = solver.solve_stats()
     ms_e2e, iters_e2e, its_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup - 2))
 
-    # replicas: every rank solves its own copy of X (partitioned solve: see DESIGN.md "multi-GPU")
-    tot_iters = sum_over_ranks(iters); tot_iters_e2e = sum_over_ranks(iters_e2e)
-    value = n * tot_iters / (ms * 1e-3) / 1e9
-    e2e_value = n * tot_iters_e2e / (ms_e2e * 1e-3) / 1e9
+    # N > 1: ONE system, element-partitioned over the ranks (strong scaling): every rank runs the same iterations
+    value = n * iters / (ms * 1e-3) / 1e9
+    e2e_value = n * iters_e2e / (ms_e2e * 1e-3) / 1e9
     peak, peak_src = hbm_peak()
-    bytes_spmv = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n
-    bytes_iter = 12.0 * nnz + 4.0 * (n + 1) + 104.0 * n
+    nnz_all = sum_over_ranks(nnz)
+    bytes_spmv = 12.0 * nnz + 4.0 * (n_loc + 1) + 16.0 * n_loc          # this rank's share (rank 0 reports)
+    bytes_iter = 12.0 * nnz + 4.0 * (n_loc + 1) + 104.0 * n_loc
     achieved = bytes_spmv / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None
     iter_ms = solve_ms / max(1, last_it)
     traffic = None
@@ -333,15 +338,18 @@ def run_b200(args):
     line = {
         "metric": "poisson_cg_gdof_per_s", "value": value, "unit": "GDoF/s per CG iteration", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, {"n_dofs": n, "nnz": nnz, "n_cells": solver.n_cells, "parallelism": "replicas x%d" % world if world > 1 else "1 GPU",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, {"n_dofs": n, "nnz": int(nnz_all), "n_cells": part["n_cells_global"],
+                                          "parallelism": ("element-partitioned over %d GPUs (RCB), NCCL p2p halo + all-reduce; rank 0: %d rows, %d ghosts, %d halo values sent"
+                                                          % (world, part["n_rows"], part["n_ghost"], part["n_send"])) if world > 1 else "1 GPU",
                                           "cg_iterations_per_step": its, "converged": bool(all(i > 0 for i in its))}),
         "e2e": {"value": e2e_value, "unit": "GDoF/s per CG iteration", "h2d_bytes_per_step": int(pxyz.nbytes + pcell.nbytes),
                 "d2h_bytes_per_step": int(h_phi_np.nbytes + 16), "ms_per_step": ms_e2e / args.steps,
                 "call": "fb_poisson_setup + fb_poisson_assemble(host particles) + fb_poisson_solve + fb_check_limits + fb_export_solution"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_spmv_dot (CSR SpMV fused with the d.h dot product)",
+        "roofline": {"bound": "hbm", "kernel": "k_spmv_jds (block-JDS SpMV fused with the d.h dot product)" + (
+                         "; rank 0 share, timed INCLUDING the halo exchange and the dot-product all-reduce" if world > 1 else ""),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_spmv, "avg_launch_ms": spmv_ms, "samples": n_samp,

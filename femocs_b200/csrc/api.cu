@@ -7,6 +7,7 @@
 #include <string>
 
 #include "kernels.h"
+#include "nccl_dyn.h"
 
 static std::string g_create_error;
 
@@ -23,6 +24,38 @@ static int sync_check(fb_ctx* c, const char* what) {
 static void drop_graph(fb_ctx* c) {
     if (c->cg_graph) { cudaGraphExecDestroy(c->cg_graph); c->cg_graph = nullptr; }
     c->cg_graph_n = 0;
+}
+
+#define FB_NCCL(ctx, call)                                                                      \
+    do {                                                                                        \
+        ncclResult_t r__ = (call);                                                              \
+        if (r__ != ncclSuccess)                                                                 \
+            return (ctx)->fail(FB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, fb::Nccl::get().GetErrorString(r__), __FILE__, __LINE__); \
+    } while (0)
+
+// owner -> ghost copy of a dof vector (n_cols entries, ghosts behind the n_dofs owned rows): pack the owned
+// entries the peers need, then grouped point-to-point transfers over NVLink; receives land directly in the
+// contiguous ghost segment of each peer.  All on the context's stream.
+static int halo_exchange(fb_ctx* c, double* vec) {
+    if (c->world == 1) return FB_OK;
+    fb::Nccl& N = fb::Nccl::get();
+    ncclComm_t comm = (ncclComm_t) c->nccl_comm;
+    fb::launch_pack(c, vec);
+    FB_NCCL(c, N.GroupStart());
+    for (int p = 0; p < c->world; ++p) {
+        if (p == c->rank) continue;
+        const int ns = c->send_off[p + 1] - c->send_off[p], nr = c->recv_off[p + 1] - c->recv_off[p];
+        if (ns > 0) FB_NCCL(c, N.Send(c->d_sendbuf.p + c->send_off[p], ns, ncclDouble, p, comm, c->stream));
+        if (nr > 0) FB_NCCL(c, N.Recv(vec + c->n_dofs + c->recv_off[p], nr, ncclDouble, p, comm, c->stream));
+    }
+    FB_NCCL(c, N.GroupEnd());
+    return FB_OK;
+}
+
+static int allreduce(fb_ctx* c, double* buf, int n, ncclRedOp_t op) {
+    if (c->world == 1) return FB_OK;
+    FB_NCCL(c, fb::Nccl::get().AllReduce(buf, buf, n, ncclDouble, op, (ncclComm_t) c->nccl_comm, c->stream));
+    return FB_OK;
 }
 
 extern "C" {
@@ -59,7 +92,9 @@ fb_ctx* fb_create(int device) {
 
 void fb_destroy(fb_ctx* c) {
     if (!c) return;
+    if (c->host_only) { delete c; return; }
     cudaSetDevice(c->device);
+    if (c->nccl_comm) { cudaStreamSynchronize(c->stream); fb::Nccl::get().CommDestroy((ncclComm_t) c->nccl_comm); c->nccl_comm = nullptr; }
     drop_graph(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -88,6 +123,72 @@ int fb_set_option(fb_ctx* c, const char* key, double value) {
 }
 
 int fb_synchronize(fb_ctx* c) { return sync_check(c, "fb_synchronize"); }
+
+int fb_comm_unique_id(char* id128) {
+    fb::Nccl& N = fb::Nccl::get();
+    if (!N.ok) { g_create_error = std::string("NCCL unavailable: ") + N.why; return FB_ERR_CUDA; }
+    ncclUniqueId id;
+    if (N.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return FB_ERR_CUDA; }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return FB_OK;
+}
+
+int fb_comm_init(fb_ctx* c, int rank, int world, const char* id128) {
+    FB_REQUIRE(c, world >= 1 && rank >= 0 && rank < world && id128, "fb_comm_init: invalid rank / world");
+    FB_REQUIRE(c, !c->mesh_ok, "fb_comm_init: must precede fb_import_mesh");
+    c->rank = rank; c->world = world;
+    if (world == 1) return FB_OK;
+    fb::Nccl& N = fb::Nccl::get();
+    if (!N.ok) return c->fail(FB_ERR_CUDA, "NCCL unavailable: %s", N.why);
+    cudaSetDevice(c->device);
+    ncclUniqueId id; memcpy(&id, id128, 128);
+    ncclComm_t comm;
+    FB_NCCL(c, N.CommInitRank(&comm, world, id, rank));
+    c->nccl_comm = comm;
+    FB_CUDA(c, c->d_red.alloc(8));
+    return FB_OK;
+}
+
+// ---- host-only view of the partition (CPU tests of the N > 1 logic; no CUDA involved) ----
+fb_ctx* fb_plan_create(int rank, int world) {
+    fb_ctx* c = new fb_ctx();
+    c->host_only = true; c->rank = rank; c->world = world;
+    return c;
+}
+int fb_plan_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex, double* bbox6) {
+    FB_REQUIRE(c, c->host_only, "fb_plan_phase1: not a plan context");
+    const int rc = fb_host_partition_phase1(c, xyz, n_nodes, hex8, hex_marker, n_hex);
+    if (rc) return rc;
+    for (int d = 0; d < 3; ++d) { bbox6[d] = c->bb_mn[d]; bbox6[3 + d] = c->bb_mx[d]; }
+    return FB_OK;
+}
+int fb_plan_phase2(fb_ctx* c, const double* bbox6_global) {
+    FB_REQUIRE(c, c->host_only, "fb_plan_phase2: not a plan context");
+    for (int d = 0; d < 3; ++d) { c->bb_mn[d] = bbox6_global[d]; c->bb_mx[d] = bbox6_global[3 + d]; }
+    return fb_host_import_phase2(c);
+}
+// sizes: n_rows (owned), n_cols, nnz, n_cells_local, n_send, n_ghost, n_vert_global, n_cells_global
+int fb_plan_sizes(const fb_ctx* c, long* out8) {
+    out8[0] = c->n_dofs; out8[1] = c->n_cols; out8[2] = c->nnz; out8[3] = c->n_cells; out8[4] = (long) c->send_idx.size();
+    out8[5] = c->n_cols - c->n_dofs; out8[6] = c->n_vert_global; out8[7] = c->n_cells_global;
+    return FB_OK;
+}
+int fb_plan_get(const fb_ctx* c, int* local2global, int* owner, int* send_off, int* send_idx, int* recv_off, int* rowptr, int* col,
+                int* cells_dof, int* local_cell2global, int* copper_flag, int* top_flag) {
+    if (local2global) std::copy(c->part_l2g.begin(), c->part_l2g.end(), local2global);
+    if (owner) std::copy(c->part_owner.begin(), c->part_owner.end(), owner);
+    if (send_off) std::copy(c->send_off.begin(), c->send_off.end(), send_off);
+    if (send_idx) std::copy(c->send_idx.begin(), c->send_idx.end(), send_idx);
+    if (recv_off) std::copy(c->recv_off.begin(), c->recv_off.end(), recv_off);
+    if (rowptr) std::copy(c->rowptr.begin(), c->rowptr.end(), rowptr);
+    if (col) std::copy(c->col.begin(), c->col.end(), col);
+    if (cells_dof) std::copy(c->cells_dof.begin(), c->cells_dof.end(), cells_dof);
+    if (local_cell2global) std::copy(c->part_cell_g.begin(), c->part_cell_g.end(), local_cell2global);
+    if (copper_flag) { std::fill(copper_flag, copper_flag + c->n_cols, 0); for (int d : c->copper_dofs) copper_flag[d] = 1; }
+    if (top_flag) { std::fill(top_flag, top_flag + c->n_cols, 0); for (int d : c->top_dofs) top_flag[d] = 1; }
+    return FB_OK;
+}
 void* fb_get_stream(fb_ctx* c) { return (void*) c->stream; }
 
 // ------------------------------------------------------------------------------------------
@@ -96,10 +197,25 @@ int fb_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, c
     cudaSetDevice(c->device);
     c->setup_ok = c->assembled = c->matrix_ok = c->interp_ok = false;
     drop_graph(c);
-    int rc = fb_host_import_mesh(c, xyz, n_nodes, hex8, hex_marker, n_hex);
-    if (rc) return rc;
-    const int n = c->n_dofs;
     cudaStream_t s = c->stream;
+    int rc;
+    if (c->world > 1) {
+        // partitioned import: local sub-mesh, extremes of the boundary-face centres reduced over the ranks
+        FB_REQUIRE(c, c->nccl_comm, "fb_import_mesh: fb_comm_init has not been called");
+        if ((rc = fb_host_partition_phase1(c, xyz, n_nodes, hex8, hex_marker, n_hex))) return rc;
+        double* hb = (double*) c->pin_out.p;                 // [max(mx), max(-mn)]
+        for (int d = 0; d < 3; ++d) { hb[d] = c->bb_mx[d]; hb[3 + d] = -c->bb_mn[d]; }
+        FB_CUDA(c, cudaMemcpyAsync(c->d_red.p, hb, 6 * sizeof(double), cudaMemcpyHostToDevice, s));
+        if ((rc = allreduce(c, c->d_red.p, 6, ncclMax))) return rc;
+        FB_CUDA(c, cudaMemcpyAsync(hb, c->d_red.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        FB_CUDA(c, cudaStreamSynchronize(s));
+        for (int d = 0; d < 3; ++d) { c->bb_mx[d] = hb[d]; c->bb_mn[d] = -hb[3 + d]; }
+        if ((rc = fb_host_import_phase2(c))) return rc;
+    } else {
+        if ((rc = fb_host_import_mesh(c, xyz, n_nodes, hex8, hex_marker, n_hex))) return rc;
+        c->n_vert_global = c->n_vert; c->n_cells_global = c->n_cells; c->n_dofs_global = c->n_dofs;
+    }
+    const int n = c->n_cols;              // vectors indexed by column (owned rows + ghosts)
     // coordinates in DoF order
     std::vector<double> vxyz(3 * (size_t) n);
     for (int d = 0; d < n; ++d) {
@@ -126,6 +242,15 @@ int fb_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, c
         FB_CUDA(c, b->alloc(n));
     FB_CUDA(c, c->d_bcflag.alloc(n));
     FB_CUDA(c, cudaMemsetAsync(c->d_x.p, 0, n * sizeof(double), s));
+    if (c->world > 1) {
+        FB_CUDA(c, c->d_send_idx.upload(c->send_idx, s));
+        FB_CUDA(c, c->d_sendbuf.alloc(std::max<size_t>(1, c->send_idx.size())));
+        FB_CUDA(c, c->d_l2g.upload(c->part_l2g, s));
+        std::vector<int> g2l(c->n_cells_global, -1);
+        for (int lc = 0; lc < c->n_cells; ++lc) g2l[c->part_cell_g[lc]] = lc;
+        FB_CUDA(c, c->d_gcell2local.upload(g2l, s));
+        FB_CUDA(c, cudaStreamSynchronize(s));
+    }
     return sync_check(c, "fb_import_mesh");
 }
 
@@ -140,7 +265,7 @@ int fb_poisson_setup(fb_ctx* c, double field, double potential, int anode_is_dir
     cudaSetDevice(c->device);
     c->applied_field = field; c->applied_potential = potential; c->anode_dirichlet = anode_is_dirichlet;
     c->setup_ok = true; c->assembled = false; c->matrix_ok = false;
-    FB_CUDA(c, cudaMemsetAsync(c->d_x.p, 0, c->n_dofs * sizeof(double), c->stream));     // solution = dirichlet_bc_value (0)
+    FB_CUDA(c, cudaMemsetAsync(c->d_x.p, 0, c->n_cols * sizeof(double), c->stream));     // solution = dirichlet_bc_value (0)
     FB_CUDA(c, cudaMemsetAsync(c->d_rhs.p, 0, c->n_dofs * sizeof(double), c->stream));
     return FB_OK;
 }
@@ -153,20 +278,28 @@ static int assemble_impl(fb_ctx* c, int first_time, const double* d_pxyz, const 
         FB_CUDA(c, cudaMemsetAsync(c->d_val_save.p, 0, c->nnz * sizeof(double), s));
         fb::launch_assemble_stiffness(c, nullptr);
         // boundary values: copper = 0 (+ anode = V0 in Dirichlet mode); map semantics: later wins
-        FB_CUDA(c, cudaMemsetAsync(c->d_bcflag.p, 0, n * sizeof(int), s));
-        FB_CUDA(c, cudaMemsetAsync(c->d_bcval.p, 0, n * sizeof(double), s));
+        FB_CUDA(c, cudaMemsetAsync(c->d_bcflag.p, 0, c->n_cols * sizeof(int), s));
+        FB_CUDA(c, cudaMemsetAsync(c->d_bcval.p, 0, c->n_cols * sizeof(double), s));
         fb::DevBuf<int> tmp;
         std::vector<int> all(c->copper_dofs);
         all.insert(all.end(), c->top_dofs.begin(), c->top_dofs.end());
         FB_CUDA(c, tmp.upload(all, s));
         fb::launch_set_bc(c, tmp.p, (int) c->copper_dofs.size(), 0.0);
-        std::vector<unsigned char> mark(n, 0);
+        std::vector<unsigned char> mark(c->n_cols, 0);
         for (int d : c->copper_dofs) mark[d] = 1;
         if (c->anode_dirichlet) {
             fb::launch_set_bc(c, tmp.p + c->copper_dofs.size(), (int) c->top_dofs.size(), c->applied_potential);
             for (int d : c->top_dofs) mark[d] = 1;
         }
-        c->n_dirichlet = (int) std::count(mark.begin(), mark.end(), (unsigned char) 1);
+        c->n_dirichlet = (int) std::count(mark.begin(), mark.begin() + n, (unsigned char) 1);
+        if (c->world > 1) {
+            // a ghost dof may be constrained through a face this rank does not hold: take flag and value from the owner
+            fb::launch_flags_to_double(c, c->d_z.p);
+            int rc = halo_exchange(c, c->d_z.p);
+            if (rc) return rc;
+            fb::launch_double_to_ghost_flags(c, c->d_z.p);
+            if ((rc = halo_exchange(c, c->d_bcval.p))) return rc;
+        }
         fb::launch_apply_bc_matrix(c);      // val, Dirichlet lift (kept in d_w), dinv, diagpos
         c->jds_val_dirty = true;
         FB_CUDA(c, cudaStreamSynchronize(s));   // tmp goes out of scope
@@ -212,11 +345,12 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
     init.tol2 = abs_tol * abs_tol; init.max_iter = max_iter;
     fb::CgScalars* h = (fb::CgScalars*) c->pin_out.p;
     *h = init;
-    FB_CUDA(c, cudaEventRecord(c->ev0, s));
-    FB_CUDA(c, cudaMemcpyAsync(c->d_cg.p, h, sizeof(fb::CgScalars), cudaMemcpyHostToDevice, s));
     long spmv = 1;
     c->prof_samples = 0; c->prof_spmv_ms = c->prof_vec_ms = 0;
-    const bool persistent = c->cg_profile == 0 && fb::persistent_eligible(c);
+    const bool persistent = c->world == 1 && c->cg_profile == 0 && fb::persistent_eligible(c);
+    if (c->world > 1) h->red = c->d_red.p;
+    FB_CUDA(c, cudaEventRecord(c->ev0, s));
+    FB_CUDA(c, cudaMemcpyAsync(c->d_cg.p, h, sizeof(fb::CgScalars), cudaMemcpyHostToDevice, s));
     if (persistent) {
         // native meshes: the whole solve is ONE cooperative launch (matrix slice resident in shared memory)
         FB_CUDA(c, fb::launch_cg_persistent(c));
@@ -284,57 +418,103 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
                 }
             }
         }
-        fb::launch_cg_init(c, lanes);
-        // CUDA graph of cg_graph_iters iterations; kernels become no-ops once cgs->done is set
-        if (!c->cg_graph || c->cg_graph_n != c->cg_graph_iters || c->cg_graph_precond != lanes) {
-            drop_graph(c);
-            cudaGraph_t graph;
-            const long before = c->launches;
-            FB_CUDA(c, cudaStreamSynchronize(s));
-            FB_CUDA(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            for (int i = 0; i < c->cg_graph_iters; ++i) fb::launch_cg_iteration(c, lanes);
-            FB_CUDA(c, cudaStreamEndCapture(s, &graph));
-            c->launches = before;     // captured, not launched
-            FB_CUDA(c, cudaGraphInstantiate(&c->cg_graph, graph, 0));
-            cudaGraphDestroy(graph);
-            c->cg_graph_n = c->cg_graph_iters; c->cg_graph_precond = lanes;
-        }
-        // optional profile: the first cg_profile iterations run un-graphed, each bracketed by CUDA
-        // events on this stream (SpMV+dot | vector updates), for the live roofline figures of bench.py
-        int n_prof = 0;
-        if (c->cg_profile > 0) {
-            while ((int) c->prof_ev.size() < 3 * c->cg_profile) {
-                cudaEvent_t e; FB_CUDA(c, cudaEventCreate(&e)); c->prof_ev.push_back(e);
+        if (c->world > 1) {
+            // ---- partitioned CG: halo exchange of the SpMV input over NVLink (NCCL point-to-point) and one
+            //      all-reduce per dot-product pair; same operation order as on one GPU ----
+            int rc;
+            if ((rc = halo_exchange(c, c->d_x.p))) return rc;
+            fb::launch_cg_init_spmv(c, lanes);
+            if ((rc = allreduce(c, c->d_red.p, 2, ncclSum))) return rc;
+            fb::launch_cg_scalars(c, 0);
+            fb::launch_cg_init_direction(c);
+            const int check_every = 16;
+            const bool prof = c->cg_profile > 0;
+            if (prof) while ((int) c->prof_ev.size() < 3 * c->cg_profile) { cudaEvent_t e; FB_CUDA(c, cudaEventCreate(&e)); c->prof_ev.push_back(e); }
+            int launched = 0, n_prof = 0;
+            while (true) {
+                FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
+                FB_CUDA(c, cudaStreamSynchronize(s));
+                if (h->done) break;
+                for (int i = 0; i < check_every; ++i, ++launched) {
+                    const bool sample = prof && launched < c->cg_profile;
+                    if (sample) FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * launched], s));
+                    if ((rc = halo_exchange(c, c->d_d.p))) return rc;
+                    fb::launch_cg_spmv(c, lanes);
+                    if ((rc = allreduce(c, c->d_red.p, 2, ncclSum))) return rc;
+                    fb::launch_cg_scalars(c, 1);
+                    if (sample) FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * launched + 1], s));
+                    fb::launch_cg_update_only(c);
+                    if ((rc = allreduce(c, c->d_red.p, 2, ncclSum))) return rc;
+                    fb::launch_cg_scalars(c, 2);
+                    fb::launch_cg_direction_only(c);
+                    if (sample) { FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * launched + 2], s)); n_prof = launched + 1; }
+                }
+                spmv += check_every;
             }
-            n_prof = std::min(c->cg_profile, std::max(0, max_iter));
-            for (int i = 0; i < n_prof; ++i) {
-                FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i], s));
-                fb::launch_cg_spmv(c, lanes);
-                FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i + 1], s));
-                fb::launch_cg_vectors(c);
-                FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i + 2], s));
+            if (n_prof > 0) {
+                const int live = std::min(n_prof, h->it);
+                for (int i = 0; i < live; ++i) {
+                    float a = 0, b = 0;
+                    cudaEventElapsedTime(&a, c->prof_ev[3 * i], c->prof_ev[3 * i + 1]);
+                    cudaEventElapsedTime(&b, c->prof_ev[3 * i + 1], c->prof_ev[3 * i + 2]);
+                    c->prof_spmv_ms += a; c->prof_vec_ms += b;
+                }
+                c->prof_samples = live;
+                if (live > 0) { c->prof_spmv_ms /= live; c->prof_vec_ms /= live; }
             }
-            spmv += n_prof;
-        }
-        FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
-        FB_CUDA(c, cudaStreamSynchronize(s));
-        if (n_prof > 0) {
-            const int live = std::min(n_prof, h->it);      // launches after convergence are no-ops: not sampled
-            for (int i = 0; i < live; ++i) {
-                float a = 0, b = 0;
-                cudaEventElapsedTime(&a, c->prof_ev[3 * i], c->prof_ev[3 * i + 1]);
-                cudaEventElapsedTime(&b, c->prof_ev[3 * i + 1], c->prof_ev[3 * i + 2]);
-                c->prof_spmv_ms += a; c->prof_vec_ms += b;
+        } else {
+            fb::launch_cg_init(c, lanes);
+            // CUDA graph of cg_graph_iters iterations; kernels become no-ops once cgs->done is set
+            if (!c->cg_graph || c->cg_graph_n != c->cg_graph_iters || c->cg_graph_precond != lanes) {
+                drop_graph(c);
+                cudaGraph_t graph;
+                const long before = c->launches;
+                FB_CUDA(c, cudaStreamSynchronize(s));
+                FB_CUDA(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+                for (int i = 0; i < c->cg_graph_iters; ++i) fb::launch_cg_iteration(c, lanes);
+                FB_CUDA(c, cudaStreamEndCapture(s, &graph));
+                c->launches = before;     // captured, not launched
+                FB_CUDA(c, cudaGraphInstantiate(&c->cg_graph, graph, 0));
+                cudaGraphDestroy(graph);
+                c->cg_graph_n = c->cg_graph_iters; c->cg_graph_precond = lanes;
             }
-            c->prof_samples = live;
-            if (live > 0) { c->prof_spmv_ms /= live; c->prof_vec_ms /= live; }
-        }
-        while (!h->done) {
-            FB_CUDA(c, cudaGraphLaunch(c->cg_graph, s));
-            c->launches += 3L * c->cg_graph_n;
-            spmv += c->cg_graph_n;
+            // optional profile: the first cg_profile iterations run un-graphed, each bracketed by CUDA
+            // events on this stream (SpMV+dot | vector updates), for the live roofline figures of bench.py
+            int n_prof = 0;
+            if (c->cg_profile > 0) {
+                while ((int) c->prof_ev.size() < 3 * c->cg_profile) {
+                    cudaEvent_t e; FB_CUDA(c, cudaEventCreate(&e)); c->prof_ev.push_back(e);
+                }
+                n_prof = std::min(c->cg_profile, std::max(0, max_iter));
+                for (int i = 0; i < n_prof; ++i) {
+                    FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i], s));
+                    fb::launch_cg_spmv(c, lanes);
+                    FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i + 1], s));
+                    fb::launch_cg_vectors(c);
+                    FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i + 2], s));
+                }
+                spmv += n_prof;
+            }
             FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
             FB_CUDA(c, cudaStreamSynchronize(s));
+            if (n_prof > 0) {
+                const int live = std::min(n_prof, h->it);      // launches after convergence are no-ops: not sampled
+                for (int i = 0; i < live; ++i) {
+                    float a = 0, b = 0;
+                    cudaEventElapsedTime(&a, c->prof_ev[3 * i], c->prof_ev[3 * i + 1]);
+                    cudaEventElapsedTime(&b, c->prof_ev[3 * i + 1], c->prof_ev[3 * i + 2]);
+                    c->prof_spmv_ms += a; c->prof_vec_ms += b;
+                }
+                c->prof_samples = live;
+                if (live > 0) { c->prof_spmv_ms /= live; c->prof_vec_ms /= live; }
+            }
+            while (!h->done) {
+                FB_CUDA(c, cudaGraphLaunch(c->cg_graph, s));
+                c->launches += 3L * c->cg_graph_n;
+                spmv += c->cg_graph_n;
+                FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
+                FB_CUDA(c, cudaStreamSynchronize(s));
+            }
         }
     }
     FB_CUDA(c, cudaEventRecord(c->ev1, s));
@@ -366,7 +546,25 @@ static int export_by_vertex(fb_ctx* c, const double* d_src, double* out) {
 int fb_export_solution(fb_ctx* c, double* phi_vertex) {
     FB_REQUIRE(c, c->mesh_ok && phi_vertex, "fb_export_solution: no mesh");
     cudaSetDevice(c->device);
+    if (c->world > 1) {
+        // partitioned: every rank scatters its owned values into a zeroed global vertex array, summed over the ranks
+        const size_t ng = (size_t) c->n_vert_global;
+        FB_CUDA(c, c->d_sol.alloc(ng));
+        FB_CUDA(c, cudaMemsetAsync(c->d_sol.p, 0, ng * sizeof(double), c->stream));
+        fb::launch_scatter(c, c->n_dofs, c->d_l2g.p, c->d_x.p, c->d_sol.p);
+        int rc = allreduce(c, c->d_sol.p, (int) ng, ncclSum);
+        if (rc) return rc;
+        FB_CUDA(c, cudaMemcpyAsync(phi_vertex, c->d_sol.p, ng * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        return sync_check(c, "fb_export_solution");
+    }
     return export_by_vertex(c, c->d_x.p, phi_vertex);
+}
+
+// rank, world, owned rows, local columns, local nnz, local cells, halo send count, ghost count, global vertices, global cells
+int fb_get_partition(const fb_ctx* c, long* out10) {
+    out10[0] = c->rank; out10[1] = c->world; out10[2] = c->n_dofs; out10[3] = c->n_cols; out10[4] = c->nnz; out10[5] = c->n_cells;
+    out10[6] = (long) c->send_idx.size(); out10[7] = c->n_cols - c->n_dofs; out10[8] = c->n_vert_global; out10[9] = c->n_cells_global;
+    return FB_OK;
 }
 
 int fb_export_charge_dens(fb_ctx* c, double* rho_vertex) {
@@ -390,6 +588,12 @@ int fb_check_limits(fb_ctx* c, double lo, double hi, int* bad, double* mn, doubl
     FB_REQUIRE(c, c->mesh_ok, "fb_check_limits: no mesh");
     cudaSetDevice(c->device);
     fb::launch_minmax(c);
+    if (c->world > 1) {
+        int rc = FB_OK;
+        FB_NCCL(c, fb::Nccl::get().AllReduce(c->d_minmax.p, c->d_minmax.p, 1, ncclDouble, ncclMin, (ncclComm_t) c->nccl_comm, c->stream));
+        FB_NCCL(c, fb::Nccl::get().AllReduce(c->d_minmax.p + 1, c->d_minmax.p + 1, 1, ncclDouble, ncclMax, (ncclComm_t) c->nccl_comm, c->stream));
+        (void) rc;
+    }
     double* h = (double*) c->pin_out.p;
     FB_CUDA(c, cudaMemcpyAsync(h, c->d_minmax.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     int rc = sync_check(c, "fb_check_limits");
@@ -435,6 +639,7 @@ int fb_interp_initialize(fb_ctx* c, const int* node_marker, const int* tet4, con
                          const int* quad4, const int* quad2hex, int n_quad, double tet_edgemax,
                          const int* voro_off, const int* voro_list, int n_voro) {
     FB_REQUIRE(c, c->mesh_ok, "fb_interp_initialize: call fb_import_mesh first");
+    FB_REQUIRE(c, c->world == 1, "fb_interp_initialize: the interpolator works on replicated (un-partitioned) meshes only");
     FB_REQUIRE(c, node_marker && tet4 && tet_nbr4 && tet_marker && n_tet > 0, "fb_interp_initialize: tetrahedra missing");
     FB_REQUIRE(c, 4L * n_tet == c->n_hex, "fb_interp_initialize: expected 4 hexahedra per tetrahedron");
     cudaSetDevice(c->device);

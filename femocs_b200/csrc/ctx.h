@@ -67,6 +67,8 @@ struct CgScalars {          // device-resident CG state (one struct, updated by 
     int done;               // 1 = converged, 2 = max_iter reached
     int max_iter;
     int pad;
+    double* red;            // multi-GPU: kernels deposit their LOCAL sums here (all-reduced over the ranks by NCCL,
+                            // then k_cg_scalars_* finishes the step); nullptr on one GPU
 };
 
 }  // namespace fb

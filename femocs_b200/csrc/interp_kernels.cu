@@ -566,10 +566,15 @@ template <bool FROM_VERTS>
 __global__ void __launch_bounds__(128) k_space_charge(const HexRec* __restrict__ hexrec, long n, const double* __restrict__ pts,
                                                       const int* __restrict__ pcell, int n_cells, const int* __restrict__ cell2hex,
                                                       const int* __restrict__ cells_dof, const double* __restrict__ vxyz,
-                                                      double charge_factor, double* __restrict__ rhs) {
+                                                      double charge_factor, double* __restrict__ rhs,
+                                                      const int* __restrict__ gcell2local, int n_cells_global, int n_rows) {
     const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int cell = pcell[i];
+    int cell = pcell[i];
+    if (gcell2local) {          // partitioned mesh: particles carry global cell ids; cells of other ranks are skipped
+        if (cell < 0 || cell >= n_cells_global) return;
+        cell = gcell2local[cell];
+    }
     if (cell < 0 || cell >= n_cells) return;
     double sf[8];
     if (FROM_VERTS) {
@@ -595,7 +600,10 @@ __global__ void __launch_bounds__(128) k_space_charge(const HexRec* __restrict__
     }
     const int perm[8] = {0, 1, 4, 5, 3, 2, 7, 6};       // shape_funs_dealii (:1355-1358)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(&rhs[cells_dof[8 * (long) cell + k]], sf[perm[k]] * charge_factor);
+    for (int k = 0; k < 8; ++k) {
+        const int dof = cells_dof[8 * (long) cell + k];
+        if (dof < n_rows) atomicAdd(&rhs[dof], sf[perm[k]] * charge_factor);       // rows of ghost dofs belong to their owner
+    }
 }
 
 __global__ void k_pack_points(long n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
@@ -698,10 +706,11 @@ void launch_space_charge(fb_ctx* c, long n, const double* d_pts, const int* d_pc
     const unsigned g = (unsigned) ((n + 127) / 128);
     if (c->interp_ok)
         k_space_charge<false><<<g, 128, 0, c->stream>>>(c->d_hex.p, n, d_pts, d_pcell, c->n_cells, c->d_cell2hex.p, c->d_cells.p,
-                                                         c->d_vxyz.p, charge_factor, c->d_rhs.p);
+                                                         c->d_vxyz.p, charge_factor, c->d_rhs.p, nullptr, 0, c->n_dofs);
     else
         k_space_charge<true><<<g, 128, 0, c->stream>>>(nullptr, n, d_pts, d_pcell, c->n_cells, c->d_cell2hex.p, c->d_cells.p,
-                                                        c->d_vxyz.p, charge_factor, c->d_rhs.p);
+                                                        c->d_vxyz.p, charge_factor, c->d_rhs.p,
+                                                        c->world > 1 ? c->d_gcell2local.p : nullptr, c->n_cells_global, c->n_dofs);
     c->launches++;
 }
 

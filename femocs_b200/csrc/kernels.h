@@ -20,6 +20,15 @@ void launch_cg_iteration(fb_ctx* c, int lanes);
 void launch_cg_spmv(fb_ctx* c, int lanes);
 void launch_cg_vectors(fb_ctx* c);
 bool persistent_eligible(fb_ctx* c);
+// multi-GPU
+void launch_pack(fb_ctx* c, const double* v);
+void launch_flags_to_double(fb_ctx* c, double* out);
+void launch_double_to_ghost_flags(fb_ctx* c, const double* in);
+void launch_cg_scalars(fb_ctx* c, int which);
+void launch_cg_init_spmv(fb_ctx* c, int lanes);
+void launch_cg_init_direction(fb_ctx* c);
+void launch_cg_update_only(fb_ctx* c);
+void launch_cg_direction_only(fb_ctx* c);
 cudaError_t launch_cg_persistent(fb_ctx* c);
 void launch_minmax(fb_ctx* c);
 void launch_gather(fb_ctx* c, int n, const int* idx, const double* src, double* dst);

@@ -76,12 +76,10 @@ int fb_host_partition_phase1(fb_ctx* c, const double* xyz, int n_nodes, const in
     std::vector<int> g2l(nv, -1), owned, ghosts;
     for (int lc = 0; lc < ncl; ++lc) {
         const int* h = &hex8[8 * (size_t) cells_g[c->part_cell_g[lc]]];
-        static const int UCD_TO_LEX_INV[8] = {0, 1, 3, 2, 4, 5, 7, 6};   // lexicographic position d holds UCD vertex [0,1,4,5,3,2,7,6][d]
-        (void) UCD_TO_LEX_INV;
-        static const int LEX2UCD[8] = {0, 1, 4, 5, 3, 2, 7, 6};
+        static const int LEX2UCD[8] = {0, 1, 4, 5, 3, 2, 7, 6};          // lexicographic position d holds UCD vertex LEX2UCD[d]
         for (int d = 0; d < 8; ++d) {
             const int v = node2vert[h[LEX2UCD[d]]];
-            if (g2l[v] >= 0) continue;
+            if (g2l[v] != -1) continue;               // already numbered (owned) or already listed (ghost, -2)
             if (owner[v] == rank) { g2l[v] = (int) owned.size(); owned.push_back(v); }
             else { g2l[v] = -2; ghosts.push_back(v); }
         }

@@ -76,6 +76,48 @@ __device__ __forceinline__ bool reduce_publish(double (&v)[NV], double* __restri
 }
 
 // ---------------------------------------------------------------------------------------
+// scalar tail of the two reduction kernels of a CG iteration (executed by ONE thread).  On one GPU the
+// last block calls them with the grid totals; with a partitioned mesh the last block only deposits the
+// rank-local sums in cgs->red, NCCL all-reduces them and k_cg_scalars_* calls the same code.
+// ---------------------------------------------------------------------------------------
+template <bool INIT>
+__device__ __forceinline__ void cg_scalars_spmv(CgScalars* cgs, const double* tot, double* alpha_out) {
+    if (INIT) {
+        cgs->gh = tot[0]; cgs->res2 = tot[1]; cgs->it = 0;
+        cgs->done = (tot[1] <= cgs->tol2) ? 1 : ((cgs->max_iter <= 0 || tot[1] != tot[1]) ? 2 : 0);
+    } else {
+        *alpha_out = cgs->gh / tot[0];
+    }
+}
+__device__ __forceinline__ void cg_scalars_update(CgScalars* cgs, const double* tot, double* beta_out) {
+    const int it = cgs->it + 1;
+    cgs->it = it;
+    cgs->res2 = tot[1];
+    *beta_out = tot[0] / cgs->gh;
+    cgs->gh = tot[0];
+    if (tot[1] <= cgs->tol2) cgs->done = 1;                     // SolverControl: success first,
+    else if (it >= cgs->max_iter || tot[1] != tot[1]) cgs->done = 2;   // then failure on max steps / NaN
+}
+template <bool INIT>
+__device__ __forceinline__ void cg_finish_spmv(CgScalars* cgs, const double* tot, double* alpha_out) {
+    if (cgs->red) { cgs->red[0] = tot[0]; cgs->red[1] = tot[1]; }
+    else cg_scalars_spmv<INIT>(cgs, tot, alpha_out);
+}
+__device__ __forceinline__ void cg_finish_update(CgScalars* cgs, const double* tot, double* beta_out) {
+    if (cgs->red) { cgs->red[0] = tot[0]; cgs->red[1] = tot[1]; }
+    else cg_scalars_update(cgs, tot, beta_out);
+}
+template <bool INIT>
+__global__ void k_cg_scalars_spmv(CgScalars* cgs, double* alpha_out) {
+    if (!INIT && cgs->done) return;
+    cg_scalars_spmv<INIT>(cgs, cgs->red, alpha_out);
+}
+__global__ void k_cg_scalars_update(CgScalars* cgs, double* beta_out) {
+    if (cgs->done) return;
+    cg_scalars_update(cgs, cgs->red, beta_out);
+}
+
+// ---------------------------------------------------------------------------------------
 // Q1 stiffness assembly: one thread per hexahedron, 2x2x2 Gauss, MappingQ1.
 //   K_e(i,j) = sum_q JxW_q grad N_i(q) . grad N_j(q)       (PoissonSolver.cpp:249-255)
 // scattered into the CSR matrix with FP64 atomics (summation order across cells is not fixed:
@@ -90,7 +132,7 @@ __device__ __forceinline__ int find_col(const int* __restrict__ col, int lo, int
     return lo;
 }
 
-__global__ void __launch_bounds__(128) k_assemble_stiffness(int n_cells, const int* __restrict__ cells,
+__global__ void __launch_bounds__(128) k_assemble_stiffness(int n_cells, int n_rows, const int* __restrict__ cells,
                                                            const double* __restrict__ vxyz,
                                                            const int* __restrict__ rowptr, const int* __restrict__ col,
                                                            double* __restrict__ val, double* __restrict__ cell_vol) {
@@ -155,20 +197,23 @@ __global__ void __launch_bounds__(128) k_assemble_stiffness(int n_cells, const i
     int k = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int ri = dof[i], lo_i = __ldg(&rowptr[ri]), hi_i = __ldg(&rowptr[ri + 1]);
+        // rows >= n_rows belong to another rank (ghost dofs of a partitioned mesh): that rank assembles them
+        const int ri = dof[i];
+        const bool own_i = ri < n_rows;
+        const int lo_i = own_i ? __ldg(&rowptr[ri]) : 0, hi_i = own_i ? __ldg(&rowptr[ri + 1]) : 0;
 #pragma unroll
         for (int j = i; j < 8; ++j, ++k) {
-            atomicAdd(&val[find_col(col, lo_i, hi_i, dof[j])], Ke[k]);
+            if (own_i) atomicAdd(&val[find_col(col, lo_i, hi_i, dof[j])], Ke[k]);
             if (j != i) {
                 const int rj = dof[j];
-                atomicAdd(&val[find_col(col, __ldg(&rowptr[rj]), __ldg(&rowptr[rj + 1]), ri)], Ke[k]);
+                if (rj < n_rows) atomicAdd(&val[find_col(col, __ldg(&rowptr[rj]), __ldg(&rowptr[rj + 1]), ri)], Ke[k]);
             }
         }
     }
 }
 
 // Neumann faces (DealSolver.cpp:389-430): b_i += sum_q N_i(q) * bc * JxW_face(q), QGauss<2>(2)
-__global__ void k_neumann_faces(int n_faces, const int* __restrict__ face_dofs, const double* __restrict__ vxyz,
+__global__ void k_neumann_faces(int n_faces, int n_rows, const int* __restrict__ face_dofs, const double* __restrict__ vxyz,
                                 double bc_value, double* __restrict__ rhs) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_faces) return;
@@ -196,7 +241,7 @@ __global__ void k_neumann_faces(int n_faces, const int* __restrict__ face_dofs, 
         r[2] += (1 - s) * t * bc_value * JxW;       r[3] += s * t * bc_value * JxW;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) atomicAdd(&rhs[d[i]], r[i]);
+    for (int i = 0; i < 4; ++i) if (d[i] < n_rows) atomicAdd(&rhs[d[i]], r[i]);
 }
 
 // mark constrained dofs
@@ -294,12 +339,7 @@ __global__ void __launch_bounds__(256) k_spmv_dot(int n, const int* __restrict__
     }
     double tot[2];
     if (reduce_publish<2>(acc, partial, counter, tot)) {
-        if (INIT) {
-            cgs->gh = tot[0]; cgs->res2 = tot[1]; cgs->it = 0;
-            cgs->done = (tot[1] <= cgs->tol2) ? 1 : ((cgs->max_iter <= 0 || tot[1] != tot[1]) ? 2 : 0);
-        } else {
-            *alpha_out = cgs->gh / tot[0];
-        }
+        cg_finish_spmv<INIT>(cgs, tot, alpha_out);
     }
 }
 
@@ -364,12 +404,7 @@ __global__ void __launch_bounds__(THREADS) k_spmv_stream(int n_blocks, const int
     }
     double tot[2];
     if (reduce_publish<2>(acc, partial, counter, tot)) {
-        if (INIT) {
-            cgs->gh = tot[0]; cgs->res2 = tot[1]; cgs->it = 0;
-            cgs->done = (tot[1] <= cgs->tol2) ? 1 : ((cgs->max_iter <= 0 || tot[1] != tot[1]) ? 2 : 0);
-        } else {
-            *alpha_out = cgs->gh / tot[0];
-        }
+        cg_finish_spmv<INIT>(cgs, tot, alpha_out);
     }
 }
 
@@ -389,13 +424,7 @@ __global__ void __launch_bounds__(256) k_update(int n, const double* __restrict_
     }
     double tot[2];
     if (reduce_publish<2>(acc, partial, counter, tot)) {
-        const int it = cgs->it + 1;
-        cgs->it = it;
-        cgs->res2 = tot[1];
-        *beta_out = tot[0] / cgs->gh;
-        cgs->gh = tot[0];
-        if (tot[1] <= cgs->tol2) cgs->done = 1;                     // SolverControl: success first,
-        else if (it >= cgs->max_iter || tot[1] != tot[1]) cgs->done = 2;   // then failure on max steps / NaN
+        cg_finish_update(cgs, tot, beta_out);
     }
 }
 
@@ -478,12 +507,7 @@ __global__ void __launch_bounds__(THREADS) k_spmv_window(int n_blocks, const int
     }
     double tot[2];
     if (reduce_publish<2>(acc, partial, counter, tot)) {
-        if (INIT) {
-            cgs->gh = tot[0]; cgs->res2 = tot[1]; cgs->it = 0;
-            cgs->done = (tot[1] <= cgs->tol2) ? 1 : ((cgs->max_iter <= 0 || tot[1] != tot[1]) ? 2 : 0);
-        } else {
-            *alpha_out = cgs->gh / tot[0];
-        }
+        cg_finish_spmv<INIT>(cgs, tot, alpha_out);
     }
 }
 
@@ -576,12 +600,7 @@ __global__ void __launch_bounds__(R / 2) k_spmv_jds(int n, int n_blocks, const i
     }
     double tot[2];
     if (reduce_publish<2>(acc, partial, counter, tot)) {
-        if (INIT) {
-            cgs->gh = tot[0]; cgs->res2 = tot[1]; cgs->it = 0;
-            cgs->done = (tot[1] <= cgs->tol2) ? 1 : ((cgs->max_iter <= 0 || tot[1] != tot[1]) ? 2 : 0);
-        } else {
-            *alpha_out = cgs->gh / tot[0];
-        }
+        cg_finish_spmv<INIT>(cgs, tot, alpha_out);
     }
 }
 
@@ -868,13 +887,13 @@ int choose_lanes(const fb_ctx* c) {
 void launch_assemble_stiffness(fb_ctx* c, double* d_cell_vol) {
     const int block = 128;
     k_assemble_stiffness<<<(c->n_cells + block - 1) / block, block, 0, c->stream>>>(
-        c->n_cells, c->d_cells.p, c->d_vxyz.p, c->d_rowptr.p, c->d_col.p, c->d_val_save.p, d_cell_vol);
+        c->n_cells, c->n_dofs, c->d_cells.p, c->d_vxyz.p, c->d_rowptr.p, c->d_col.p, c->d_val_save.p, d_cell_vol);
     c->launches++;
 }
 
 void launch_neumann(fb_ctx* c) {
     if (c->n_top_faces == 0) return;
-    k_neumann_faces<<<(c->n_top_faces + 127) / 128, 128, 0, c->stream>>>(c->n_top_faces, c->d_topfaces.p, c->d_vxyz.p,
+    k_neumann_faces<<<(c->n_top_faces + 127) / 128, 128, 0, c->stream>>>(c->n_top_faces, c->n_dofs, c->d_topfaces.p, c->d_vxyz.p,
                                                                        c->applied_field, c->d_rhs.p);
     c->launches++;
 }
@@ -1063,6 +1082,56 @@ cudaError_t launch_cg_persistent(fb_ctx* c) {
     if (pt <= 12) return launch_persistent_pt<12>(c, smem);
     if (pt <= 16) return launch_persistent_pt<16>(c, smem);
     return launch_persistent_pt<24>(c, smem);
+}
+
+// ---- multi-GPU helpers -------------------------------------------------------------------
+__global__ void k_pack(int n, const int* __restrict__ idx, const double* __restrict__ v, double* __restrict__ out) {
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) out[i] = v[idx[i]];
+}
+__global__ void k_flags_to_double(int n, const int* __restrict__ flag, double* __restrict__ out) {
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) out[i] = flag[i] ? 1.0 : 0.0;
+}
+__global__ void k_double_to_flags(int n0, int n1, const double* __restrict__ in, int* __restrict__ flag) {
+    for (long i = n0 + (long) blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += (long) gridDim.x * blockDim.x) flag[i] = in[i] != 0.0;
+}
+void launch_pack(fb_ctx* c, const double* v) {
+    const int n = (int) c->send_idx.size();
+    if (n == 0) return;
+    k_pack<<<grid_for(c, n, 256), 256, 0, c->stream>>>(n, c->d_send_idx.p, v, c->d_sendbuf.p);
+    c->launches++;
+}
+void launch_flags_to_double(fb_ctx* c, double* out) {
+    k_flags_to_double<<<grid_for(c, c->n_cols, 256), 256, 0, c->stream>>>(c->n_cols, c->d_bcflag.p, out);
+    c->launches++;
+}
+void launch_double_to_ghost_flags(fb_ctx* c, const double* in) {
+    if (c->n_cols == c->n_dofs) return;
+    k_double_to_flags<<<grid_for(c, c->n_cols - c->n_dofs, 256), 256, 0, c->stream>>>(c->n_dofs, c->n_cols, in, c->d_bcflag.p);
+    c->launches++;
+}
+void launch_cg_scalars(fb_ctx* c, int which) {      // 0: after the initial residual, 1: after SpMV, 2: after the update
+    if (which == 0) k_cg_scalars_spmv<true><<<1, 1, 0, c->stream>>>(c->d_cg.p, nullptr);
+    else if (which == 1) k_cg_scalars_spmv<false><<<1, 1, 0, c->stream>>>(c->d_cg.p, alpha_ptr(c));
+    else k_cg_scalars_update<<<1, 1, 0, c->stream>>>(c->d_cg.p, beta_ptr(c));
+    c->launches++;
+}
+void launch_cg_init_spmv(fb_ctx* c, int lanes) { spmv_dispatch<true>(c, lanes, c->d_x.p, c->d_g.p, nullptr); }
+void launch_cg_init_direction(fb_ctx* c) {
+    const int g = grid_for(c, c->n_dofs, 256);
+    k_direction<true><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_g.p, c->d_dinv.p, c->d_d.p, c->d_cg.p, nullptr);
+    c->launches++;
+}
+void launch_cg_update_only(fb_ctx* c) {
+    unsigned* counter = (unsigned*) (c->d_partial.p + c->d_partial.n - 8);
+    const int g = grid_for(c, c->n_dofs, 256);
+    k_update<<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_d.p, c->d_h.p, c->d_dinv.p, c->d_x.p, c->d_g.p, c->d_partial.p, counter,
+                                       c->d_cg.p, alpha_ptr(c), beta_ptr(c));
+    c->launches++;
+}
+void launch_cg_direction_only(fb_ctx* c) {
+    const int g = grid_for(c, c->n_dofs, 256);
+    k_direction<false><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_g.p, c->d_dinv.p, c->d_d.p, c->d_cg.p, beta_ptr(c));
+    c->launches++;
 }
 
 void launch_minmax(fb_ctx* c) {

@@ -21,6 +21,14 @@ SIGNATURES = {
     "fb_create_error": (C.c_char_p, []),
     "fb_kernel_launches": (C.c_long, [vp]),
     "fb_set_option": (C.c_int, [vp, C.c_char_p, C.c_double]),
+    "fb_comm_unique_id": (C.c_int, [vp]),
+    "fb_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+    "fb_get_partition": (C.c_int, [vp, vp]),
+    "fb_plan_create": (vp, [C.c_int, C.c_int]),
+    "fb_plan_phase1": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
+    "fb_plan_phase2": (C.c_int, [vp, vp]),
+    "fb_plan_sizes": (C.c_int, [vp, vp]),
+    "fb_plan_get": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "fb_import_mesh": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int]),
     "fb_get_sizes": (C.c_int, [vp, vp]),
     "fb_poisson_setup": (C.c_int, [vp, C.c_double, C.c_double, C.c_int]),

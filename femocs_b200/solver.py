@@ -78,6 +78,37 @@ class Context:
     def synchronize(self):
         self.check(self.L.fb_synchronize(self.h))
 
+    # ---- multi-GPU: one process per GPU; call before PoissonSolver.import_mesh ----
+    def init_comm(self, rank, world, unique_id):
+        """unique_id: the 128 bytes drawn by rank 0 with Context.unique_id() and broadcast by the host code."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self.check(self.L.fb_comm_init(self.h, int(rank), int(world), C.cast(buf, C.c_void_p)))
+
+    @staticmethod
+    def unique_id():
+        L = _lib.load()
+        buf = C.create_string_buffer(128)
+        if L.fb_comm_unique_id(C.cast(buf, C.c_void_p)) != 0:
+            raise FemocsB200Error("fb_comm_unique_id failed: " + L.fb_create_error().decode())
+        return buf.raw
+
+    def init_comm_torch(self, dist):
+        """Convenience for torchrun launches: broadcast the id over an initialised torch.distributed group."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(self.unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(t, 0)
+        self.init_comm(rank, world, bytes(t.cpu().numpy().tobytes()))
+
+    def partition(self):
+        out = np.zeros(10, np.int64)
+        self.check(self.L.fb_get_partition(self.h, _p(out)))
+        keys = ("rank", "world", "n_rows", "n_cols", "nnz", "n_cells", "n_send", "n_ghost", "n_vert_global", "n_cells_global")
+        return dict(zip(keys, (int(v) for v in out)))
+
     @property
     def stream(self):
         """cudaStream_t of the context (integer address)."""
@@ -120,6 +151,12 @@ class PoissonSolver:
         sz = np.zeros(7, np.int64)
         self.ctx.check(self.ctx.L.fb_get_sizes(self.ctx.h, _p(sz)))
         (self.n_dofs, self.n_cells, self.nnz, self.n_vertices, self.n_bfaces, self.n_top_faces, _) = [int(v) for v in sz]
+        part = self.ctx.partition()
+        if part["world"] > 1:           # partitioned: n_dofs / nnz / n_cells above are this rank's share
+            self.n_vertices = part["n_vert_global"]
+            self.n_dofs_global = part["n_vert_global"]
+        else:
+            self.n_dofs_global = self.n_dofs
         return True
 
     def size(self):
@@ -394,3 +431,47 @@ class Pic:
         E = np.zeros((len(cells), 3))
         self.ctx.check(self.ctx.L.fb_particle_field(self.ctx.h, len(cells), _p(xyz), _p(cells), _p(E)))
         return E
+
+
+class PartitionPlan:
+    """Host-only view of the multi-GPU partition logic (fb_plan_*; no CUDA): what rank `rank` of `world` keeps of
+    a mesh, its local sparsity and its halo lists.  Used by the world_size-2 CPU tests."""
+
+    def __init__(self, rank, world):
+        self.L = _lib.load()
+        self.h = C.c_void_p(self.L.fb_plan_create(int(rank), int(world)))
+        self.rank, self.world = rank, world
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.fb_destroy(self.h)
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise FemocsB200Error("fb_plan error %d: %s" % (rc, self.L.fb_last_error(self.h).decode()))
+
+    def phase1(self, nodes, hexs, hex_markers):
+        nodes = _f(nodes); hexs = _i(hexs); hex_markers = _i(hex_markers)
+        bbox = np.zeros(6)
+        self._check(self.L.fb_plan_phase1(self.h, _p(nodes), len(nodes), _p(hexs), _p(hex_markers), len(hexs), _p(bbox)))
+        return bbox                      # local (min xyz, max xyz) of the boundary-face centres
+
+    def phase2(self, bbox_global):
+        b = _f(bbox_global)
+        self._check(self.L.fb_plan_phase2(self.h, _p(b)))
+        sz = np.zeros(8, np.int64)
+        self.L.fb_plan_sizes(self.h, _p(sz))
+        (self.n_rows, self.n_cols, self.nnz, self.n_cells, self.n_send, self.n_ghost, self.n_vert_global, self.n_cells_global) = [int(v) for v in sz]
+        w = self.world
+        a = dict(local2global=np.zeros(self.n_cols, np.int32), owner=np.zeros(self.n_cols, np.int32), send_off=np.zeros(w + 1, np.int32),
+                 send_idx=np.zeros(max(1, self.n_send), np.int32), recv_off=np.zeros(w + 1, np.int32), rowptr=np.zeros(self.n_rows + 1, np.int32),
+                 col=np.zeros(self.nnz, np.int32), cells_dof=np.zeros((self.n_cells, 8), np.int32), cell2global=np.zeros(self.n_cells, np.int32),
+                 copper=np.zeros(self.n_cols, np.int32), top=np.zeros(self.n_cols, np.int32))
+        self._check(self.L.fb_plan_get(self.h, _p(a["local2global"]), _p(a["owner"]), _p(a["send_off"]), _p(a["send_idx"]), _p(a["recv_off"]),
+                                       _p(a["rowptr"]), _p(a["col"]), _p(a["cells_dof"]), _p(a["cell2global"]), _p(a["copper"]), _p(a["top"])))
+        a["send_idx"] = a["send_idx"][:self.n_send]
+        self.__dict__.update(a)
+        return self

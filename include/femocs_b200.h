@@ -63,6 +63,32 @@ long        fb_kernel_launches(const fb_ctx* ctx);
 int         fb_set_option(fb_ctx* ctx, const char* key, double value);
 
 /* ---------------------------------------------------------------------------------------
+ * multi-GPU (no reference counterpart: DealSolver is serial, include/DealSolver.h:135-143).  One process
+ * per GPU.  Rank 0 draws a 128-byte communicator id, the host code hands it to every rank by any channel
+ * (torch.distributed / MPI broadcast), and each rank calls fb_comm_init BEFORE fb_import_mesh.  With
+ * world > 1 fb_import_mesh takes the SAME full mesh on every rank and keeps the rank's element partition
+ * (recursive coordinate bisection of the vertices; rows of the owned vertices, ghost columns behind them);
+ * assemble / solve / check_limits / export_solution then work on the distributed system: the CG exchanges
+ * the halo of its search direction with NCCL point-to-point over NVLink and all-reduces its dot products.
+ * fb_export_solution returns the complete potential (global solver-vertex order) on every rank.
+ * The interpolator entry points need an un-partitioned context (native meshes are "replicas only").
+ * ------------------------------------------------------------------------------------- */
+int fb_comm_unique_id(char* id128);
+int fb_comm_init(fb_ctx* ctx, int rank, int world, const char* id128);
+/* out[0..9] = rank, world, owned rows, local columns (rows + ghosts), local nnz, local cells,
+ * halo values sent per exchange, ghosts received, global solver vertices, global solver cells */
+int fb_get_partition(const fb_ctx* ctx, long* out10);
+/* host-only view of the same partition logic (no CUDA): used by the world_size-2 CPU tests.
+ * phase1 returns the extremes of the local boundary-face centres (min xyz, max xyz); the caller reduces
+ * them over the ranks (min / max) and passes the result to phase2.  Destroy with fb_destroy. */
+fb_ctx* fb_plan_create(int rank, int world);
+int fb_plan_phase1(fb_ctx* plan, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex, double* bbox6);
+int fb_plan_phase2(fb_ctx* plan, const double* bbox6_global);
+int fb_plan_sizes(const fb_ctx* plan, long* out8);
+int fb_plan_get(const fb_ctx* plan, int* local2global, int* owner, int* send_off, int* send_idx, int* recv_off, int* rowptr, int* col,
+                int* cells_dof, int* local_cell2global, int* copper_flag, int* top_flag);
+
+/* ---------------------------------------------------------------------------------------
  * bool DealSolver<3>::import_mesh(vector<Point<3>> vertices, vector<CellData<3>> cells)
  *   src/DealSolver.cpp:191-209 (+ mark_boundary :460-518, PoissonSolver::mark_mesh
  *   src/PoissonSolver.cpp:52-55), fed by TetgenNodes::export_dealii and
