@@ -351,6 +351,7 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
     if (c->world > 1) h->red = c->d_red.p;
     FB_CUDA(c, cudaEventRecord(c->ev0, s));
     FB_CUDA(c, cudaMemcpyAsync(c->d_cg.p, h, sizeof(fb::CgScalars), cudaMemcpyHostToDevice, s));
+    c->last_kernel = -2;
     if (persistent) {
         // native meshes: the whole solve is ONE cooperative launch (matrix slice resident in shared memory)
         FB_CUDA(c, fb::launch_cg_persistent(c));
@@ -370,12 +371,15 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
         }
     } else {
         int lanes = fb::choose_lanes(c);
-        if (lanes >= 300) {                        // block-JDS SpMV: tables once per mesh, values once per assemble
-            const int R = (lanes == 301) ? 128 : (lanes == 302 ? 512 : 256);
-            if (!c->jds_ready || c->jds_R != R) {
+        while (lanes >= 300) {                     // block-JDS SpMV: tables once per mesh, values once per assemble
+            const bool sym = lanes >= 310;         // 310/311: symmetric layout (lower triangle only)
+            const int R = sym ? (lanes == 311 ? 256 : 512) : ((lanes == 301) ? 128 : (lanes == 302 ? 512 : 256));
+            if (!c->jds_ready || c->jds_R != R || c->jds_sym != sym) {
                 drop_graph(c);
-                if (fb_host_jds_build(c, R, 8192)) {
+                // window capacity: shared memory holds the input window (and, symmetric layout, its accumulators)
+                if (fb_host_jds_build(c, R, sym ? 6144 : 8192, sym)) {
                     c->win_cap = (c->win_max + 15) & ~15;
+                    if (sym) FB_CUDA(c, c->d_diag.alloc(c->n_dofs));
                     FB_CUDA(c, c->d_col16.upload(c->col16, s));
                     FB_CUDA(c, c->d_win_off.upload(c->win_off, s)); FB_CUDA(c, c->d_win_list.upload(c->win_list, s));
                     FB_CUDA(c, c->d_jds_perm.upload(c->jds_perm, s)); FB_CUDA(c, c->d_jds_len.upload(c->jds_len, s));
@@ -389,11 +393,14 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
                     std::vector<int>().swap(c->win_list);
                     c->jds_ready = true; c->jds_val_dirty = true;
                     c->rowblk_chunk = 0; c->n_rowblk = 0;              // col16 / windows now belong to the JDS layout
+                } else if (sym) {
+                    lanes = 302; continue;         // a window + its accumulators exceed shared memory: full block-JDS
                 } else {
-                    lanes = 100;                   // window too large for shared memory: plain streaming kernel
+                    lanes = 100; break;            // window too large for shared memory: plain streaming kernel
                 }
             }
-            if (lanes >= 300 && c->jds_val_dirty) { fb::launch_csr_to_jds(c); c->jds_val_dirty = false; }
+            if (c->jds_val_dirty) { fb::launch_csr_to_jds(c); c->jds_val_dirty = false; }
+            break;
         }
         if (lanes == 0 || (lanes >= 100 && lanes < 300)) {          // streaming SpMV: (re)build its row blocks for the chosen variant
             if (lanes >= 200) c->jds_ready = false;                  // the windowed variants reuse the col16 / window buffers
@@ -418,6 +425,7 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
                 }
             }
         }
+        c->last_kernel = lanes;
         if (c->world > 1) {
             // ---- partitioned CG: halo exchange of the SpMV input over NVLink (NCCL point-to-point) and one
             //      all-reduce per dot-product pair; same operation order as on one GPU ----
@@ -530,6 +538,8 @@ int fb_last_solve_stats(const fb_ctx* c, double* ms, int* it, long* spmv) {
     if (ms) *ms = c->last_solve_ms; if (it) *it = c->last_iters; if (spmv) *spmv = c->last_spmv;
     return FB_OK;
 }
+
+int fb_last_solve_kernel(const fb_ctx* c) { return c->last_kernel; }
 
 int fb_last_solve_profile(const fb_ctx* c, double* spmv_ms, double* vec_ms, int* n_samples) {
     if (spmv_ms) *spmv_ms = c->prof_spmv_ms; if (vec_ms) *vec_ms = c->prof_vec_ms; if (n_samples) *n_samples = c->prof_samples;

@@ -121,7 +121,7 @@ struct fb_ctx {
     std::vector<int> win_off, win_list;      // per row block: sorted distinct columns (CSR over blocks)
     int win_max = 0, win_cap = 0;
     // block-JDS layout of the HBM-roofline SpMV
-    int jds_R = 0, jds_nb = 0, jds_maxlen = 0; bool jds_ready = false, jds_val_dirty = true;
+    int jds_R = 0, jds_nb = 0, jds_maxlen = 0; bool jds_ready = false, jds_val_dirty = true, jds_sym = false, h_needs_zero = false;
     std::vector<unsigned short> jds_perm, jds_len, jds_slot; std::vector<int> jds_jdp, jds_jd, jds_base; int jds_size = 0;
     struct BFace { int cell, face, id; };
     std::vector<BFace> bfaces;
@@ -137,7 +137,7 @@ struct fb_ctx {
     fb::DevBuf<int> d_cells;                 // 8*n_cells dof ids (lexicographic)
     fb::DevBuf<int> d_rowptr, d_col, d_diagpos, d_rowblk, d_win_off, d_win_list;
     fb::DevBuf<unsigned short> d_col16, d_jds_perm, d_jds_len, d_jds_slot;
-    fb::DevBuf<int> d_jds_jdp, d_jds_jd, d_jds_base; fb::DevBuf<double> d_val_jds;
+    fb::DevBuf<int> d_jds_jdp, d_jds_jd, d_jds_base; fb::DevBuf<double> d_val_jds, d_diag;
     fb::DevBuf<double> d_val, d_val_save;
     fb::DevBuf<double> d_rhs, d_x, d_g, d_d, d_h, d_dinv, d_z, d_w;
     fb::DevBuf<int> d_topfaces;              // 4 dof ids per top (Neumann) face
@@ -153,7 +153,7 @@ struct fb_ctx {
     fb::DevBuf<long long> d_dbg; int cg_debug = 0, pers_ctas = 0;
     cudaGraphExec_t cg_graph = nullptr;
     int cg_graph_precond = -1, cg_graph_n = 0;
-    double last_solve_ms = 0; int last_iters = 0; long last_spmv = 0;
+    double last_solve_ms = 0; int last_iters = 0; long last_spmv = 0; int last_kernel = -1;
     double cheb_lmax = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> prof_ev;        // 3 events per profiled iteration
@@ -174,6 +174,7 @@ struct fb_ctx {
     fb::DevBuf<int> d_qtet, d_qtri;          // 10 / 6 node ids
     // scratch for queries
     fb::DevBuf<double> d_pts; fb::DevBuf<int> d_cellsA, d_cellsB, d_scan, d_scan2, d_flag;
+    fb::DevBuf<int> d_needy;                 // [0] = count, [1..] = indices of the points deferred to the block-cooperative scan
     int chain_blocks_per_sm = 0; fb::DevBuf<double> d_sol;
     fb::DevBuf<unsigned char> d_dirtyA, d_dirtyB;
     fb::PinnedBuf pin_in, pin_out;
@@ -196,7 +197,7 @@ struct fb_ctx {
 // implemented in host_setup.cpp
 bool fb_host_row_blocks(fb_ctx* c, int chunk, int maxrows);
 bool fb_host_col_windows(fb_ctx* c, int max_window);
-bool fb_host_jds_build(fb_ctx* c, int R, int max_window);
+bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym);
 int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
 int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
 int fb_host_import_phase2(fb_ctx* c);

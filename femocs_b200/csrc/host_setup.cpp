@@ -369,10 +369,17 @@ bool fb_host_col_windows(fb_ctx* c, int max_window) {
 // diagonals: diagonal j holds the j-th entry of every row longer than j, so that thread t of the
 // CTA walks "its" row with perfectly coalesced loads and NO padding.  Columns are replaced by 16-bit
 // positions inside the block's window (the sorted distinct columns the block touches).
-bool fb_host_jds_build(fb_ctx* c, int R, int max_window) {
+bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym) {
+    // sym: only the strictly lower triangle (columns < row: a prefix of every sorted CSR row) is stored; the window
+    // list then holds the distinct columns BELOW the block (sorted), and the block's own rows follow implicitly:
+    // window position of column j is  rank(j) for j < r0,  n_ext + (j - r0) for r0 <= j < row.
     const int n = c->n_dofs;
     const int nb = (n + R - 1) / R;
-    c->jds_R = R; c->jds_nb = nb;
+    auto rowlen = [&](int r) {
+        const int* lo = c->col.data() + c->rowptr[r]; const int* hi = c->col.data() + c->rowptr[r + 1];
+        return sym ? (int) (std::lower_bound(lo, hi, r) - lo) : (int) (hi - lo);
+    };
+    c->jds_R = R; c->jds_nb = nb; c->jds_sym = sym;
     c->jds_perm.assign((size_t) nb * R, 0); c->jds_len.assign((size_t) nb * R, 0); c->jds_slot.assign(n, 0);
     c->jds_jdp.assign(nb + 1, 0); c->jds_base.assign(nb + 1, 0);
     std::vector<int> maxlen(nb, 0);
@@ -382,16 +389,16 @@ bool fb_host_jds_build(fb_ctx* c, int R, int max_window) {
         const int r0 = b * R, nr = std::min(R, n - r0);
         std::vector<int> ord(nr);
         std::iota(ord.begin(), ord.end(), 0);
-        std::stable_sort(ord.begin(), ord.end(), [&](int a, int q) {
-            return c->rowptr[r0 + a + 1] - c->rowptr[r0 + a] > c->rowptr[r0 + q + 1] - c->rowptr[r0 + q];
-        });
+        std::vector<int> lens(nr);
+        for (int a = 0; a < nr; ++a) lens[a] = rowlen(r0 + a);
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int q) { return lens[a] > lens[q]; });
         for (int t = 0; t < nr; ++t) {
-            const int len = c->rowptr[r0 + ord[t] + 1] - c->rowptr[r0 + ord[t]];
+            const int len = lens[ord[t]];
             c->jds_perm[(size_t) b * R + t] = (unsigned short) ord[t];
             c->jds_len[(size_t) b * R + t] = (unsigned short) std::min(len, 65535);
             c->jds_slot[r0 + ord[t]] = (unsigned short) t;
         }
-        maxlen[b] = c->rowptr[r0 + ord[0] + 1] - c->rowptr[r0 + ord[0]];
+        maxlen[b] = lens[ord[0]];
     }
     for (int b = 0; b < nb; ++b) {
         if (maxlen[b] > 60000) return false;
@@ -429,19 +436,28 @@ bool fb_host_jds_build(fb_ctx* c, int R, int max_window) {
             const int* jd = &c->jds_jd[c->jds_jdp[b]];      // jd[j] = (padded) entries stored before diagonal j
             const int k0 = c->rowptr[r0], k1 = c->rowptr[r0 + nr];
             const size_t base = (size_t) c->jds_base[b];
-            buf.assign(c->col.begin() + k0, c->col.begin() + k1);
+            if (sym) {
+                buf.clear();
+                for (int k = k0; k < k1; ++k) if (c->col[k] < r0) buf.push_back(c->col[k]);
+            } else {
+                buf.assign(c->col.begin() + k0, c->col.begin() + k1);
+            }
             std::sort(buf.begin(), buf.end());
             buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
-            if ((int) buf.size() > max_window) {
+            if ((int) buf.size() + (sym ? R : 0) > max_window) {
 #pragma omp atomic write
                 ok = false;
                 continue;
             }
+            const int n_ext = (int) buf.size();
             for (int t = 0; t < nr; ++t) {
                 const int r = r0 + c->jds_perm[(size_t) b * R + t];
-                for (int k = c->rowptr[r]; k < c->rowptr[r + 1]; ++k)
-                    c->col16[base + jd[k - c->rowptr[r]] + t] =
-                        (unsigned short) (std::lower_bound(buf.begin(), buf.end(), c->col[k]) - buf.begin());
+                const int len = (int) c->jds_len[(size_t) b * R + t];
+                for (int k = c->rowptr[r]; k < c->rowptr[r] + len; ++k) {
+                    const int cj = c->col[k];
+                    c->col16[base + jd[k - c->rowptr[r]] + t] = (unsigned short)
+                        ((sym && cj >= r0) ? n_ext + (cj - r0) : (int) (std::lower_bound(buf.begin(), buf.end(), cj) - buf.begin()));
+                }
             }
             win[b] = buf;
         }
@@ -458,6 +474,10 @@ bool fb_host_jds_build(fb_ctx* c, int R, int max_window) {
     for (int b = 0; b < nb; ++b) std::copy(win[b].begin(), win[b].end(), c->win_list.begin() + c->win_off[b]);
     c->win_max = wmax;
     c->jds_maxlen = *std::max_element(maxlen.begin(), maxlen.end());
+    if (getenv("FB_VERBOSE"))
+        fprintf(stderr, "[fb] block-JDS%s: R=%d, %d blocks, %ld stored entries (%.2f per row), window avg %.0f max %d, longest row %d\n",
+                sym ? " (symmetric, lower triangle)" : "", R, nb, (long) c->jds_size, (double) c->jds_size / std::max(1, n),
+                (double) c->win_off[nb] / std::max(1, nb), wmax, c->jds_maxlen);
     return true;
 }
 

@@ -127,6 +127,50 @@ __device__ int scan_all(const Tables& T, P3 p) {
     return -min_index;
 }
 
+// The same linear scan done by a whole thread block for ONE point (all threads pass the same p and get the same
+// answer).  Warp w tests cells [32 w, 32 w + 32), then strides by the block size; the first hit in index order is
+// the minimum over the warps of their own first hit (a warp stops once a hit at a smaller index is known); the
+// nearest centroid is the lexicographic minimum of (distance^2, index), i.e. the first index that attains the
+// minimum -- exactly what the sequential loop returns.  Used for the few points whose guess and neighbours fail:
+// one block per such point (k_finish_scanned, k_particle_scanned) instead of one thread walking all cells.
+template <class Fam>
+__device__ int block_scan_all(const Tables& T, P3 p) {
+    __shared__ int s_first;
+    __shared__ double s_d2[32];
+    __shared__ int s_idx[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int n = Fam::count(T);
+    __syncthreads();                          // previous use of the scratch is over
+    if (threadIdx.x == 0) s_first = 0x7fffffff;
+    __syncthreads();
+    double min_d2 = 1e100; int min_index = 0;
+    for (int base = warp * 32; base < n; base += nwarp * 32) {
+        if (base > *((volatile int*) &s_first)) break;
+        const int c = base + lane;
+        bool hit = false;
+        if (c < n) {
+            hit = Fam::searchable(T, c) && Fam::in(Fam::recs(T)[c], p);
+            const double d2 = dist2(p, Fam::cents(T) + 3 * (long) c);
+            if (d2 < min_d2) { min_d2 = d2; min_index = c; }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) { if (lane == 0) atomicMin(&s_first, base + __ffs(m) - 1); break; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double d2o = __shfl_xor_sync(0xffffffffu, min_d2, o);
+        const int io = __shfl_xor_sync(0xffffffffu, min_index, o);
+        if (d2o < min_d2 || (d2o == min_d2 && io < min_index)) { min_d2 = d2o; min_index = io; }
+    }
+    if (lane == 0) { s_d2[warp] = min_d2; s_idx[warp] = min_index; }
+    __syncthreads();
+    if (s_first != 0x7fffffff) return s_first;
+    double d2 = s_d2[0]; int mi = s_idx[0];
+    for (int w = 1; w < nwarp; ++w)
+        if (s_d2[w] < d2 || (s_d2[w] == d2 && s_idx[w] < mi)) { d2 = s_d2[w]; mi = s_idx[w]; }
+    return -mi;
+}
+
 // guess -> neighbours -> (fallback) ; returns true on a hit
 template <class Fam>
 __device__ __forceinline__ bool try_guess(const Tables& T, P3 p, int guess, int& cell) {
@@ -148,42 +192,74 @@ __device__ __forceinline__ int locate_cell(const Tables& T, P3 p, int guess) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Guess-free linear scan for MANY points: one thread per point, cell records staged through
-// shared memory in tiles so that a block reads each record from L2 once.
+// Guess-free linear scan for MANY points.  A block of 8 warps serves 32 points (4 per warp); the cell
+// records are staged through shared memory in tiles (a block reads each record from L2 once) and the
+// 32 lanes of a warp test 32 different cells of the tile against the warp's 4 points.  First hit in
+// index order = lowest set bit of the first non-empty ballot; nearest centroid = lexicographic minimum
+// of (distance^2, index): both identical to the sequential loop of InterpolatorCells.cpp:292-306.
 // ---------------------------------------------------------------------------------------
 template <class Fam, int TILE>
-__global__ void __launch_bounds__(128) k_scan_cells(Tables T, long n, const double* __restrict__ pts, int* __restrict__ out) {
-    __shared__ typename Fam::Rec s_rec[TILE];
+__global__ void __launch_bounds__(256) k_scan_cells(Tables T, long n, const double* __restrict__ pts, int* __restrict__ out) {
+    constexpr int PPW = 4, WARPS = 8;
+    constexpr int WORDS = sizeof(typename Fam::Rec) / 8, WP = WORDS | 1;     // odd stride: conflict-free 8-byte reads
+    __shared__ double s_rec[TILE * WP];
     __shared__ double s_cent[TILE * 3];
     __shared__ int s_ok[TILE];
-    const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < n;
-    P3 p = {0, 0, 0};
-    if (active) p = ldp(pts, i);
-    bool found = !active;
-    int result = 0, min_index = 0;
-    double min_d2 = 1e100;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long i0 = ((long) blockIdx.x * WARPS + warp) * PPW;
+    P3 p[PPW];
+    bool found[PPW];
+    int result[PPW], min_index[PPW];
+    double min_d2[PPW];
+#pragma unroll
+    for (int q = 0; q < PPW; ++q) {
+        const bool active = i0 + q < n;
+        p[q] = active ? ldp(pts, i0 + q) : P3{0, 0, 0};
+        found[q] = !active; result[q] = 0; min_index[q] = 0; min_d2[q] = 1e100;
+    }
     const int n_cells = Fam::count(T);
-    constexpr int WORDS = sizeof(typename Fam::Rec) / 8;
     for (int base = 0; base < n_cells; base += TILE) {
         const int cnt = min(TILE, n_cells - base);
         __syncthreads();
         const double* src = (const double*) (Fam::recs(T) + base);
-        double* dst = (double*) s_rec;
-        for (int w = threadIdx.x; w < cnt * WORDS; w += blockDim.x) dst[w] = src[w];
+        for (int w = threadIdx.x; w < cnt * WORDS; w += blockDim.x) s_rec[(w / WORDS) * WP + (w % WORDS)] = src[w];
         for (int w = threadIdx.x; w < cnt * 3; w += blockDim.x) s_cent[w] = Fam::cents(T)[3 * (long) base + w];
         for (int w = threadIdx.x; w < cnt; w += blockDim.x) s_ok[w] = Fam::searchable(T, base + w);
         __syncthreads();
-        if (!found) {
-            for (int k = 0; k < cnt; ++k) {
-                if (s_ok[k] && Fam::in(s_rec[k], p)) { found = true; result = base + k; break; }
-                const double d2 = dist2(p, s_cent + 3 * k);
-                if (d2 < min_d2) { min_d2 = d2; min_index = base + k; }
+        for (int sub = 0; sub < cnt; sub += 32) {
+            const int k = sub + lane;
+            const bool valid = k < cnt;
+            const typename Fam::Rec& R = *reinterpret_cast<const typename Fam::Rec*>(&s_rec[(valid ? k : 0) * WP]);
+            const bool ok = valid && s_ok[valid ? k : 0];
+#pragma unroll
+            for (int q = 0; q < PPW; ++q) {
+                if (found[q]) continue;                      // warp-uniform
+                const bool hit = ok && Fam::in(R, p[q]);
+                if (valid) {
+                    const double d2 = dist2(p[q], s_cent + 3 * k);
+                    if (d2 < min_d2[q]) { min_d2[q] = d2; min_index[q] = base + k; }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (m) { found[q] = true; result[q] = base + sub + __ffs(m) - 1; }
             }
         }
-        if (__syncthreads_and(found)) break;
+        bool all = true;
+#pragma unroll
+        for (int q = 0; q < PPW; ++q) all &= found[q];
+        if (__syncthreads_and(all)) break;
     }
-    if (active) out[i] = found ? result : -min_index;
+#pragma unroll
+    for (int q = 0; q < PPW; ++q) {
+        if (i0 + q >= n) continue;
+        double d2 = min_d2[q]; int mi = min_index[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double d2o = __shfl_xor_sync(0xffffffffu, d2, o);
+            const int io = __shfl_xor_sync(0xffffffffu, mi, o);
+            if (d2o < d2 || (d2o == d2 && io < mi)) { d2 = d2o; mi = io; }
+        }
+        if (lane == 0) out[i0 + q] = found[q] ? result[q] : -mi;
+    }
 }
 
 // One Jacobi sweep of the chained-guess recurrence  T_i = F(p_i, |T_{i-1}|), T_{-1} = first_guess:
@@ -358,30 +434,37 @@ __device__ void hex_interp(const Tables& T, P3 p, int c, double out[5]) {
     weighted<8>(T, T.hex8 + 8 * (long) cell, w, out);
 }
 
-// dim = 2 variants hop from the surface cell to the adjacent 3D cell (:1662-1686, :1838-1861, :1898-1920)
-__device__ void surface_interp(const Tables& T, int rank, P3 p, int c, double out[5]) {
+// dim = 2 variants hop from the surface cell to the adjacent 3D cell (:1662-1686, :1838-1861, :1898-1920).
+// Split in two so that the linear-scan tail of locate_cell (:292-306) can be done warp-cooperatively in between:
+//   surface_resolve : cheap part; returns false when guess and neighbours failed (the scan decides),
+//   surface_finish  : interpolation in the resolved 3D cell.
+// `cell3d` is a tetrahedron (signed after a scan) except for rank 3 when the quadrangle's own hexahedron is taken.
+__device__ bool surface_resolve(const Tables& T, int rank, P3 p, int c, int& cell3d, bool& is_hex) {
     const int cell = abs(c);
+    is_hex = false;
     if (rank == 3) {
         const int h0 = T.quad2hex[2 * cell], h1 = T.quad2hex[2 * cell + 1];
         const double d = fabs(tri_fast_distance(T.tri[cell / 3], p));
-        if (d <= 100.0 * FB_ZERO) { hex_interp(T, p, h0, out); return; }
-        if (hex_in(T, p, h0)) { hex_interp(T, p, h0, out); return; }
-        hex_interp(T, p, hex_locate(T, p, h1), out);
-        return;
+        if (d <= 100.0 * FB_ZERO || hex_in(T, p, h0)) { cell3d = h0; is_hex = true; return true; }
+        return try_guess<TetFam>(T, p, h1 / 4, cell3d);            // hex_locate: tet search from the other hexahedron
     }
     const int t0 = T.tri2tet[2 * cell], t1 = T.tri2tet[2 * cell + 1];
     const double d = fabs(tri_fast_distance(T.tri[cell], p));
-    int tet;
-    if (d <= 100.0 * FB_ZERO) tet = t0;
-    else if (tet_in(T.tet[t0], p)) tet = t0;
-    else tet = locate_cell<TetFam>(T, p, t1);
-    if (rank == 1) tet_interp(T, p, tet, out); else qtet_interp(T, p, tet, out);
+    if (d <= 100.0 * FB_ZERO || tet_in(T.tet[t0], p)) { cell3d = t0; return true; }
+    return try_guess<TetFam>(T, p, t1, cell3d);
+}
+__device__ void surface_finish(const Tables& T, int rank, P3 p, int cell3d, bool is_hex, double out[5]) {
+    if (rank == 3) hex_interp(T, p, is_hex ? cell3d : hex_from_tet(T, p, cell3d), out);
+    else if (rank == 1) tet_interp(T, p, cell3d, out);
+    else qtet_interp(T, p, cell3d, out);
 }
 
-// final stage of locate_interpolate: base-family cell -> reported cell + interpolation
+// final stage of locate_interpolate: base-family cell -> reported cell + interpolation.  Surface points whose
+// hand-over to the 3D cell needs the linear scan are appended to `needy` and finished by k_finish_scanned.
 __global__ void __launch_bounds__(128) k_finish_interp(Tables T, int dim, int rank, long n, const double* __restrict__ pts,
                                                        const int* __restrict__ base_cells, int cells_are_final,
-                                                       int* __restrict__ cells_out, double* __restrict__ sol5) {
+                                                       int* __restrict__ cells_out, double* __restrict__ sol5,
+                                                       int* __restrict__ needy_count, int* __restrict__ needy_idx) {
     const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const P3 p = ldp(pts, i);
@@ -389,12 +472,34 @@ __global__ void __launch_bounds__(128) k_finish_interp(Tables T, int dim, int ra
     if (!cells_are_final && rank == 3) cell = (dim == 2) ? quad_from_tri(T, p, cell) : hex_from_tet(T, p, cell);
     if (cells_out) cells_out[i] = cell;
     double out[5];
-    if (dim == 2) surface_interp(T, rank, p, cell, out);
+    if (dim == 2) {
+        int cell3d; bool is_hex;
+        if (!surface_resolve(T, rank, p, cell, cell3d, is_hex)) { needy_idx[atomicAdd(needy_count, 1)] = (int) i; return; }
+        surface_finish(T, rank, p, cell3d, is_hex, out);
+    }
     else if (rank == 1) tet_interp(T, p, cell, out);
     else if (rank == 2) qtet_interp(T, p, cell, out);
     else hex_interp(T, p, cell, out);
 #pragma unroll
     for (int k = 0; k < 5; ++k) sol5[5 * i + k] = out[k];
+}
+
+// one block per deferred surface point: block-cooperative linear scan over the tetrahedra, then the interpolation
+__global__ void __launch_bounds__(256) k_finish_scanned(Tables T, int rank, const double* __restrict__ pts,
+                                                        const int* __restrict__ needy_count, const int* __restrict__ needy_idx,
+                                                        double* __restrict__ sol5) {
+    const int count = *needy_count;
+    for (int e = blockIdx.x; e < count; e += gridDim.x) {
+        const long i = needy_idx[e];
+        const P3 p = ldp(pts, i);
+        const int tet = block_scan_all<TetFam>(T, p);
+        if (threadIdx.x == 0) {
+            double out[5];
+            surface_finish(T, rank, p, tet, false, out);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) sol5[5 * i + k] = out[k];
+        }
+    }
 }
 
 // ---- gradients ----------------------------------------------------------------------
@@ -518,22 +623,29 @@ __global__ void __launch_bounds__(128) k_nodal_field(int n_nodes, const int* __r
 
 // Interpolator::average_nodal_fields (:142-170): only tet nodes are written, only centroid-type
 // nodes are read (TetgenMesh.cpp:819-837), so the in-place update is order independent.
-__global__ void k_smooth(int n_voro, const int* __restrict__ off, const int* __restrict__ list, const double* __restrict__ nxyz,
-                         double decay, double* __restrict__ nodal) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_smooth(int n_voro, const int* __restrict__ off, const int* __restrict__ list,
+                                                const double* __restrict__ nxyz, double decay, double* __restrict__ nodal) {
+    // one warp per tet node: the lanes stride its (long, uneven) list of pseudo-Voronoi neighbours; the weighted sums
+    // are reduced with shuffles (summation order differs from the sequential loop by ~1e-16 relative)
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n_voro) return;
     const int lo = off[i], hi = off[i + 1];
     if (hi == lo) return;
     const P3 tetnode = ldp(nxyz, i);
     P3 vec = {0, 0, 0};
     double w_sum = 0;
-    for (int q = lo; q < hi; ++q) {
+    for (int q = lo + lane; q < hi; q += 32) {
         const int nb = list[q];
         const double w = exp(decay * sqrt(dist2(tetnode, nxyz + 3 * (long) nb)));
         w_sum += w;
         vec = vec + P3{nodal[5 * (long) nb], nodal[5 * (long) nb + 1], nodal[5 * (long) nb + 2]} * w;
     }
-    if (w_sum > 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        w_sum += __shfl_xor_sync(0xffffffffu, w_sum, o);
+        vec.x += __shfl_xor_sync(0xffffffffu, vec.x, o); vec.y += __shfl_xor_sync(0xffffffffu, vec.y, o); vec.z += __shfl_xor_sync(0xffffffffu, vec.z, o);
+    }
+    if (lane == 0 && w_sum > 0) {
         vec = vec * (1.0 / w_sum);
         nodal[5 * (long) i] = vec.x; nodal[5 * (long) i + 1] = vec.y; nodal[5 * (long) i + 2] = vec.z;
     }
@@ -541,13 +653,34 @@ __global__ void k_smooth(int n_voro, const int* __restrict__ off, const int* __r
 
 // ---- PIC particles --------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_particle_cells(Tables T, long n, const double* __restrict__ pts, const int* __restrict__ cell2hex,
-                                                        const int* __restrict__ hex2cell, int* __restrict__ cell_inout) {
+                                                        const int* __restrict__ hex2cell, int* __restrict__ cell_inout,
+                                                        int* __restrict__ needy_count, int* __restrict__ needy_idx) {
     const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const P3 p = ldp(pts, i);
     const int c = cell_inout[i];
     const int guess = c < 0 ? 0 : cell2hex[c];
-    const int fc = hex_locate(T, ldp(pts, i), guess);
+    int tet;
+    // hex_locate (:1536-1562): tetrahedron from the guess / its neighbours; particles that left the neighbourhood
+    // are deferred to the block-cooperative scan of k_particle_scanned
+    if (!try_guess<TetFam>(T, p, guess / 4, tet)) { needy_idx[atomicAdd(needy_count, 1)] = (int) i; return; }
+    const int fc = hex_from_tet(T, p, tet);
     cell_inout[i] = fc < 0 ? -1 : hex2cell[fc];
+}
+
+__global__ void __launch_bounds__(256) k_particle_scanned(Tables T, const double* __restrict__ pts, const int* __restrict__ hex2cell,
+                                                          const int* __restrict__ needy_count, const int* __restrict__ needy_idx,
+                                                          int* __restrict__ cell_inout) {
+    const int count = *needy_count;
+    for (int e = blockIdx.x; e < count; e += gridDim.x) {
+        const long i = needy_idx[e];
+        const P3 p = ldp(pts, i);
+        const int tet = block_scan_all<TetFam>(T, p);
+        if (threadIdx.x == 0) {
+            const int fc = hex_from_tet(T, p, tet);
+            cell_inout[i] = fc < 0 ? -1 : hex2cell[fc];
+        }
+    }
 }
 
 __global__ void __launch_bounds__(128) k_particle_field(Tables T, long n, const double* __restrict__ pts, const int* __restrict__ cell2hex,
@@ -634,7 +767,7 @@ void launch_extract(fb_ctx* c, int smoothen) {
                                             c->d_nodal.p);
     c->launches += 2;
     if (smoothen && c->n_voro > 0) {
-        k_smooth<<<(c->n_voro + 127) / 128, 128, 0, c->stream>>>(c->n_voro, c->d_voro_off.p, c->d_voro_list.p, c->d_nxyz.p, c->decay_factor, c->d_nodal.p);
+        k_smooth<<<(c->n_voro + 3) / 4, 128, 0, c->stream>>>(c->n_voro, c->d_voro_off.p, c->d_voro_list.p, c->d_nxyz.p, c->decay_factor, c->d_nodal.p);
         c->launches++;
     }
 }
@@ -668,12 +801,12 @@ static int chain_fixpoint(fb_ctx* c, const Tables& T, long n, const double* d_pt
 
 int launch_locate_chain(fb_ctx* c, int dim, int rank, long n, const double* d_pts, int** result) {
     const Tables T = make_tables(c);
-    const unsigned g = (unsigned) ((n + 127) / 128);
     // abs(-1) = 1 is the first guess of the reference loop (SolutionReader.cpp:145, InterpolatorCells.cpp:443);
     // hex/quad ranks divide it by 4/3 (:1539, :1955)
     const int first_guess = (rank == 3) ? 0 : 1;
-    if (dim == 2) k_scan_cells<TriFam, 64><<<g, 128, 0, c->stream>>>(T, n, d_pts, c->d_scan.p);
-    else k_scan_cells<TetFam, 64><<<g, 128, 0, c->stream>>>(T, n, d_pts, c->d_scan.p);
+    const unsigned gs = (unsigned) ((n + 31) / 32);          // 32 points per block of 8 warps
+    if (dim == 2) k_scan_cells<TriFam, 128><<<gs, 256, 0, c->stream>>>(T, n, d_pts, c->d_scan.p);
+    else k_scan_cells<TetFam, 128><<<gs, 256, 0, c->stream>>>(T, n, d_pts, c->d_scan.p);
     c->launches++;
     cudaMemsetAsync(c->d_flag.p, 0, 4 * sizeof(int), c->stream);
     const int rc = (dim == 2) ? chain_fixpoint<TriFam>(c, T, n, d_pts, first_guess) : chain_fixpoint<TetFam>(c, T, n, d_pts, first_guess);
@@ -685,14 +818,24 @@ int launch_locate_chain(fb_ctx* c, int dim, int rank, long n, const double* d_pt
 void launch_finish_interp(fb_ctx* c, int dim, int rank, long n, const double* d_pts, const int* d_base, int final_cells,
                           int* d_cells_out, double* d_sol) {
     const Tables T = make_tables(c);
-    k_finish_interp<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(T, dim, rank, n, d_pts, d_base, final_cells, d_cells_out, d_sol);
+    if (dim == 2) { c->d_needy.alloc((size_t) n + 1); cudaMemsetAsync(c->d_needy.p, 0, sizeof(int), c->stream); }
+    k_finish_interp<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(T, dim, rank, n, d_pts, d_base, final_cells, d_cells_out, d_sol,
+                                                                        c->d_needy.p, c->d_needy.p + 1);
     c->launches++;
+    if (dim == 2) {     // deferred points (device-side count): one block each, grid-stride
+        k_finish_scanned<<<(unsigned) std::min<long>(n, 4L * c->n_sm), 256, 0, c->stream>>>(T, rank, d_pts, c->d_needy.p, c->d_needy.p + 1, d_sol);
+        c->launches++;
+    }
 }
 
 void launch_particle_cells(fb_ctx* c, long n, const double* d_pts, int* d_cells) {
     const Tables T = make_tables(c);
-    k_particle_cells<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(T, n, d_pts, c->d_cell2hex.p, c->d_hex2cell.p, d_cells);
-    c->launches++;
+    c->d_needy.alloc((size_t) n + 1);
+    cudaMemsetAsync(c->d_needy.p, 0, sizeof(int), c->stream);
+    k_particle_cells<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(T, n, d_pts, c->d_cell2hex.p, c->d_hex2cell.p, d_cells,
+                                                                         c->d_needy.p, c->d_needy.p + 1);
+    k_particle_scanned<<<(unsigned) std::min<long>(n, 8L * c->n_sm), 256, 0, c->stream>>>(T, d_pts, c->d_hex2cell.p, c->d_needy.p, c->d_needy.p + 1, d_cells);
+    c->launches += 2;
 }
 
 void launch_particle_field(fb_ctx* c, long n, const double* d_pts, const int* d_cells, double* d_E) {

@@ -408,17 +408,39 @@ __global__ void __launch_bounds__(THREADS) k_spmv_stream(int n_blocks, const int
     }
 }
 
-__global__ void __launch_bounds__(256) k_update(int n, const double* __restrict__ d, const double* __restrict__ h,
+template <bool ZERO_H>
+__global__ void __launch_bounds__(256, 6) k_update(int n, const double* __restrict__ d, double* __restrict__ h,
                                                 const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ g,
                                                 double* __restrict__ partial, unsigned* counter, CgScalars* __restrict__ cgs,
                                                 const double* __restrict__ alpha_in, double* __restrict__ beta_out) {
     if (cgs->done) return;
     const double alpha = *alpha_in;
     double acc[2] = {0, 0};
-    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+    // two entries per thread and trip with 16-byte accesses; all five loads of a trip are issued before the first
+    // store, so every thread keeps 80 B in flight (the scalar loop serialised load -> fma -> store per vector)
+    const long n2 = n >> 1, stride = (long) gridDim.x * blockDim.x;
+    const double2* __restrict__ d2 = reinterpret_cast<const double2*>(d);
+    const double2* __restrict__ i2 = reinterpret_cast<const double2*>(dinv);
+    double2* __restrict__ h2 = reinterpret_cast<double2*>(h);
+    double2* __restrict__ x2 = reinterpret_cast<double2*>(x);
+    double2* __restrict__ g2 = reinterpret_cast<double2*>(g);
+#pragma unroll 1
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        const double2 dd = __ldg(&d2[i]), di = __ldg(&i2[i]), hh = h2[i];
+        double2 xx = x2[i], gg = g2[i];
+        xx.x += alpha * dd.x; xx.y += alpha * dd.y;
+        gg.x += alpha * hh.x; gg.y += alpha * hh.y;
+        x2[i] = xx; g2[i] = gg;
+        if (ZERO_H) h2[i] = make_double2(0.0, 0.0);   // the symmetric SpMV accumulates into h with reductions: hand it a zeroed vector
+        acc[0] += gg.x * gg.x * di.x + gg.y * gg.y * di.y;
+        acc[1] += gg.x * gg.x + gg.y * gg.y;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int i = n - 1;
         x[i] += alpha * d[i];
         const double gi = g[i] + alpha * h[i];
         g[i] = gi;
+        if (ZERO_H) h[i] = 0.0;
         acc[0] += gi * gi * dinv[i];
         acc[1] += gi * gi;
     }
@@ -524,12 +546,15 @@ __global__ void __launch_bounds__(THREADS) k_spmv_window(int n_blocks, const int
 // ---------------------------------------------------------------------------------------
 __global__ void k_csr_to_jds(int n, int R, const int* __restrict__ rowptr, const unsigned short* __restrict__ slot,
                              const int* __restrict__ jbase, const int* __restrict__ jdp, const int* __restrict__ jd,
-                             const double* __restrict__ val, double* __restrict__ val_jds) {
-    // 8 lanes per row
+                             const double* __restrict__ val, double* __restrict__ val_jds,
+                             const int* __restrict__ diagpos, double* __restrict__ diag) {
+    // 8 lanes per row; diagpos != nullptr: symmetric layout, only the entries left of the diagonal (a prefix of
+    // the sorted row) are stored and the diagonal goes to diag[]
     const int lane = threadIdx.x & 7;
     for (long r = ((long) blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < n; r += ((long) gridDim.x * blockDim.x) >> 3) {
         const int b = (int) (r / R);
-        const int base = jbase[b], lo = rowptr[r], hi = rowptr[r + 1], t = slot[r];
+        const int base = jbase[b], lo = rowptr[r], hi = diagpos ? diagpos[r] : rowptr[r + 1], t = slot[r];
+        if (diagpos && lane == 0) diag[r] = val[hi];
         const int* __restrict__ jdb = jd + jdp[b];
         for (int k = lo + lane; k < hi; k += 8) val_jds[(long) base + jdb[k - lo] + t] = val[k];
     }
@@ -605,6 +630,97 @@ __global__ void __launch_bounds__(R / 2) k_spmv_jds(int n, int n_blocks, const i
 }
 
 // ---------------------------------------------------------------------------------------
+// Symmetric block-JDS SpMV: the matrix after the symmetric Dirichlet elimination (apply_boundary_values with
+// eliminate_columns, DealSolver.cpp:439) is symmetric, so only its strictly lower triangle is stored and
+// streamed -- half the bytes of k_spmv_jds.  Thread t owns two rows i of the block; for every stored entry
+// a_ij (j < i) it adds a_ij x_j to its own sum (gather from the shared-memory window, as before) AND adds
+// a_ij x_i to the shared-memory accumulator of column j (the transposed entry).  At the end of the block the
+// accumulators -- window columns below the block and the block's own rows, the latter including gather sum
+// and diagonal -- are added to the (pre-zeroed) output vector with FP64 reductions in L2 (red.global.add.f64),
+// because later blocks scatter into the same rows.
+//   d.h = sum_i d_i (a_ii d_i + 2 sum_{j<i} a_ij d_j)   (d'L'd = d'Ld), so the dot product needs only the gather.
+// Summation order differs from the sequential CSR order and, through the reductions, from run to run
+// (~1e-16 relative), far below the 1e-8 parity bar.
+// Algorithmic bytes per launch of THIS formulation: 10 B per stored entry ((nnz - n) / 2 of them) + 8 n (diag)
+// + 16 n (read d, accumulate h) + 4 n (row permutation / lengths).
+// STATUS (B200, X mesh, profiles/r01e_*): correct, DRAM traffic 4.2 GB instead of 7.6 GB per launch, but 2.09 ms
+// against 1.43 ms for k_spmv_jds: shared-memory FP64 atomics are CAS loops (ATOMS.CAST.SPIN) that serialise in every
+// thread (+0.7 ms), and the lower-triangle row lengths (0..26) unbalance the jagged diagonals (barrier stalls; the
+// gather alone, without any scatter, still takes 1.39 ms).  Kept as a selectable variant (option "spmv_kernel" 310 /
+// 311), not the default; DESIGN.md section 3.5 lists what a faster version needs.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+template <int R>
+__global__ void __launch_bounds__(R / 2, 1536 / R) k_spmv_sym(int n, int n_blocks, const int* __restrict__ jbase,
+                                                    const unsigned short* __restrict__ perm, const unsigned short* __restrict__ rlen,
+                                                    const int* __restrict__ jdp, const int* __restrict__ jd,
+                                                    const unsigned short* __restrict__ col16, const double* __restrict__ val,
+                                                    const double* __restrict__ diag,
+                                                    const int* __restrict__ win_off, const int* __restrict__ win_list,
+                                                    const double* __restrict__ xin, double* __restrict__ out,
+                                                    double* __restrict__ partial, unsigned* counter, CgScalars* __restrict__ cgs,
+                                                    double* __restrict__ alpha_out, int wcap, int jcap) {
+    if (cgs->done) return;
+    constexpr int T = R / 2;
+    extern __shared__ double s_dyn[];
+    double* s_x = s_dyn;                          // wcap + R input entries (window below the block, then the block's rows)
+    double* s_y = s_dyn + wcap + R;               // matching accumulators of the transposed entries
+    int* s_jd = (int*) (s_y + wcap + R);          // jcap + 1 diagonal offsets (in 2-entry units)
+    const int tid = threadIdx.x;
+    double acc[2] = {0, 0};
+    for (int b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        const int r0 = b * R;
+        const int w0 = __ldg(&win_off[b]), nw = __ldg(&win_off[b + 1]) - w0;
+        const int j0 = __ldg(&jdp[b]), nj = __ldg(&jdp[b + 1]) - j0;
+        const long base = __ldg(&jbase[b]);
+        const int sl0 = r0 + 2 * tid, sl1 = sl0 + 1;
+        const int len0 = sl0 < n ? (int) __ldg(&rlen[sl0]) : 0, len1 = sl1 < n ? (int) __ldg(&rlen[sl1]) : 0;
+        const int p0 = sl0 < n ? (int) __ldg(&perm[sl0]) : 0, p1 = sl1 < n ? (int) __ldg(&perm[sl1]) : 0;
+        const double dg0 = sl0 < n ? __ldg(&diag[r0 + p0]) : 0.0, dg1 = sl1 < n ? __ldg(&diag[r0 + p1]) : 0.0;
+        for (int i = tid; i < nw; i += T) { s_x[i] = __ldg(&xin[__ldg(&win_list[w0 + i])]); s_y[i] = 0.0; }
+        for (int i = tid; i < R; i += T) { s_x[nw + i] = (r0 + i < n) ? __ldg(&xin[r0 + i]) : 0.0; s_y[nw + i] = 0.0; }
+        for (int i = tid; i < nj; i += T) s_jd[i] = __ldg(&jd[j0 + i]) >> 1;
+        __syncthreads();
+        const double x0 = s_x[nw + p0], x1 = s_x[nw + p1];
+        const double2* __restrict__ vb = reinterpret_cast<const double2*>(val + base) + tid;
+        const ushort2* __restrict__ cb = reinterpret_cast<const ushort2*>(col16 + base) + tid;
+        double sum0 = 0, sum1 = 0;
+        double2 va[4], vb2[4];
+        ushort2 ca[4], cb2[4];
+#define FB_ISSUE(JJ, V, C)                                                                     \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u)                                          \
+            if ((JJ) + u < len0) { const int o = s_jd[(JJ) + u]; V[u] = __ldcg(&vb[o]); C[u] = __ldcg(&cb[o]); }
+#define FB_CONSUME(JJ, V, C)                                                                   \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                        \
+            if ((JJ) + u < len0) { sum0 += V[u].x * s_x[C[u].x]; atomicAdd(&s_y[C[u].x], V[u].x * x0); } \
+            if ((JJ) + u < len1) { sum1 += V[u].y * s_x[C[u].y]; atomicAdd(&s_y[C[u].y], V[u].y * x1); } \
+        }
+        FB_ISSUE(0, va, ca)
+        for (int j = 0; j < len0; j += 8) {
+            FB_ISSUE(j + 4, vb2, cb2)
+            FB_CONSUME(j, va, ca)
+            FB_ISSUE(j + 8, va, ca)
+            FB_CONSUME(j + 4, vb2, cb2)
+        }
+#undef FB_ISSUE
+#undef FB_CONSUME
+        if (sl0 < n) { atomicAdd(&s_y[nw + p0], dg0 * x0 + sum0); acc[0] += x0 * (dg0 * x0 + 2.0 * sum0); }
+        if (sl1 < n) { atomicAdd(&s_y[nw + p1], dg1 * x1 + sum1); acc[0] += x1 * (dg1 * x1 + 2.0 * sum1); }
+        __syncthreads();
+        for (int i = tid; i < nw; i += T) { const double v = s_y[i]; if (v != 0.0) red_add_f64(&out[__ldg(&win_list[w0 + i])], v); }
+        for (int i = tid; i < R; i += T) if (r0 + i < n) red_add_f64(&out[r0 + i], s_y[nw + i]);
+        __syncthreads();
+    }
+    double tot[2];
+    if (reduce_publish<2>(acc, partial, counter, tot)) {
+        cg_finish_spmv<false>(cgs, tot, alpha_out);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Persistent cooperative CG for the native (L2-resident) meshes: the WHOLE solve is one launch.
 // One CTA per SM owns a contiguous, nnz-balanced slice of rows for the entire solve: its matrix
 // values live in shared memory, its column indices in registers, its slices of x, g, d, h, 1/diag
@@ -616,19 +732,21 @@ __global__ void __launch_bounds__(R / 2) k_spmv_jds(int n, int n_blocks, const i
 // (deal.II SolverCG): h = A d; alpha = gh/(d.h); x += alpha d; g += alpha h; test |g|;
 // beta = g.Dinv g / gh; d = beta d - Dinv g.
 // ---------------------------------------------------------------------------------------
-// All-to-all through L2 without a central counter: every CTA publishes {partials, sequence flag};
-// warp 0 of every CTA polls the G flags (message passing: data store, fence, flag store | flag load,
-// fence, data load), then adds the G partials in index order -> bit-identical totals in all CTAs.
-// Partials are double-buffered by sequence parity: a CTA can run at most one phase ahead of the
-// slowest one, so a slot is never overwritten while somebody still reads it.
-__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ int ld_relaxed_gpu(const int* p) { int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// Grid-wide all-reduce through L2: every CTA publishes its partial sums, then arrives on ONE monotonic counter
+// with a release reduction (red.release.gpu: the partials and -- through the preceding bar.sync -- the d slice
+// written by the other threads of the CTA are visible to whoever observes the count); one lane per CTA polls the
+// counter with acquire loads until all G CTAs of this phase have arrived, then warp 0 adds the G partials in index
+// order -> bit-identical totals in all CTAs.  (A first version polled one flag per CTA: G x G loads per phase on
+// five cache lines of one L2 slice cost ~9000 cycles per barrier; the single counter costs 148 loads per poll round.)
+// Partials are double-buffered by sequence parity: a CTA can run at most one phase ahead of the slowest one, so a
+// slot is never overwritten while somebody still reads it.
+__device__ __forceinline__ void red_release_gpu_inc(unsigned* p) { asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 struct GridComm {
     double* part;        // [2][NVMAX][G]
-    int* flag;           // [G]
-    int G, seq;
+    unsigned* counter;   // arrivals since the launch (zeroed by the host)
+    int G; unsigned seq;
     long long* dbg;
 };
 constexpr int PERS_NV = 2;
@@ -647,7 +765,7 @@ __device__ __forceinline__ void grid_allreduce(GridComm& gc, double (&v)[NV], do
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (lane == 0) s_red[k][warp] = x;
     }
-    __syncthreads();            // also orders this CTA's global stores (d slice) before the flag below
+    __syncthreads();            // also orders this CTA's global stores (d slice) before the arrival below
     if (warp == 0) {
         if (gc.dbg) t1 = clock64();
 #pragma unroll
@@ -657,25 +775,27 @@ __device__ __forceinline__ void grid_allreduce(GridComm& gc, double (&v)[NV], do
             for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
             if (lane == 0) __stcg(&slot[(size_t) k * gc.G + blockIdx.x], t);
         }
-        // release store: the partials above and (through the bar.sync) the d slice written by the other
-        // threads of this CTA are visible to whoever observes the flag
-        if (lane == 0) st_release_gpu(&gc.flag[blockIdx.x], gc.seq);
-        if (gc.dbg) t2 = clock64();
-        bool ready;
-        do {                     // every lane polls its (up to 8) flags in one batch of independent loads
-            ready = true;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int i = lane + 32 * j;
-                if (i < gc.G) ready &= (ld_relaxed_gpu(&gc.flag[i]) >= gc.seq);
-            }
-        } while (!__all_sync(0xffffffffu, ready));
+        if (lane == 0) {
+            red_release_gpu_inc(gc.counter);
+            if (gc.dbg) t2 = clock64();
+            const unsigned target = gc.seq * (unsigned) gc.G;
+            while (ld_acquire_gpu(gc.counter) < target) { }
+        }
+        __syncwarp();
         if (gc.dbg) t3 = clock64();
-        fence_acq_rel_gpu();     // acquire side of the message passing
+        // all partials of all NV sums are requested before the first add (G <= 160: five per lane and sum), so the
+        // read costs one L2 round trip instead of one per 32 CTAs
+        double pv[NV][5];
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const int i = lane + 32 * j;
+                pv[k][j] = (i < gc.G) ? __ldcg(&slot[(size_t) k * gc.G + i]) : 0.0;
+            }
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            double x = 0;
-            for (int i = lane; i < gc.G; i += 32) x += __ldcg(&slot[(size_t) k * gc.G + i]);
+            double x = ((pv[k][0] + pv[k][1]) + (pv[k][2] + pv[k][3])) + pv[k][4];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
             if (lane == 0) s_red[k][0] = x;
@@ -696,14 +816,19 @@ template <int THREADS, int PT>
 __global__ void __launch_bounds__(THREADS, 1) k_cg_persistent(const int* __restrict__ cta_row, const int* __restrict__ rowptr,
                                                               const int* __restrict__ col, const double* __restrict__ val,
                                                               const double* __restrict__ rhs, const double* __restrict__ dinv_g,
-                                                              double* x_g, double* d_g, double* partial, int* flags, CgScalars* cgs,
+                                                              double* x_g, double* z_g, double* partial, int* flags, CgScalars* cgs,
                                                               int cap, int rmax, long long* dbg) {
+    // TWO grid-wide barriers per iteration.  What crosses SMs is z = Dinv g (published by the owner of a row right
+    // after the update, i.e. BEFORE the all-reduce that yields beta); every CTA keeps the search direction at the
+    // column of each of its non-zeros in shared memory (s_dc) and advances it itself,  d_j <- beta d_j - z_j,  with
+    // the very same two instructions (__dmul_rn, __fma_rn) the owner uses, so all copies of d_j are bit-identical.
+    // A third barrier ("every slice of the new d is visible") is therefore not needed.
     extern __shared__ double smem[];
     long long t_ph[6] = {0, 0, 0, 0, 0, 0}, t_last = clock64();
     auto lap = [&](int k) { if (dbg) { const long long t = clock64(); t_ph[k] += t - t_last; t_last = t; } };
     double* s_val = smem;
-    double* s_prod = s_val + cap;
-    double* s_x = s_prod + cap;
+    double* s_dc = s_val + cap;          // d (at start: x) at the column of every non-zero of the slice
+    double* s_x = s_dc + cap;
     double* s_g = s_x + rmax;
     double* s_d = s_g + rmax;
     double* s_h = s_d + rmax;
@@ -711,7 +836,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_cg_persistent(const int* __restr
     int* s_rp = (int*) (s_dinv + rmax);
     __shared__ double s_red[PERS_NV][32];
     const int tid = threadIdx.x;
-    GridComm gc = {partial, flags, (int) gridDim.x, 0, dbg};
+    GridComm gc = {partial, (unsigned*) flags, (int) gridDim.x, 0u, dbg};
     const int r0 = cta_row[blockIdx.x], nr = cta_row[blockIdx.x + 1] - r0;
     const int k0 = rowptr[r0], cnt = rowptr[r0 + nr] - k0;
 
@@ -720,26 +845,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_cg_persistent(const int* __restr
     for (int u = 0; u < PT; ++u) {
         const int k = tid + u * THREADS;
         cidx[u] = (k < cnt) ? __ldg(&col[k0 + k]) : -1;
-        if (k < cnt) s_val[k] = __ldg(&val[k0 + k]);
+        if (k < cnt) { s_val[k] = __ldg(&val[k0 + k]); s_dc[k] = x_g[cidx[u]]; }
     }
     for (int r = tid; r <= nr; r += THREADS) s_rp[r] = rowptr[r0 + r] - k0;
-    for (int r = tid; r < nr; r += THREADS) { s_x[r] = x_g[r0 + r]; s_dinv[r] = dinv_g[r0 + r]; }
+    for (int r = tid; r < nr; r += THREADS) { s_x[r] = x_g[r0 + r]; s_dinv[r] = dinv_g[r0 + r]; s_d[r] = 0.0; }
     __syncthreads();
 
-    // s_h = (A vec) on the CTA's rows; vec is gathered through L2 (other CTAs wrote it).  Four lanes add
-    // one row (fixed order: lane-strided partial sums, then a 4-lane butterfly), so the ~150-entry rows of
-    // the tet vertices do not serialise the phase.
-    auto spmv = [&](const double* vec) {
-#pragma unroll
-        for (int u = 0; u < PT; ++u)
-            if (cidx[u] >= 0) s_prod[tid + u * THREADS] = s_val[tid + u * THREADS] * __ldcg(&vec[cidx[u]]);
-        __syncthreads();
+    // s_h = A * (vector held in s_dc) on the CTA's rows.  Four lanes add one row (fixed order: lane-strided partial
+    // sums, then a 4-lane butterfly), so the ~150-entry rows of the tet vertices do not serialise the phase.
+    auto rowsums = [&]() {
         const int sub = tid & 3;
         for (int rb = 0; rb < nr; rb += THREADS / 4) {          // block-uniform trip count
             const int r = rb + (tid >> 2);
             double sum = 0;
             if (r < nr)
-                for (int j = s_rp[r] + sub; j < s_rp[r + 1]; j += 4) sum += s_prod[j];
+                for (int j = s_rp[r] + sub; j < s_rp[r + 1]; j += 4) sum += s_val[j] * s_dc[j];
             sum += __shfl_xor_sync(0xffffffffu, sum, 1);
             sum += __shfl_xor_sync(0xffffffffu, sum, 2);
             if (r < nr && sub == 0) s_h[r] = sum;
@@ -749,63 +869,56 @@ __global__ void __launch_bounds__(THREADS, 1) k_cg_persistent(const int* __restr
 
     const double tol2 = cgs->tol2;
     const int max_iter = cgs->max_iter;
-    // ---- start: g = A x - b (deal.II SolverCG), d = -Dinv g ----
-    spmv(x_g);
+    // ---- start: g = A x - b (deal.II SolverCG), z = Dinv g published ----
+    rowsums();
     double acc[2] = {0, 0}, tot[2];
     for (int r = tid; r < nr; r += THREADS) {
         const double g = s_h[r] - rhs[r0 + r];
         s_g[r] = g;
+        __stcg(&z_g[r0 + r], __dmul_rn(s_dinv[r], g));
         acc[0] += g * g * s_dinv[r];
         acc[1] += g * g;
     }
-    grid_allreduce<2>(gc, acc, s_red, tot);
-    double gh = tot[0], res2 = tot[1];
+    grid_allreduce<2>(gc, acc, s_red, tot);       // also: every slice of z is visible
+    double gh = tot[0], res2 = tot[1], beta = 0.0;    // first direction: d = -z  (beta = 0; x, the old content of s_dc, is finite)
     int it = 0;
     int done = (res2 <= tol2) ? 1 : ((max_iter <= 0 || res2 != res2) ? 2 : 0);
-    if (!done) {
-        for (int r = tid; r < nr; r += THREADS) { const double d = -s_dinv[r] * s_g[r]; s_d[r] = d; __stcg(&d_g[r0 + r], d); }
-        double z[1] = {0}, zt[1];
-        grid_allreduce<1>(gc, z, s_red, zt);          // barrier: every slice of d is visible
-    }
     while (!done) {
-        // phase A: h = A d, alpha = gh / (d.h)
+        // phase A: d = beta d - z (own rows and the column copies), h = A d, alpha = gh / (d.h)
         lap(5);
-        spmv(d_g);
+#pragma unroll
+        for (int u = 0; u < PT; ++u)
+            if (cidx[u] >= 0) { const int k = tid + u * THREADS; s_dc[k] = __fma_rn(beta, s_dc[k], -__ldcg(&z_g[cidx[u]])); }
+        for (int r = tid; r < nr; r += THREADS) s_d[r] = __fma_rn(beta, s_d[r], -__dmul_rn(s_dinv[r], s_g[r]));
+        __syncthreads();
+        rowsums();
         double a[1] = {0}, at[1];
         for (int r = tid; r < nr; r += THREADS) a[0] += s_d[r] * s_h[r];
         lap(0);
-        grid_allreduce<1>(gc, a, s_red, at);
+        grid_allreduce<1>(gc, a, s_red, at);      // also: every CTA has finished reading z
         lap(1);
-        // phase B: x += alpha d, g += alpha h, |g|, g.Dinv g
+        // phase B: x += alpha d, g += alpha h, z = Dinv g published, |g|, g.Dinv g
         const double alpha = gh / at[0];
         acc[0] = 0; acc[1] = 0;
         for (int r = tid; r < nr; r += THREADS) {
             s_x[r] += alpha * s_d[r];
             const double g = s_g[r] + alpha * s_h[r];
             s_g[r] = g;
+            __stcg(&z_g[r0 + r], __dmul_rn(s_dinv[r], g));
             acc[0] += g * g * s_dinv[r];
             acc[1] += g * g;
         }
         lap(2);
         grid_allreduce<2>(gc, acc, s_red, tot);
         lap(3);
-        // phase C: convergence test (deal.II SolverControl: success first), d = beta d - Dinv g
+        // convergence test (deal.II SolverControl: success first), beta
         res2 = tot[1];
         ++it;
-        const double beta = tot[0] / gh;
+        beta = tot[0] / gh;
         gh = tot[0];
         if (res2 <= tol2) done = 1;
         else if (it >= max_iter || res2 != res2) done = 2;
-        if (!done) {
-            for (int r = tid; r < nr; r += THREADS) {
-                const double d = beta * s_d[r] - s_dinv[r] * s_g[r];
-                s_d[r] = d;
-                __stcg(&d_g[r0 + r], d);
-            }
-            double z[1] = {0}, zt[1];
-            lap(4);
-            grid_allreduce<1>(gc, z, s_red, zt);      // barrier: every slice of the new d is visible
-        }
+        lap(4);
     }
     if (dbg && tid == 0 && blockIdx.x < 4) for (int k = 0; k < 6; ++k) dbg[6 * blockIdx.x + k] = t_ph[k];
     for (int r = tid; r < nr; r += THREADS) x_g[r0 + r] = s_x[r];
@@ -875,7 +988,7 @@ void stream_block_shape(int kernel, int& chunk, int& maxrows) {
 
 int choose_lanes(const fb_ctx* c) {
     // 0 selects the row-block streaming kernel (option "spmv_kernel": -1 auto, 0 stream, else lanes per row)
-    if (c->spmv_kernel >= 0) return c->spmv_kernel;
+    if (c->spmv_kernel >= 0) return (c->world > 1 && c->spmv_kernel >= 310) ? 302 : c->spmv_kernel;
     if (c->nnz >= 4000000) return 302;
     const double avg = c->n_dofs ? (double) c->nnz / c->n_dofs : 1.0;
     if (avg > 48) return 32;
@@ -914,7 +1027,7 @@ void launch_apply_bc_matrix(fb_ctx* c) {
 void launch_csr_to_jds(fb_ctx* c) {
     const int g = grid_for(c, (long) c->n_dofs * 8, 256);
     k_csr_to_jds<<<g, 256, 0, c->stream>>>(c->n_dofs, c->jds_R, c->d_rowptr.p, c->d_jds_slot.p, c->d_jds_base.p, c->d_jds_jdp.p, c->d_jds_jd.p,
-                                           c->d_val.p, c->d_val_jds.p);
+                                           c->d_val.p, c->d_val_jds.p, c->jds_sym ? c->d_diagpos.p : nullptr, c->d_diag.p);
     c->launches++;
 }
 
@@ -928,6 +1041,23 @@ template <bool INIT>
 static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, double* alpha) {
     unsigned* counter = (unsigned*) (c->d_partial.p + c->d_partial.n - 8);
     double* part = c->d_partial.p;
+    if (lanes >= 310) {         // symmetric block-JDS kernel (310: 512 rows per block, 311: 256); accumulates into a zeroed `out`
+        if (INIT) { spmv_dispatch<true>(c, 8, xin, out, alpha); return; }      // the initial residual (once per solve) streams the CSR copy
+        const int nb = c->jds_nb;
+        const size_t smem = 2 * sizeof(double) * ((size_t) c->win_cap + c->jds_R) + sizeof(int) * ((size_t) c->jds_maxlen + 2);
+#define FB_SYM(RR, OCC) do {                                                                                                        \
+        auto kern = k_spmv_sym<RR>;                                                                                                 \
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);                                        \
+        const int occ = std::max(1, std::min((OCC), (int) (200 * 1024 / (smem + 1024))));                                           \
+        const int g = std::min(nb, c->n_sm * occ);                                                                                  \
+        kern<<<g, (RR) / 2, smem, c->stream>>>(c->n_dofs, nb, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_jdp.p, c->d_jds_jd.p, \
+                                         c->d_col16.p, c->d_val_jds.p, c->d_diag.p, c->d_win_off.p, c->d_win_list.p, xin,           \
+                                         out, part, counter, c->d_cg.p, alpha, c->win_cap, c->jds_maxlen); } while (0)
+        if (c->jds_R == 256) FB_SYM(256, 12); else FB_SYM(512, 6);
+#undef FB_SYM
+        c->launches++;
+        return;
+    }
     if (lanes >= 300) {         // block-JDS kernel (300: 256 rows per block, 301: 128)
         const int nb = c->jds_nb;
         const size_t smem = sizeof(double) * (size_t) c->win_cap + sizeof(int) * ((size_t) c->jds_maxlen + 2);
@@ -1000,6 +1130,8 @@ static inline double* alpha_ptr(fb_ctx* c) { return (double*) (c->d_cg.p + 1); }
 static inline double* beta_ptr(fb_ctx* c) { return (double*) (c->d_cg.p + 1) + 1; }
 
 void launch_cg_init(fb_ctx* c, int lanes) {
+    c->h_needs_zero = lanes >= 310;
+    if (c->h_needs_zero) cudaMemsetAsync(c->d_h.p, 0, (size_t) c->n_dofs * sizeof(double), c->stream);
     spmv_dispatch<true>(c, lanes, c->d_x.p, c->d_g.p, nullptr);
     const int g = grid_for(c, c->n_dofs, 256);
     k_direction<true><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_g.p, c->d_dinv.p, c->d_d.p, c->d_cg.p, nullptr);
@@ -1013,8 +1145,13 @@ void launch_cg_spmv(fb_ctx* c, int lanes) {       // h = A d, alpha = gh / (d.h)
 void launch_cg_vectors(fb_ctx* c) {               // x, g update + dots + convergence test, then new direction
     unsigned* counter = (unsigned*) (c->d_partial.p + c->d_partial.n - 8);
     const int g = grid_for(c, c->n_dofs, 256);
-    k_update<<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_d.p, c->d_h.p, c->d_dinv.p, c->d_x.p, c->d_g.p, c->d_partial.p, counter,
-                                       c->d_cg.p, alpha_ptr(c), beta_ptr(c));
+    const int gu = std::min(g, c->n_sm * 6);          // k_update: 6 resident blocks per SM, one wave
+    if (c->h_needs_zero)
+        k_update<true><<<gu, 256, 0, c->stream>>>(c->n_dofs, c->d_d.p, c->d_h.p, c->d_dinv.p, c->d_x.p, c->d_g.p, c->d_partial.p, counter,
+                                                 c->d_cg.p, alpha_ptr(c), beta_ptr(c));
+    else
+        k_update<false><<<gu, 256, 0, c->stream>>>(c->n_dofs, c->d_d.p, c->d_h.p, c->d_dinv.p, c->d_x.p, c->d_g.p, c->d_partial.p, counter,
+                                                   c->d_cg.p, alpha_ptr(c), beta_ptr(c));
     k_direction<false><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_g.p, c->d_dinv.p, c->d_d.p, c->d_cg.p, beta_ptr(c));
     c->launches += 2;
 }
@@ -1042,7 +1179,7 @@ bool persistent_eligible(fb_ctx* c) {
     if (c->cg_persistent == 0 || c->n_dofs <= 0) return false;
     if (c->pers_grid == 0) {
         // nnz-balanced contiguous row slices, one per SM
-        const int G = std::min(c->pers_ctas > 0 ? std::min(c->pers_ctas, c->n_sm) : c->n_sm, std::max(1, c->n_dofs / 8));
+        const int G = std::min(std::min(c->pers_ctas > 0 ? std::min(c->pers_ctas, c->n_sm) : c->n_sm, 160), std::max(1, c->n_dofs / 8));   // grid_allreduce reads <= 160 partials
         std::vector<int> cta_row(G + 1, c->n_dofs);
         cta_row[0] = 0;
         int r = 0, cap = 0, rmax = 0;
@@ -1123,9 +1260,9 @@ void launch_cg_init_direction(fb_ctx* c) {
 }
 void launch_cg_update_only(fb_ctx* c) {
     unsigned* counter = (unsigned*) (c->d_partial.p + c->d_partial.n - 8);
-    const int g = grid_for(c, c->n_dofs, 256);
-    k_update<<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_d.p, c->d_h.p, c->d_dinv.p, c->d_x.p, c->d_g.p, c->d_partial.p, counter,
-                                       c->d_cg.p, alpha_ptr(c), beta_ptr(c));
+    const int g = std::min(grid_for(c, c->n_dofs, 256), c->n_sm * 6);
+    k_update<false><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_d.p, c->d_h.p, c->d_dinv.p, c->d_x.p, c->d_g.p, c->d_partial.p, counter,
+                                              c->d_cg.p, alpha_ptr(c), beta_ptr(c));
     c->launches++;
 }
 void launch_cg_direction_only(fb_ctx* c) {

@@ -56,6 +56,7 @@ SIGNATURES = {
     "fb_synchronize": (C.c_int, [vp]),
     "fb_last_solve_stats": (C.c_int, [vp, c_double_p, c_int_p, c_long_p]),
     "fb_last_solve_profile": (C.c_int, [vp, c_double_p, c_double_p, c_int_p]),
+    "fb_last_solve_kernel": (C.c_int, [vp]),
     "fb_get_stream": (vp, [vp]),
 }
 

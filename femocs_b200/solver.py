@@ -202,6 +202,10 @@ class PoissonSolver:
         self.ctx.L.fb_last_solve_stats(self.ctx.h, C.byref(ms), C.byref(it), C.byref(sp))
         return ms.value, it.value, sp.value
 
+    def solve_kernel(self):
+        """SpMV kernel code of the last solve (include/femocs_b200.h: fb_last_solve_kernel)"""
+        return int(self.ctx.L.fb_last_solve_kernel(self.ctx.h))
+
     # (avg ms of the SpMV+dot kernel, avg ms of the vector kernels, samples) of the last solve; needs
     # ctx.set_option("cg_profile", k)
     def solve_profile(self):
