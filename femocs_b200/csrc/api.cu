@@ -830,4 +830,89 @@ int fb_particle_field(fb_ctx* c, long n, const double* xyz, const int* cells, do
     return sync_check(c, "fb_particle_field");
 }
 
+// ---- PIC push: Pic::update_positions / update_velocities with the particles on the device ----
+static int pic_positions_impl(fb_ctx* c, long n, double* d_pos, double* d_vel, int* d_cell, double dt, const double* box6, int periodic,
+                              long* n_lost) {
+    cudaStream_t s = c->stream;
+    fb::launch_pic_move(c, n, d_pos, d_vel, d_cell, dt, box6, periodic);
+    fb::launch_particle_cells(c, n, d_pos, d_cell, true);
+    const size_t nb = (size_t) (n + 1023) / 1024;
+    FB_CUDA(c, c->d_pic_pos.alloc(3 * (size_t) n)); FB_CUDA(c, c->d_pic_vel.alloc(3 * (size_t) n)); FB_CUDA(c, c->d_pic_cell.alloc(n));
+    FB_CUDA(c, c->d_pic_blk.alloc(nb + 2));
+    long* d_total = (long*) c->d_minmax.p;                   // 16 bytes of device scratch
+    fb::launch_pic_compact(c, n, d_pos, d_vel, d_cell, c->d_pic_blk.p, d_total, c->d_pic_pos.p, c->d_pic_vel.p, c->d_pic_cell.p);
+    long* h = (long*) c->pin_out.p;
+    FB_CUDA(c, cudaMemcpyAsync(h, d_total, sizeof(long), cudaMemcpyDeviceToHost, s));
+    FB_CUDA(c, cudaStreamSynchronize(s));
+    const long kept = *h;
+    if (kept < n) {                                          // somebody was lost: the compacted copy replaces the arrays
+        FB_CUDA(c, cudaMemcpyAsync(d_pos, c->d_pic_pos.p, 3 * kept * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        FB_CUDA(c, cudaMemcpyAsync(d_vel, c->d_pic_vel.p, 3 * kept * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        FB_CUDA(c, cudaMemcpyAsync(d_cell, c->d_pic_cell.p, kept * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    }
+    if (n_lost) *n_lost = n - kept;
+    return FB_OK;
+}
+
+int fb_pic_update_positions_dev(fb_ctx* c, long n, double* pos3, double* vel3, int* cell, double dt, const double* box6, int periodic,
+                                long* n_lost) {
+    FB_REQUIRE(c, c->interp_ok, "fb_pic_update_positions: interpolator not initialised");
+    FB_REQUIRE(c, box6 && box6[1] > box6[0] && box6[3] > box6[2], "fb_pic_update_positions: invalid simulation box");
+    if (n_lost) *n_lost = 0;
+    if (n <= 0) return FB_OK;
+    cudaSetDevice(c->device);
+    int rc = pic_positions_impl(c, n, pos3, vel3, cell, dt, box6, periodic, n_lost);
+    if (rc) return rc;
+    return sync_check(c, "fb_pic_update_positions");
+}
+
+int fb_pic_update_positions(fb_ctx* c, long n, double* pos3, double* vel3, int* cell, double dt, const double* box6, int periodic,
+                            long* n_lost) {
+    FB_REQUIRE(c, c->interp_ok, "fb_pic_update_positions: interpolator not initialised");
+    FB_REQUIRE(c, box6 && box6[1] > box6[0] && box6[3] > box6[2], "fb_pic_update_positions: invalid simulation box");
+    if (n_lost) *n_lost = 0;
+    if (n <= 0) return FB_OK;
+    FB_REQUIRE(c, pos3 && vel3 && cell, "fb_pic_update_positions: particle arrays missing");
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    FB_CUDA(c, c->d_pts.alloc(3 * (size_t) n)); FB_CUDA(c, c->d_sol.alloc(3 * (size_t) n)); FB_CUDA(c, c->d_cellsA.alloc(n));
+    FB_CUDA(c, cudaMemcpyAsync(c->d_pts.p, pos3, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+    FB_CUDA(c, cudaMemcpyAsync(c->d_sol.p, vel3, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+    FB_CUDA(c, cudaMemcpyAsync(c->d_cellsA.p, cell, n * sizeof(int), cudaMemcpyHostToDevice, s));
+    long lost = 0;
+    int rc = pic_positions_impl(c, n, c->d_pts.p, c->d_sol.p, c->d_cellsA.p, dt, box6, periodic, &lost);
+    if (rc) return rc;
+    const long kept = n - lost;
+    if (kept > 0) {
+        FB_CUDA(c, cudaMemcpyAsync(pos3, c->d_pts.p, 3 * kept * sizeof(double), cudaMemcpyDeviceToHost, s));
+        FB_CUDA(c, cudaMemcpyAsync(vel3, c->d_sol.p, 3 * kept * sizeof(double), cudaMemcpyDeviceToHost, s));
+        FB_CUDA(c, cudaMemcpyAsync(cell, c->d_cellsA.p, kept * sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
+    if (n_lost) *n_lost = lost;
+    return sync_check(c, "fb_pic_update_positions");
+}
+
+int fb_pic_update_velocities_dev(fb_ctx* c, long n, const double* pos3, const int* cell, double* vel3, double dt, double q_over_m) {
+    FB_REQUIRE(c, c->interp_ok, "fb_pic_update_velocities: interpolator not initialised");
+    if (n <= 0) return FB_OK;
+    cudaSetDevice(c->device);
+    fb::launch_pic_velocities(c, n, pos3, cell, vel3, dt * q_over_m);
+    return FB_OK;
+}
+
+int fb_pic_update_velocities(fb_ctx* c, long n, const double* pos3, const int* cell, double* vel3, double dt, double q_over_m) {
+    FB_REQUIRE(c, c->interp_ok, "fb_pic_update_velocities: interpolator not initialised");
+    if (n <= 0) return FB_OK;
+    FB_REQUIRE(c, pos3 && vel3 && cell, "fb_pic_update_velocities: particle arrays missing");
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    FB_CUDA(c, c->d_pts.alloc(3 * (size_t) n)); FB_CUDA(c, c->d_sol.alloc(3 * (size_t) n)); FB_CUDA(c, c->d_cellsA.alloc(n));
+    FB_CUDA(c, cudaMemcpyAsync(c->d_pts.p, pos3, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+    FB_CUDA(c, cudaMemcpyAsync(c->d_sol.p, vel3, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+    FB_CUDA(c, cudaMemcpyAsync(c->d_cellsA.p, cell, n * sizeof(int), cudaMemcpyHostToDevice, s));
+    fb::launch_pic_velocities(c, n, c->d_pts.p, c->d_cellsA.p, c->d_sol.p, dt * q_over_m);
+    FB_CUDA(c, cudaMemcpyAsync(vel3, c->d_sol.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    return sync_check(c, "fb_pic_update_velocities");
+}
+
 }  // extern "C"

@@ -174,6 +174,7 @@ struct fb_ctx {
     fb::DevBuf<int> d_qtet, d_qtri;          // 10 / 6 node ids
     // scratch for queries
     fb::DevBuf<double> d_pts; fb::DevBuf<int> d_cellsA, d_cellsB, d_scan, d_scan2, d_flag;
+    fb::DevBuf<double> d_pic_pos, d_pic_vel; fb::DevBuf<int> d_pic_cell, d_pic_blk;   // compaction targets of the PIC push
     fb::DevBuf<int> d_needy;                 // [0] = count, [1..] = indices of the points deferred to the block-cooperative scan
     int chain_blocks_per_sm = 0; fb::DevBuf<double> d_sol;
     fb::DevBuf<unsigned char> d_dirtyA, d_dirtyB;

@@ -654,11 +654,12 @@ __global__ void __launch_bounds__(128) k_smooth(int n_voro, const int* __restric
 // ---- PIC particles --------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_particle_cells(Tables T, long n, const double* __restrict__ pts, const int* __restrict__ cell2hex,
                                                         const int* __restrict__ hex2cell, int* __restrict__ cell_inout,
-                                                        int* __restrict__ needy_count, int* __restrict__ needy_idx) {
+                                                        int* __restrict__ needy_count, int* __restrict__ needy_idx, int lost_marker) {
     const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const P3 p = ldp(pts, i);
     const int c = cell_inout[i];
+    if (c == lost_marker) { cell_inout[i] = -1; return; }     // left the simulation box in k_pic_move: no search (Pic.cpp:177-180)
     const int guess = c < 0 ? 0 : cell2hex[c];
     int tet;
     // hex_locate (:1536-1562): tetrahedron from the guess / its neighbours; particles that left the neighbourhood
@@ -689,6 +690,108 @@ __global__ void __launch_bounds__(128) k_particle_field(Tables T, long n, const 
     if (i >= n) return;
     const P3 E = hex_point_gradient(T, ldp(pts, i), cell2hex[cells[i]]);
     E3[3 * i] = E.x; E3[3 * i + 1] = E.y; E3[3 * i + 2] = E.z;
+}
+
+// ---- PIC push --------------------------------------------------------
+// Pic<3>::update_position (src/Pic.cpp:151-184) without the cell search: pos += vel dt (separate multiply and add,
+// as the reference's Vec3 operators compile for baseline x86-64), periodic images (src/Macros.cpp:41-48) or the
+// x/y box test, z < zmax; particles that left the box get cell = FB_PIC_LOST and are not searched.
+#define FB_PIC_LOST (-2)
+__device__ __forceinline__ double periodic_image(double p, double mx, double mn) {
+    const double from_max = p - mx;
+    if (from_max > 0) return mn + from_max;
+    const double from_min = p - mn;
+    if (from_min < 0) return mx + from_min;
+    return p;
+}
+__global__ void __launch_bounds__(256) k_pic_move(long n, double* __restrict__ pos, const double* __restrict__ vel, int* __restrict__ cell,
+                                                  double dt, double xmin, double xmax, double ymin, double ymax, double zmax, int periodic) {
+    const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = pos[3 * i] + vel[3 * i] * dt, y = pos[3 * i + 1] + vel[3 * i + 1] * dt;
+    const double z = pos[3 * i + 2] + vel[3 * i + 2] * dt;
+    bool b1 = true, b2 = true;
+    const bool b3 = z < zmax;
+    if (periodic) { x = periodic_image(x, xmax, xmin); y = periodic_image(y, ymax, ymin); }
+    else { b1 = x > xmin && x < xmax; b2 = y > ymin && y < ymax; }
+    pos[3 * i] = x; pos[3 * i + 1] = y; pos[3 * i + 2] = z;
+    if (!(b1 && b2 && b3)) cell[i] = FB_PIC_LOST;
+}
+
+// Pic<3>::update_velocities (src/Pic.cpp:198-209): vel += interp_gradient(pos, deal2femocs(cell)) * (dt q/m)
+__global__ void __launch_bounds__(128) k_pic_velocities(Tables T, long n, const double* __restrict__ pts, const int* __restrict__ cell2hex,
+                                                        const int* __restrict__ cells, double* __restrict__ vel, double dt_q_over_m) {
+    const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const P3 E = hex_point_gradient(T, ldp(pts, i), cell2hex[cells[i]]);
+    vel[3 * i] += E.x * dt_q_over_m; vel[3 * i + 1] += E.y * dt_q_over_m; vel[3 * i + 2] += E.z * dt_q_over_m;
+}
+
+// ParticleSpecies::clear_lost (src/ParticleSpecies.cpp:16-31): stable removal of the particles with cell == -1.
+// Three passes: kept particles per block of 1024 -> exclusive scan of the block counts (one block) -> scatter.
+constexpr int COMPACT_BLOCK = 1024;
+__global__ void __launch_bounds__(256) k_compact_count(long n, const int* __restrict__ cell, int* __restrict__ block_count) {
+    const long base = (long) blockIdx.x * COMPACT_BLOCK;
+    int cnt = 0;
+    for (int k = threadIdx.x; k < COMPACT_BLOCK; k += 256) { const long i = base + k; cnt += (i < n && cell[i] != -1); }
+    __shared__ int s[8];
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s[w]; block_count[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(1024) k_compact_scan(int nb, int* __restrict__ block_count, long* __restrict__ total) {
+    // exclusive scan of nb counts by one block (chunks of 1024 with a running carry)
+    __shared__ int s[1024];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < nb ? block_count[i] : 0;
+        s[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+            __syncthreads();
+            s[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nb) block_count[i] = carry + s[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += s[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(256) k_compact_scatter(long n, const double* __restrict__ pos, const double* __restrict__ vel,
+                                                         const int* __restrict__ cell, const int* __restrict__ block_offset,
+                                                         double* __restrict__ pos_out, double* __restrict__ vel_out, int* __restrict__ cell_out) {
+    // 4 rounds of 256 particles; inside a round the rank of a kept particle = kept in lower warps + lower lanes
+    __shared__ int s_w[8];
+    __shared__ int s_round;
+    const long base = (long) blockIdx.x * COMPACT_BLOCK;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_round = block_offset[blockIdx.x];
+    __syncthreads();
+    for (int r = 0; r < COMPACT_BLOCK / 256; ++r) {
+        const long i = base + r * 256 + threadIdx.x;
+        const bool keep = i < n && cell[i] != -1;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        int off = s_round;
+        for (int w = 0; w < warp; ++w) off += s_w[w];
+        if (keep) {
+            const long o = off + __popc(m & ((1u << lane) - 1));
+            pos_out[3 * o] = pos[3 * i]; pos_out[3 * o + 1] = pos[3 * i + 1]; pos_out[3 * o + 2] = pos[3 * i + 2];
+            vel_out[3 * o] = vel[3 * i]; vel_out[3 * o + 1] = vel[3 * i + 1]; vel_out[3 * o + 2] = vel[3 * i + 2];
+            cell_out[o] = cell[i];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_w[w]; s_round += t; }
+        __syncthreads();
+    }
 }
 
 // PoissonSolver<3>::assemble_space_charge_fast (PoissonSolver.cpp:299-319): 8 scatter-adds per particle.
@@ -828,12 +931,12 @@ void launch_finish_interp(fb_ctx* c, int dim, int rank, long n, const double* d_
     }
 }
 
-void launch_particle_cells(fb_ctx* c, long n, const double* d_pts, int* d_cells) {
+void launch_particle_cells(fb_ctx* c, long n, const double* d_pts, int* d_cells, bool after_move) {
     const Tables T = make_tables(c);
     c->d_needy.alloc((size_t) n + 1);
     cudaMemsetAsync(c->d_needy.p, 0, sizeof(int), c->stream);
     k_particle_cells<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(T, n, d_pts, c->d_cell2hex.p, c->d_hex2cell.p, d_cells,
-                                                                         c->d_needy.p, c->d_needy.p + 1);
+                                                                         c->d_needy.p, c->d_needy.p + 1, after_move ? FB_PIC_LOST : (int) 0x80000000);
     k_particle_scanned<<<(unsigned) std::min<long>(n, 8L * c->n_sm), 256, 0, c->stream>>>(T, d_pts, c->d_hex2cell.p, c->d_needy.p, c->d_needy.p + 1, d_cells);
     c->launches += 2;
 }
@@ -842,6 +945,27 @@ void launch_particle_field(fb_ctx* c, long n, const double* d_pts, const int* d_
     const Tables T = make_tables(c);
     k_particle_field<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(T, n, d_pts, c->d_cell2hex.p, d_cells, d_E);
     c->launches++;
+}
+
+void launch_pic_move(fb_ctx* c, long n, double* d_pos, const double* d_vel, int* d_cells, double dt, const double* box6, int periodic) {
+    k_pic_move<<<(unsigned) ((n + 255) / 256), 256, 0, c->stream>>>(n, d_pos, d_vel, d_cells, dt, box6[0], box6[1], box6[2], box6[3], box6[5], periodic);
+    c->launches++;
+}
+
+void launch_pic_velocities(fb_ctx* c, long n, const double* d_pos, const int* d_cells, double* d_vel, double dt_q_over_m) {
+    const Tables T = make_tables(c);
+    k_pic_velocities<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(T, n, d_pos, c->d_cell2hex.p, d_cells, d_vel, dt_q_over_m);
+    c->launches++;
+}
+
+// stable compaction into (pos_out, vel_out, cell_out); the number of kept particles lands in *d_total (device)
+void launch_pic_compact(fb_ctx* c, long n, const double* d_pos, const double* d_vel, const int* d_cells, int* d_block_count,
+                        long* d_total, double* pos_out, double* vel_out, int* cell_out) {
+    const int nb = (int) ((n + COMPACT_BLOCK - 1) / COMPACT_BLOCK);
+    k_compact_count<<<nb, 256, 0, c->stream>>>(n, d_cells, d_block_count);
+    k_compact_scan<<<1, 1024, 0, c->stream>>>(nb, d_block_count, d_total);
+    k_compact_scatter<<<nb, 256, 0, c->stream>>>(n, d_pos, d_vel, d_cells, d_block_count, pos_out, vel_out, cell_out);
+    c->launches += 3;
 }
 
 void launch_space_charge(fb_ctx* c, long n, const double* d_pts, const int* d_pcell, double charge_factor) {

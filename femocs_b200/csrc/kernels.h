@@ -40,8 +40,12 @@ void launch_pack_points(fb_ctx* c, long n, const double* x, const double* y, con
 int launch_locate_chain(fb_ctx* c, int dim, int rank, long n, const double* d_pts, int** result);
 void launch_finish_interp(fb_ctx* c, int dim, int rank, long n, const double* d_pts, const int* d_base, int final_cells,
                           int* d_cells_out, double* d_sol);
-void launch_particle_cells(fb_ctx* c, long n, const double* d_pts, int* d_cells);
+void launch_particle_cells(fb_ctx* c, long n, const double* d_pts, int* d_cells, bool after_move = false);
 void launch_particle_field(fb_ctx* c, long n, const double* d_pts, const int* d_cells, double* d_E);
 void launch_space_charge(fb_ctx* c, long n, const double* d_pts, const int* d_pcell, double charge_factor);
+void launch_pic_move(fb_ctx* c, long n, double* d_pos, const double* d_vel, int* d_cells, double dt, const double* box6, int periodic);
+void launch_pic_velocities(fb_ctx* c, long n, const double* d_pos, const int* d_cells, double* d_vel, double dt_q_over_m);
+void launch_pic_compact(fb_ctx* c, long n, const double* d_pos, const double* d_vel, const int* d_cells, int* d_block_count,
+                        long* d_total, double* pos_out, double* vel_out, int* cell_out);
 
 }  // namespace fb

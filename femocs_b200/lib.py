@@ -53,6 +53,10 @@ SIGNATURES = {
     "fb_particle_cells_dev": (C.c_int, [vp, C.c_long, vp, vp]),
     "fb_particle_field_dev": (C.c_int, [vp, C.c_long, vp, vp, vp]),
     "fb_poisson_assemble_dev": (C.c_int, [vp, C.c_int, vp, vp, C.c_long, C.c_double]),
+    "fb_pic_update_positions": (C.c_int, [vp, C.c_long, vp, vp, vp, C.c_double, vp, C.c_int, c_long_p]),
+    "fb_pic_update_velocities": (C.c_int, [vp, C.c_long, vp, vp, vp, C.c_double, C.c_double]),
+    "fb_pic_update_positions_dev": (C.c_int, [vp, C.c_long, vp, vp, vp, C.c_double, vp, C.c_int, c_long_p]),
+    "fb_pic_update_velocities_dev": (C.c_int, [vp, C.c_long, vp, vp, vp, C.c_double, C.c_double]),
     "fb_synchronize": (C.c_int, [vp]),
     "fb_last_solve_stats": (C.c_int, [vp, c_double_p, c_int_p, c_long_p]),
     "fb_last_solve_profile": (C.c_int, [vp, c_double_p, c_double_p, c_int_p]),

@@ -437,6 +437,23 @@ class Pic:
         return E
 
 
+    # Pic::update_positions + ParticleSpecies::clear_lost (src/Pic.cpp:137-184, src/ParticleSpecies.cpp:16-31):
+    # returns the surviving (pos, vel, cells) in their original order and the number of lost particles
+    def update_positions(self, pos, vel, cells, dt, box, periodic=True):
+        pos = _f(pos).copy(); vel = _f(vel).copy(); cells = _i(cells).copy(); box = _f(box)
+        lost = C.c_long(0)
+        self.ctx.check(self.ctx.L.fb_pic_update_positions(self.ctx.h, len(cells), _p(pos), _p(vel), _p(cells), float(dt), _p(box),
+                                                          int(periodic), C.byref(lost)))
+        k = len(cells) - lost.value
+        return pos[:k], vel[:k], cells[:k], lost.value
+
+    # Pic::update_velocities (src/Pic.cpp:198-209)
+    def update_velocities(self, pos, vel, cells, dt, q_over_m):
+        pos = _f(pos); vel = _f(vel).copy(); cells = _i(cells)
+        self.ctx.check(self.ctx.L.fb_pic_update_velocities(self.ctx.h, len(cells), _p(pos), _p(cells), _p(vel), float(dt), float(q_over_m)))
+        return vel
+
+
 class PartitionPlan:
     """Host-only view of the multi-GPU partition logic (fb_plan_*; no CUDA): what rank `rank` of `world` keeps of
     a mesh, its local sparsity and its halo lists.  Used by the world_size-2 CPU tests."""

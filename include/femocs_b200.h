@@ -204,6 +204,20 @@ int fb_particle_cells(fb_ctx* ctx, long n, const double* xyz, int* cell_inout);
  *   (src/InterpolatorCells.cpp:410-423,1363-1416) */
 int fb_particle_field(fb_ctx* ctx, long n, const double* xyz, const int* cells, double* E3);
 
+/* int Pic<3>::update_positions()                                 src/Pic.cpp:137-184
+ *   + ParticleSpecies::clear_lost()                              src/ParticleSpecies.cpp:16-31
+ *   pos += vel dt; periodic images in x, y (src/Macros.cpp:41-48) or loss outside the x/y box; loss at
+ *   z >= zmax; cell search from the previous cell (update_point_cell); particles whose cell is -1 are removed
+ *   and the rest moved forward keeping their order.  pos3 / vel3 / cell are updated IN PLACE (first n - n_lost
+ *   entries valid afterwards).  box6 = {xmin, xmax, ymin, ymax, zmin, zmax} (Medium::Sizes of Pic::set_params). */
+int fb_pic_update_positions(fb_ctx* ctx, long n, double* pos3, double* vel3, int* cell, double dt,
+                            const double* box6, int periodic, long* n_lost);
+
+/* void Pic<3>::update_velocities()                               src/Pic.cpp:198-209
+ *   vel_i += linhex.interp_gradient(pos_i, deal2femocs(cell_i)) * (dt * q_over_m) */
+int fb_pic_update_velocities(fb_ctx* ctx, long n, const double* pos3, const int* cell, double* vel3,
+                             double dt, double q_over_m);
+
 /* ---------------------------------------------------------------------------------------
  * device-resident variants (inputs/outputs already in HBM; asynchronous on the context
  * stream until fb_synchronize).  Used by the benchmark's "value" leg and by callers that
@@ -216,6 +230,12 @@ int fb_particle_field_dev(fb_ctx* ctx, long n, const double* xyz_dev, const int*
                           double* E3_dev);
 int fb_poisson_assemble_dev(fb_ctx* ctx, int first_time, const double* particle_xyz_dev,
                             const int* particle_cell_dev, long n_particles, double charge_factor);
+/* particles resident in HBM across PIC steps; n_lost is written once the stream has been drained (the call
+ * synchronises, as the caller needs the new particle count) */
+int fb_pic_update_positions_dev(fb_ctx* ctx, long n, double* pos3_dev, double* vel3_dev, int* cell_dev, double dt,
+                                const double* box6, int periodic, long* n_lost);
+int fb_pic_update_velocities_dev(fb_ctx* ctx, long n, const double* pos3_dev, const int* cell_dev, double* vel3_dev,
+                                 double dt, double q_over_m);
 int fb_synchronize(fb_ctx* ctx);
 
 /* timing hooks for the roofline report: device time (ms, CUDA events on the context's

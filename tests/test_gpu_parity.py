@@ -240,6 +240,37 @@ def test_particles_golden(name, fb, golden, gpu_interp):
     assert np.abs(E - g["pic_field"]).max() <= 1e-12 * np.abs(g["pic_field"]).max()
 
 
+@pytest.mark.parametrize("name", ["hemicone", "mdsmall"])
+def test_pic_push_golden(name, fb, golden, gpu_interp):
+    """Pic::update_positions (+clear_lost) and Pic::update_velocities on the device against vectors produced with the
+    reference's own cell search (tests/golden/picpush_*.npz): positions, cells, survivors bit-exact; velocities 1e-12"""
+    g = golden("picpush", name)
+    c, s, it = gpu_interp[name]
+    it.set_solutions(hash_field(it.n_nodes, 5, 1))
+    pic = fb.Pic(it)
+    dt = float(g["dt"][0]); qm = float(g["q_over_m"][0])
+    for periodic in (1, 0):
+        pos, vel, cells = g["pos0"], g["vel0"], g["cells0"]
+        for step in range(3):
+            tag = "p%d_s%d_" % (periodic, step)
+            p1, v1, c1, lost = pic.update_positions(pos, vel, cells, dt, g["box"], bool(periodic))
+            assert lost == int(g[tag + "lost"][0]) and len(c1) == len(g[tag + "cells"])
+            assert np.array_equal(c1, g[tag + "cells"]) and np.array_equal(p1, g[tag + "pos"])
+            v2 = pic.update_velocities(p1, v1, c1, dt, qm)
+            assert np.abs(v2 - g[tag + "vel"]).max() <= 1e-12 * np.abs(g[tag + "vel"]).max()
+            pos, vel, cells = g[tag + "pos"], g[tag + "vel"], g[tag + "cells"]      # next step starts from the golden state
+    # nobody lost / everybody lost / empty set
+    p1, v1, c1, lost = pic.update_positions(g["pos0"][:100], np.zeros((100, 3)), g["cells0"][:100], dt, g["box"], True)
+    assert lost == 0 and np.array_equal(p1, g["pos0"][:100]) and np.array_equal(c1, g["cells0"][:100])
+    up = np.tile(np.array([0.0, 0.0, 1e4]), (100, 1))
+    p1, v1, c1, lost = pic.update_positions(g["pos0"][:100], up, g["cells0"][:100], dt, g["box"], True)
+    assert lost == 100 and len(c1) == 0
+    p1, v1, c1, lost = pic.update_positions(np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0, np.int32), dt, g["box"], True)
+    assert lost == 0 and len(c1) == 0
+    with pytest.raises(fb.FemocsB200Error):
+        pic.update_positions(g["pos0"][:4], g["vel0"][:4], g["cells0"][:4], dt, np.array([1.0, 0.0, 0.0, 1.0, 0.0, 1.0]), True)
+
+
 @pytest.mark.parametrize("name", MESHES)
 def test_extract_solution_golden(name, fb, golden, gpu_interp):
     m = golden("mesh", name); g = golden("interp", name)
