@@ -362,6 +362,7 @@ def run_b200(args):
         if not args.skip_native:
             del d_pxyz, d_pcell
             line["native"] = native_step(fb, torch, args)
+            line["pic"] = pic_step(fb, torch, args)
         if not args.skip_cpu:
             o = oracle_x_sample()
             it, dt = oracle_x_step(o)
@@ -462,6 +463,106 @@ def native_step(fb, torch, args):
             if best is None or r["field_step_ms"] < best["field_step_ms"]:
                 best = r
         out["cpu_baseline"] = best
+    ctx.close()
+    return out
+
+
+def pic_particles(m, n, seed=2024):
+    """config 3: n electrons uniform (in natural coordinates) inside the vacuum hexahedra whose centroid lies within
+    50 A of the apex, velocities N(0, 0.1 A/fs); returns (pos, vel, solver cell)"""
+    rng = np.random.default_rng(seed)
+    vac = np.flatnonzero(m["hex_markers"] > 0)
+    cent = m["nodes"][m["hexs"][vac]].mean(1)
+    apex = m["surf_atoms"][np.argmax(m["surf_atoms"][:, 2])]
+    near = np.flatnonzero(np.linalg.norm(cent - apex, axis=1) < 50.0)
+    pick = near[rng.integers(0, len(near), size=n)]            # index into the vacuum list = solver cell id
+    u, v, w = rng.uniform(-0.9, 0.9, size=(3, n))
+    su = np.array([-1, 1, 1, -1, -1, 1, 1, -1.0]); sv = np.array([-1, -1, 1, 1, -1, -1, 1, 1.0]); sw = np.array([-1, -1, -1, -1, 1, 1, 1, 1.0])
+    N = (1 + su[None] * u[:, None]) * (1 + sv[None] * v[:, None]) * (1 + sw[None] * w[:, None]) / 8.0
+    pos = np.einsum("nk,nkd->nd", N, m["nodes"][m["hexs"][vac[pick]]])
+    vel = rng.normal(0.0, 0.1, size=(n, 3))
+    return np.ascontiguousarray(pos), np.ascontiguousarray(vel), pick.astype(np.int32)
+
+
+def pic_step(fb, torch, args):
+    """BASELINE.json config 3: PIC on the nanotip_small mesh with 1e6 synthetic electrons resident in HBM.  One step =
+    ProjectRunaway::make_pic_step (ProjectRunaway.cpp:492-533) without emission/injection/collisions: update_positions
+    (push, periodic images, cell search, clear_lost) -> assemble(space-charge RHS) -> warm-started CG -> check_limits ->
+    extract_solution -> update_velocities."""
+    with np.load(os.path.join(ROOT, "tests", "golden", "mesh_mdsmall.npz")) as z:
+        m = {k: z[k] for k in z.files}
+    n_p = args.particles
+    pos, vel, cells = pic_particles(m, n_p)
+    ctx = fb.Context(torch.cuda.current_device())
+    solver = fb.PoissonSolver(ctx, fb.FieldConfig(E0=E0, cg_tolerance=CG_TOL, n_cg=N_CG, mode="transient"))
+    assert solver.import_mesh(m["nodes"], m["hexs"], m["hex_markers"])
+    interp = fb.Interpolator(ctx); interp.initialize(m)
+    lo = m["nodes"].min(0); hi = m["nodes"].max(0)
+    box = np.array([lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]])
+    dt, q_over_m, cf = 0.5, -17.5882, Q_OVER_EPS0 * WSP * 1e-3      # Pic.h:90; weight scaled so that 1e6 SPs stay within V limits
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    K, W = max(args.steps, 5), max(args.warmup, 3)
+    import ctypes as C
+
+    def fresh():
+        return torch.from_numpy(pos).cuda(), torch.from_numpy(vel).cuda(), torch.from_numpy(cells).cuda()
+
+    d_pos, d_vel, d_cell = fresh()
+    state = {"n": n_p}
+    solver.setup(-E0, 0.0); solver.assemble(True); solver.solve()           # Laplace start, as solve_laplace before the PIC loop
+
+    def step():
+        lost = C.c_long(0)
+        n = state["n"]
+        ctx.check(ctx.L.fb_pic_update_positions_dev(ctx.h, n, d_pos.data_ptr(), d_vel.data_ptr(), d_cell.data_ptr(), dt,
+                                                    box.ctypes.data, 1, C.byref(lost)))
+        n -= lost.value; state["n"] = n
+        solver.assemble_dev(False, d_pos.data_ptr(), d_cell.data_ptr(), n, cf)
+        it = solver.solve()
+        solver.check_limits(-1e30, 1e30)
+        interp.extract_solution(solver, True)
+        ctx.check(ctx.L.fb_pic_update_velocities_dev(ctx.h, n, d_pos.data_ptr(), d_cell.data_ptr(), d_vel.data_ptr(), dt, q_over_m))
+        ctx.synchronize()
+        return it
+
+    for _ in range(W):
+        step()
+    launches0 = ctx.kernel_launches
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    its = [step() for _ in range(K)]
+    b.record(stream); b.synchronize()
+    ms = a.elapsed_time(b) / K
+    launches = (ctx.kernel_launches - launches0) / K
+    n_alive = state["n"]
+    # the two particle passes alone
+    lost = C.c_long(0)
+    a.record(stream)
+    ctx.check(ctx.L.fb_pic_update_positions_dev(ctx.h, n_alive, d_pos.data_ptr(), d_vel.data_ptr(), d_cell.data_ptr(), dt, box.ctypes.data, 1, C.byref(lost)))
+    b.record(stream); b.synchronize(); push_ms = a.elapsed_time(b); n_alive -= lost.value
+    a.record(stream)
+    ctx.check(ctx.L.fb_pic_update_velocities_dev(ctx.h, n_alive, d_pos.data_ptr(), d_cell.data_ptr(), d_vel.data_ptr(), dt, q_over_m))
+    ctx.synchronize(); b.record(stream); b.synchronize(); vel_ms = a.elapsed_time(b)
+    out = {"workload": "config 3: nanotip_small mesh (%d DoF), %d synthetic electrons resident in HBM, dt %.2f fs, periodic box; step = update_positions "
+                       "(push + cell search + clear_lost) + space-charge assemble + warm-started CG + check_limits + extract_solution + update_velocities"
+                       % (solver.n_dofs, n_p, dt),
+           "ms_per_step": ms, "particles_alive": int(n_alive), "cg_iterations_per_step": its, "gpu_launches_per_step": launches,
+           "update_positions_ms": push_ms, "update_positions_particles_per_s": n_alive / (push_ms * 1e-3),
+           "update_velocities_ms": vel_ms, "update_velocities_particles_per_s": n_alive / (vel_ms * 1e-3),
+           "particle_steps_per_s": n_alive / (ms * 1e-3)}
+    if not args.skip_cpu:
+        from oracle import pic as opic
+        from oracle.oracle import Oracle
+        o = Oracle(); o.import_mesh(m["nodes"], m["hexs"], m["hex_markers"]); o.interp_initialize(m)
+        o.setup(-E0, 0.0, False); o.assemble(True); o.solve(N_CG, CG_TOL, 1.2, 0); o.extract_solution(True)
+        ns = min(n_p, 50000)
+        t = time.perf_counter()
+        p1, v1, c1, _ = opic.update_positions(o, pos[:ns], vel[:ns], cells[:ns], dt, box, True)
+        t1 = time.perf_counter()
+        opic.update_velocities(o, p1, v1, c1, dt, q_over_m)
+        t2 = time.perf_counter()
+        out["cpu_baseline"] = {"kind": "port", "cores": 1, "sample": "%d particles of the same set" % ns,
+                               "update_positions_particles_per_s": ns / (t1 - t), "update_velocities_particles_per_s": len(c1) / (t2 - t1)}
     ctx.close()
     return out
 

@@ -260,6 +260,17 @@ public:
     void update_point_cells(long n, const double* xyz, int* cells) { interpolator->ctx.check(fb_particle_cells(interpolator->ctx.h, n, xyz, cells)); }
     // field look-up of Pic::update_velocities (src/Pic.cpp:198-209)
     void fields(long n, const double* xyz, const int* cells, double* E3) { interpolator->ctx.check(fb_particle_field(interpolator->ctx.h, n, xyz, cells, E3)); }
+    // Pic::update_positions + ParticleSpecies::clear_lost (src/Pic.cpp:137-184, src/ParticleSpecies.cpp:16-31): arrays updated in
+    // place, the first n - n_lost entries are the survivors in their original order; returns n_lost
+    int update_positions(long n, double* pos3, double* vel3, int* cells, double dt, const double box6[6], bool periodic) {
+        long lost = 0;
+        interpolator->ctx.check(fb_pic_update_positions(interpolator->ctx.h, n, pos3, vel3, cells, dt, box6, periodic ? 1 : 0, &lost));
+        return (int) lost;
+    }
+    // Pic::update_velocities (src/Pic.cpp:198-209)
+    void update_velocities(long n, const double* pos3, const int* cells, double* vel3, double dt, double q_over_m) {
+        interpolator->ctx.check(fb_pic_update_velocities(interpolator->ctx.h, n, pos3, cells, vel3, dt, q_over_m));
+    }
 private:
     Interpolator* interpolator;
 };
