@@ -23,6 +23,7 @@ static int sync_check(fb_ctx* c, const char* what) {
 
 static void drop_graph(fb_ctx* c) {
     if (c->cg_graph) { cudaGraphExecDestroy(c->cg_graph); c->cg_graph = nullptr; }
+    if (c->mg_graph) { cudaGraphExecDestroy(c->mg_graph); c->mg_graph = nullptr; }
     c->cg_graph_n = 0;
 }
 
@@ -111,7 +112,9 @@ long fb_kernel_launches(const fb_ctx* c) { return c->launches; }
 int fb_set_option(fb_ctx* c, const char* key, double value) {
     const std::string k(key);
     if (k == "cg_graph_iters") { c->cg_graph_iters = std::max(1, (int) value); drop_graph(c); }
-    else if (k == "cheb_degree") c->cheb_degree = (int) value;
+    else if (k == "cheb_degree") { c->cheb_degree = (int) value; drop_graph(c); }
+    else if (k == "cheb_eig_ratio") { c->cheb_ratio = value; drop_graph(c); }
+    else if (k == "cheb_power_iters") { c->cheb_power_iters = std::max(0, (int) value); c->cheb_lmax = 0; }
     else if (k == "dof_order") c->dof_order = (int) value;
     else if (k == "spmv_kernel") { c->spmv_kernel = (int) value; drop_graph(c); }
     else if (k == "cg_persistent") c->cg_persistent = (int) value;
@@ -302,6 +305,7 @@ static int assemble_impl(fb_ctx* c, int first_time, const double* d_pxyz, const 
         }
         fb::launch_apply_bc_matrix(c);      // val, Dirichlet lift (kept in d_w), dinv, diagpos
         c->jds_val_dirty = true;
+        c->cheb_lmax = 0;                   // Gershgorin bound of the new matrix is computed by the next Chebyshev solve
         FB_CUDA(c, cudaStreamSynchronize(s));   // tmp goes out of scope
         c->matrix_ok = true;
     }
@@ -338,7 +342,11 @@ int fb_poisson_assemble(fb_ctx* c, int first_time, const double* pxyz, const int
 
 int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* n_iter, double* final_residual) {
     FB_REQUIRE(c, c->assembled, "fb_poisson_solve: system not assembled");
-    FB_REQUIRE(c, precond == FB_PRECOND_JACOBI, "fb_poisson_solve: only FB_PRECOND_JACOBI is implemented in this build");
+    FB_REQUIRE(c, precond == FB_PRECOND_JACOBI || precond == FB_PRECOND_CHEBYSHEV,
+               "fb_poisson_solve: preconditioner must be FB_PRECOND_JACOBI or FB_PRECOND_CHEBYSHEV (SSOR is sequential and not provided)");
+    FB_REQUIRE(c, precond == FB_PRECOND_JACOBI || c->world == 1, "fb_poisson_solve: FB_PRECOND_CHEBYSHEV runs on un-partitioned meshes only");
+    const bool cheb = precond == FB_PRECOND_CHEBYSHEV && c->cheb_degree >= 2;        // degree 1 is Jacobi up to a scale factor
+    c->cheb_active = false;
     cudaSetDevice(c->device);
     cudaStream_t s = c->stream;
     fb::CgScalars init; memset(&init, 0, sizeof init);
@@ -347,7 +355,7 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
     *h = init;
     long spmv = 1;
     c->prof_samples = 0; c->prof_spmv_ms = c->prof_vec_ms = 0;
-    const bool persistent = c->world == 1 && c->cg_profile == 0 && fb::persistent_eligible(c);
+    const bool persistent = c->world == 1 && c->cg_profile == 0 && !cheb && fb::persistent_eligible(c);
     if (c->world > 1) h->red = c->d_red.p;
     FB_CUDA(c, cudaEventRecord(c->ev0, s));
     FB_CUDA(c, cudaMemcpyAsync(c->d_cg.p, h, sizeof(fb::CgScalars), cudaMemcpyHostToDevice, s));
@@ -438,25 +446,51 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
             const int check_every = 16;
             const bool prof = c->cg_profile > 0;
             if (prof) while ((int) c->prof_ev.size() < 3 * c->cg_profile) { cudaEvent_t e; FB_CUDA(c, cudaEventCreate(&e)); c->prof_ev.push_back(e); }
-            int launched = 0, n_prof = 0;
+            auto iteration = [&](int sample) -> int {          // one CG iteration on the stream (sample >= 0: bracketed by events)
+                int rc2;
+                if (sample >= 0) FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * sample], s));
+                if ((rc2 = halo_exchange(c, c->d_d.p))) return rc2;
+                fb::launch_cg_spmv(c, lanes);
+                if ((rc2 = allreduce(c, c->d_red.p, 2, ncclSum))) return rc2;
+                fb::launch_cg_scalars(c, 1);
+                if (sample >= 0) FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * sample + 1], s));
+                fb::launch_cg_update_only(c);
+                if ((rc2 = allreduce(c, c->d_red.p, 2, ncclSum))) return rc2;
+                fb::launch_cg_scalars(c, 2);
+                fb::launch_cg_direction_only(c);
+                if (sample >= 0) FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * sample + 2], s));
+                return FB_OK;
+            };
+            // the first cg_profile iterations run un-graphed, each bracketed by events; NCCL's lazy set-up of the
+            // point-to-point and all-reduce kernels has happened above, so the loop body can be captured:
+            // check_every iterations (kernels + NCCL operations) = ONE cudaGraphLaunch per rank, which removes the
+            // ~0.1 ms of host launch gaps per iteration that the un-graphed loop showed at 4 GPUs
+            int n_prof = 0;
+            for (; prof && n_prof < c->cg_profile; ++n_prof)
+                if ((rc = iteration(n_prof))) return rc;
+            spmv += n_prof;
+            if (!c->mg_graph || c->mg_graph_key != lanes) {
+                if (c->mg_graph) { cudaGraphExecDestroy(c->mg_graph); c->mg_graph = nullptr; }
+                cudaGraph_t graph = nullptr;
+                const long before = c->launches;
+                FB_CUDA(c, cudaStreamSynchronize(s));
+                FB_CUDA(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+                int rc_cap = FB_OK;
+                for (int i = 0; i < check_every && !rc_cap; ++i) rc_cap = iteration(-1);
+                cudaError_t ec = cudaStreamEndCapture(s, &graph);
+                c->launches = before;
+                if (rc_cap) { if (graph) cudaGraphDestroy(graph); return rc_cap; }
+                FB_CUDA(c, ec);
+                FB_CUDA(c, cudaGraphInstantiate(&c->mg_graph, graph, 0));
+                cudaGraphDestroy(graph);
+                c->mg_graph_key = lanes;
+            }
             while (true) {
                 FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
                 FB_CUDA(c, cudaStreamSynchronize(s));
                 if (h->done) break;
-                for (int i = 0; i < check_every; ++i, ++launched) {
-                    const bool sample = prof && launched < c->cg_profile;
-                    if (sample) FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * launched], s));
-                    if ((rc = halo_exchange(c, c->d_d.p))) return rc;
-                    fb::launch_cg_spmv(c, lanes);
-                    if ((rc = allreduce(c, c->d_red.p, 2, ncclSum))) return rc;
-                    fb::launch_cg_scalars(c, 1);
-                    if (sample) FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * launched + 1], s));
-                    fb::launch_cg_update_only(c);
-                    if ((rc = allreduce(c, c->d_red.p, 2, ncclSum))) return rc;
-                    fb::launch_cg_scalars(c, 2);
-                    fb::launch_cg_direction_only(c);
-                    if (sample) { FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * launched + 2], s)); n_prof = launched + 1; }
-                }
+                FB_CUDA(c, cudaGraphLaunch(c->mg_graph, s));
+                c->launches += 6L * check_every;
                 spmv += check_every;
             }
             if (n_prof > 0) {
@@ -471,9 +505,16 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
                 if (live > 0) { c->prof_spmv_ms /= live; c->prof_vec_ms /= live; }
             }
         } else {
+            int graph_key = lanes;
+            if (cheb) {
+                FB_CUDA(c, fb::cheb_prepare(c, lanes));
+                c->cheb_active = true;
+                graph_key = lanes + 1000 * c->cheb_k;
+                FB_CUDA(c, cudaMemcpyAsync(c->d_cg.p, h, sizeof(fb::CgScalars), cudaMemcpyHostToDevice, s));   // cheb_prepare may have used the stream
+            }
             fb::launch_cg_init(c, lanes);
             // CUDA graph of cg_graph_iters iterations; kernels become no-ops once cgs->done is set
-            if (!c->cg_graph || c->cg_graph_n != c->cg_graph_iters || c->cg_graph_precond != lanes) {
+            if (!c->cg_graph || c->cg_graph_n != c->cg_graph_iters || c->cg_graph_precond != graph_key) {
                 drop_graph(c);
                 cudaGraph_t graph;
                 const long before = c->launches;
@@ -484,7 +525,7 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
                 c->launches = before;     // captured, not launched
                 FB_CUDA(c, cudaGraphInstantiate(&c->cg_graph, graph, 0));
                 cudaGraphDestroy(graph);
-                c->cg_graph_n = c->cg_graph_iters; c->cg_graph_precond = lanes;
+                c->cg_graph_n = c->cg_graph_iters; c->cg_graph_precond = graph_key;
             }
             // optional profile: the first cg_profile iterations run un-graphed, each bracketed by CUDA
             // events on this stream (SpMV+dot | vector updates), for the live roofline figures of bench.py
@@ -518,8 +559,8 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
             }
             while (!h->done) {
                 FB_CUDA(c, cudaGraphLaunch(c->cg_graph, s));
-                c->launches += 3L * c->cg_graph_n;
-                spmv += c->cg_graph_n;
+                c->launches += (cheb ? 1L + 2L * c->cheb_k : 3L) * c->cg_graph_n;
+                spmv += (long) (cheb ? c->cheb_k : 1) * c->cg_graph_n;
                 FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
                 FB_CUDA(c, cudaStreamSynchronize(s));
             }

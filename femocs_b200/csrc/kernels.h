@@ -20,6 +20,7 @@ void launch_cg_iteration(fb_ctx* c, int lanes);
 void launch_cg_spmv(fb_ctx* c, int lanes);
 void launch_cg_vectors(fb_ctx* c);
 bool persistent_eligible(fb_ctx* c);
+cudaError_t cheb_prepare(fb_ctx* c, int lanes);
 // multi-GPU
 void launch_pack(fb_ctx* c, const double* v);
 void launch_flags_to_double(fb_ctx* c, double* out);

@@ -98,6 +98,15 @@ __device__ __forceinline__ void cg_scalars_update(CgScalars* cgs, const double* 
     if (tot[1] <= cgs->tol2) cgs->done = 1;                     // SolverControl: success first,
     else if (it >= cgs->max_iter || tot[1] != tot[1]) cgs->done = 2;   // then failure on max steps / NaN
 }
+// Chebyshev-preconditioned CG: the update kernel only knows |g| (iteration count, convergence); g.z -- and with it
+// beta -- comes from the last Chebyshev step
+__device__ __forceinline__ void cg_scalars_update_cheb(CgScalars* cgs, const double* tot) {
+    const int it = cgs->it + 1;
+    cgs->it = it;
+    cgs->res2 = tot[1];
+    if (tot[1] <= cgs->tol2) cgs->done = 1;
+    else if (it >= cgs->max_iter || tot[1] != tot[1]) cgs->done = 2;
+}
 template <bool INIT>
 __device__ __forceinline__ void cg_finish_spmv(CgScalars* cgs, const double* tot, double* alpha_out) {
     if (cgs->red) { cgs->red[0] = tot[0]; cgs->red[1] = tot[1]; }
@@ -408,11 +417,12 @@ __global__ void __launch_bounds__(THREADS) k_spmv_stream(int n_blocks, const int
     }
 }
 
-template <bool ZERO_H>
+template <bool ZERO_H, bool CHEB>
 __global__ void __launch_bounds__(256, 6) k_update(int n, const double* __restrict__ d, double* __restrict__ h,
                                                 const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ g,
                                                 double* __restrict__ partial, unsigned* counter, CgScalars* __restrict__ cgs,
-                                                const double* __restrict__ alpha_in, double* __restrict__ beta_out) {
+                                                const double* __restrict__ alpha_in, double* __restrict__ beta_out,
+                                                double* __restrict__ cheb_p, double* __restrict__ cheb_z, double inv_theta) {
     if (cgs->done) return;
     const double alpha = *alpha_in;
     double acc[2] = {0, 0};
@@ -432,6 +442,10 @@ __global__ void __launch_bounds__(256, 6) k_update(int n, const double* __restri
         gg.x += alpha * hh.x; gg.y += alpha * hh.y;
         x2[i] = xx; g2[i] = gg;
         if (ZERO_H) h2[i] = make_double2(0.0, 0.0);   // the symmetric SpMV accumulates into h with reductions: hand it a zeroed vector
+        if (CHEB) {                                   // first Chebyshev step: p = Dinv g / theta, z = p
+            const double2 pp = make_double2(di.x * gg.x * inv_theta, di.y * gg.y * inv_theta);
+            reinterpret_cast<double2*>(cheb_p)[i] = pp; reinterpret_cast<double2*>(cheb_z)[i] = pp;
+        }
         acc[0] += gg.x * gg.x * di.x + gg.y * gg.y * di.y;
         acc[1] += gg.x * gg.x + gg.y * gg.y;
     }
@@ -441,13 +455,114 @@ __global__ void __launch_bounds__(256, 6) k_update(int n, const double* __restri
         const double gi = g[i] + alpha * h[i];
         g[i] = gi;
         if (ZERO_H) h[i] = 0.0;
+        if (CHEB) { const double pp = dinv[i] * gi * inv_theta; cheb_p[i] = pp; cheb_z[i] = pp; }
         acc[0] += gi * gi * dinv[i];
         acc[1] += gi * gi;
     }
     double tot[2];
     if (reduce_publish<2>(acc, partial, counter, tot)) {
-        cg_finish_update(cgs, tot, beta_out);
+        if (CHEB) cg_scalars_update_cheb(cgs, tot); else cg_finish_update(cgs, tot, beta_out);
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Chebyshev polynomial preconditioner  z = p_k(Dinv A) Dinv g  (k = option "cheb_degree" >= 2) on the interval
+// [lmax / ratio, lmax] of the Jacobi-scaled operator; lmax = Gershgorin bound max_i sum_j |a_ij| / a_ii computed on
+// the device after every assembly.  Three-term recurrence (Saad, Iterative Methods, Alg. 12.1) with
+//   theta = (lmax + lmin) / 2, delta = (lmax - lmin) / 2, sigma = theta / delta, rho_0 = 1 / sigma:
+//   p_0 = Dinv g / theta, z = p_0;   r_i = r_{i-1} - A p_{i-1};  rho_i = 1 / (2 sigma - rho_{i-1});
+//   p_i = rho_i rho_{i-1} p_{i-1} + (2 rho_i / delta) Dinv r_i;  z += p_i            (i = 1 .. k-1)
+// The coefficients depend only on (lmax, ratio, i) and are computed on the host.  One step = one SpMV (k_spmv_jds,
+// its fused dot product unused) + k_cheb_step [64 B per DoF]; the last step also reduces g.z, from which beta follows.
+// The polynomial is fixed and positive on (0, lmax], so M^-1 is SPD and CG stays CG; each iteration costs k SpMVs and
+// needs ~sqrt-fewer iterations -- and, on several GPUs, fewer all-reduces per unit of work.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gershgorin(int n, const int* __restrict__ rowptr, const double* __restrict__ val,
+                                                    const double* __restrict__ dinv, unsigned long long* __restrict__ out_bits) {
+    // 8 lanes per row; warp-uniform trip count; positive doubles order like their bit patterns
+    const int lane = threadIdx.x & 7;
+    const long gtid = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long stride = (long) gridDim.x * blockDim.x / 8;
+    double mx = 0;
+    for (long rb = (gtid / 32) * 4; rb < n; rb += stride) {
+        const long r = rb + (threadIdx.x % 32) / 8;
+        double s = 0;
+        if (r < n) for (int k = rowptr[r] + lane; k < rowptr[r + 1]; k += 8) s += fabs(val[k]);
+        s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (r < n) mx = fmax(mx, s * dinv[r]);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, (unsigned long long) __double_as_longlong(mx));
+}
+
+// Power iteration on Dinv A for a sharper lmax than the Gershgorin bound: v <- Dinv A v (unnormalised: <= lmax^its
+// growth), Rayleigh quotient (v.Av) / (v.Dv) of the similar symmetric matrix D^-1/2 A D^-1/2 -- a lower bound that
+// converges from below, hence the safety factor applied by cheb_prepare.
+__global__ void k_power_init(int n, double* __restrict__ v) {
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+        unsigned x = (unsigned) i * 2654435761u + 12345u;          // deterministic pseudo-random start in [-0.5, 0.5)
+        x ^= x >> 16; x *= 2246822519u; x ^= x >> 13;
+        v[i] = (double) x * (1.0 / 4294967296.0) - 0.5;
+    }
+}
+__global__ void __launch_bounds__(256) k_power_step(int n, const double* __restrict__ h, const double* __restrict__ dinv,
+                                                    double* __restrict__ v, double* __restrict__ partial, unsigned* counter,
+                                                    double* __restrict__ out2) {
+    double acc[2] = {0, 0};
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+        const double vi = v[i], hi = h[i], di = dinv[i];
+        acc[0] += vi * hi;
+        acc[1] += vi * vi / di;
+        v[i] = di * hi;
+    }
+    double tot[2];
+    if (reduce_publish<2>(acc, partial, counter, tot)) { out2[0] = tot[0]; out2[1] = tot[1]; }
+}
+
+__global__ void __launch_bounds__(256) k_cheb_start(int n, const double* __restrict__ g, const double* __restrict__ dinv,
+                                                    double* __restrict__ p, double* __restrict__ z, double inv_theta,
+                                                    const CgScalars* __restrict__ cgs) {
+    if (cgs->done) return;
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+        const double pp = dinv[i] * g[i] * inv_theta;
+        p[i] = pp; z[i] = pp;
+    }
+}
+
+// r = r_in - w;  p = c1 p + c2 Dinv r;  z += p.   LAST: also g.z -> beta = g.z / gh (INIT: only gh = g.z)
+template <bool LAST, bool INIT>
+__global__ void __launch_bounds__(256) k_cheb_step(int n, const double* __restrict__ w, const double* __restrict__ r_in, double* __restrict__ r_out,
+                                                   const double* __restrict__ dinv, double* __restrict__ p, double* __restrict__ z,
+                                                   const double* __restrict__ g, double c1, double c2,
+                                                   double* __restrict__ partial, unsigned* counter, CgScalars* __restrict__ cgs,
+                                                   double* __restrict__ beta_out) {
+    if (cgs->done) return;
+    double acc[1] = {0};
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+        const double r = r_in[i] - w[i];
+        const double pp = c1 * p[i] + c2 * dinv[i] * r;
+        const double zz = z[i] + pp;
+        z[i] = zz;
+        if (!LAST) { r_out[i] = r; p[i] = pp; }
+        else acc[0] += g[i] * zz;
+    }
+    if (LAST) {
+        double tot[1];
+        if (reduce_publish<1>(acc, partial, counter, tot)) {
+            if (!INIT) *beta_out = tot[0] / cgs->gh;
+            cgs->gh = tot[0];
+        }
+    }
+}
+
+// d = beta d - z
+template <bool INIT>
+__global__ void __launch_bounds__(256) k_direction_z(int n, const double* __restrict__ z, double* __restrict__ d,
+                                                     const CgScalars* __restrict__ cgs, const double* __restrict__ beta_in) {
+    if (cgs->done) return;
+    const double beta = INIT ? 0.0 : *beta_in;
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x)
+        d[i] = (INIT ? 0.0 : beta * d[i]) - z[i];
 }
 
 template <bool INIT>
@@ -1129,7 +1244,85 @@ static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, 
 static inline double* alpha_ptr(fb_ctx* c) { return (double*) (c->d_cg.p + 1); }
 static inline double* beta_ptr(fb_ctx* c) { return (double*) (c->d_cg.p + 1) + 1; }
 
+// steps 1 .. k-1 of the Chebyshev recurrence on the current (p, z): SpMV w = A p into d_h (free once k_update has read
+// it), then k_cheb_step; r_0 = g is read in place, later residuals live in d_cheb_r
+static void launch_cheb_steps(fb_ctx* c, bool init) {
+    unsigned* counter = (unsigned*) (c->d_partial.p + c->d_partial.n - 8);
+    const int g = grid_for(c, c->n_dofs, 256);
+    const int k = c->cheb_k;
+    for (int i = 1; i < k; ++i) {
+        spmv_dispatch<false>(c, c->cheb_lanes, c->d_cheb_p.p, c->d_h.p, (double*) (c->d_cg.p + 1) + 3);     // alpha slot 3 = scratch
+        const double* r_in = (i == 1) ? c->d_g.p : c->d_cheb_r.p;
+        const double c1 = c->cheb_c1[i], c2 = c->cheb_c2[i];
+#define FB_CHEB(LAST, INIT) k_cheb_step<LAST, INIT><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_h.p, r_in, c->d_cheb_r.p, c->d_dinv.p, c->d_cheb_p.p, \
+                                c->d_z.p, c->d_g.p, c1, c2, c->d_partial.p, counter, c->d_cg.p, (double*) (c->d_cg.p + 1) + 1)
+        if (i < k - 1) FB_CHEB(false, false); else if (init) FB_CHEB(true, true); else FB_CHEB(true, false);
+#undef FB_CHEB
+        c->launches++;
+    }
+}
+
+// Gershgorin bound of Dinv A (once per assembly) and the recurrence coefficients
+cudaError_t cheb_prepare(fb_ctx* c, int lanes) {
+    const int k = std::max(2, std::min(16, c->cheb_degree));
+    cudaError_t e = c->d_cheb_p.alloc(c->n_cols);
+    if (e == cudaSuccess) e = c->d_cheb_r.alloc(c->n_cols);
+    if (e != cudaSuccess) return e;
+    if (c->cheb_lmax <= 0) {
+        unsigned long long* bits = (unsigned long long*) c->d_minmax.p;
+        cudaMemsetAsync(bits, 0, sizeof(unsigned long long), c->stream);
+        k_gershgorin<<<grid_for(c, (long) c->n_dofs * 8, 256), 256, 0, c->stream>>>(c->n_dofs, c->d_rowptr.p, c->d_val.p, c->d_dinv.p, bits);
+        c->launches++;
+        double lmax = 0;
+        e = cudaMemcpyAsync(&lmax, bits, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return e;
+        c->cheb_gershgorin = lmax;
+        if (c->cheb_power_iters > 0) {
+            // sharpen: power iteration (lower bound) x 1.2, never above the Gershgorin bound
+            unsigned* counter = (unsigned*) (c->d_partial.p + c->d_partial.n - 8);
+            const int g = grid_for(c, c->n_dofs, 256);
+            const int pl = (lanes >= 310) ? 302 : lanes;
+            k_power_init<<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_cheb_p.p);
+            for (int i = 0; i < c->cheb_power_iters; ++i) {
+                spmv_dispatch<false>(c, pl, c->d_cheb_p.p, c->d_h.p, (double*) (c->d_cg.p + 1) + 3);
+                k_power_step<<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_h.p, c->d_dinv.p, c->d_cheb_p.p, c->d_partial.p, counter, c->d_minmax.p);
+            }
+            c->launches += 1 + c->cheb_power_iters;
+            double q[2] = {0, 0};
+            e = cudaMemcpyAsync(q, c->d_minmax.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) return e;
+            if (q[1] > 0 && q[0] > 0) lmax = std::min(lmax, 1.2 * q[0] / q[1]);
+        }
+        c->cheb_lmax = lmax;
+        if (getenv("FB_VERBOSE")) fprintf(stderr, "[fb] Chebyshev: lmax(Dinv A) = %.4f (Gershgorin %.4f)\n", c->cheb_lmax, c->cheb_gershgorin);
+    }
+    const double lmax = c->cheb_lmax, lmin = lmax / std::max(1.5, c->cheb_ratio);
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+    c->cheb_inv_theta = 1.0 / theta;
+    double rho = 1.0 / sigma;
+    for (int i = 1; i < k; ++i) {
+        const double rho_new = 1.0 / (2.0 * sigma - rho);
+        c->cheb_c1[i] = rho_new * rho; c->cheb_c2[i] = 2.0 * rho_new / delta;
+        rho = rho_new;
+    }
+    c->cheb_k = k;
+    c->cheb_lanes = (lanes >= 310) ? 302 : lanes;       // the symmetric layout accumulates into a zeroed vector: not used here
+    return cudaSuccess;
+}
+
 void launch_cg_init(fb_ctx* c, int lanes) {
+    if (c->cheb_active) {
+        spmv_dispatch<true>(c, lanes, c->d_x.p, c->d_g.p, nullptr);
+        const int g = grid_for(c, c->n_dofs, 256);
+        k_cheb_start<<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_g.p, c->d_dinv.p, c->d_cheb_p.p, c->d_z.p, c->cheb_inv_theta, c->d_cg.p);
+        c->launches++;
+        launch_cheb_steps(c, true);
+        k_direction_z<true><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_z.p, c->d_d.p, c->d_cg.p, nullptr);
+        c->launches++;
+        return;
+    }
     c->h_needs_zero = lanes >= 310;
     if (c->h_needs_zero) cudaMemsetAsync(c->d_h.p, 0, (size_t) c->n_dofs * sizeof(double), c->stream);
     spmv_dispatch<true>(c, lanes, c->d_x.p, c->d_g.p, nullptr);
@@ -1146,12 +1339,21 @@ void launch_cg_vectors(fb_ctx* c) {               // x, g update + dots + conver
     unsigned* counter = (unsigned*) (c->d_partial.p + c->d_partial.n - 8);
     const int g = grid_for(c, c->n_dofs, 256);
     const int gu = std::min(g, c->n_sm * 6);          // k_update: 6 resident blocks per SM, one wave
+    if (c->cheb_active) {       // Chebyshev-preconditioned iteration: update (+ first step), k-1 x (SpMV + step), direction
+        k_update<false, true><<<gu, 256, 0, c->stream>>>(c->n_dofs, c->d_d.p, c->d_h.p, c->d_dinv.p, c->d_x.p, c->d_g.p, c->d_partial.p, counter,
+                                                         c->d_cg.p, alpha_ptr(c), beta_ptr(c), c->d_cheb_p.p, c->d_z.p, c->cheb_inv_theta);
+        c->launches++;
+        launch_cheb_steps(c, false);
+        k_direction_z<false><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_z.p, c->d_d.p, c->d_cg.p, beta_ptr(c));
+        c->launches++;
+        return;
+    }
     if (c->h_needs_zero)
-        k_update<true><<<gu, 256, 0, c->stream>>>(c->n_dofs, c->d_d.p, c->d_h.p, c->d_dinv.p, c->d_x.p, c->d_g.p, c->d_partial.p, counter,
-                                                 c->d_cg.p, alpha_ptr(c), beta_ptr(c));
+        k_update<true, false><<<gu, 256, 0, c->stream>>>(c->n_dofs, c->d_d.p, c->d_h.p, c->d_dinv.p, c->d_x.p, c->d_g.p, c->d_partial.p, counter,
+                                                        c->d_cg.p, alpha_ptr(c), beta_ptr(c), nullptr, nullptr, 0.0);
     else
-        k_update<false><<<gu, 256, 0, c->stream>>>(c->n_dofs, c->d_d.p, c->d_h.p, c->d_dinv.p, c->d_x.p, c->d_g.p, c->d_partial.p, counter,
-                                                   c->d_cg.p, alpha_ptr(c), beta_ptr(c));
+        k_update<false, false><<<gu, 256, 0, c->stream>>>(c->n_dofs, c->d_d.p, c->d_h.p, c->d_dinv.p, c->d_x.p, c->d_g.p, c->d_partial.p, counter,
+                                                          c->d_cg.p, alpha_ptr(c), beta_ptr(c), nullptr, nullptr, 0.0);
     k_direction<false><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_g.p, c->d_dinv.p, c->d_d.p, c->d_cg.p, beta_ptr(c));
     c->launches += 2;
 }
@@ -1261,8 +1463,8 @@ void launch_cg_init_direction(fb_ctx* c) {
 void launch_cg_update_only(fb_ctx* c) {
     unsigned* counter = (unsigned*) (c->d_partial.p + c->d_partial.n - 8);
     const int g = std::min(grid_for(c, c->n_dofs, 256), c->n_sm * 6);
-    k_update<false><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_d.p, c->d_h.p, c->d_dinv.p, c->d_x.p, c->d_g.p, c->d_partial.p, counter,
-                                              c->d_cg.p, alpha_ptr(c), beta_ptr(c));
+    k_update<false, false><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_d.p, c->d_h.p, c->d_dinv.p, c->d_x.p, c->d_g.p, c->d_partial.p, counter,
+                                                     c->d_cg.p, alpha_ptr(c), beta_ptr(c), nullptr, nullptr, 0.0);
     c->launches++;
 }
 void launch_cg_direction_only(fb_ctx* c) {

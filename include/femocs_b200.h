@@ -57,7 +57,9 @@ const char* fb_last_error(const fb_ctx* ctx);
 const char* fb_create_error(void);
 /* number of kernels launched by this context since creation (bench.py "gpu_launches") */
 long        fb_kernel_launches(const fb_ctx* ctx);
-/* tunables: "cg_graph_iters" (iterations per CUDA-graph launch), "cheb_degree",
+/* tunables: "cg_graph_iters" (iterations per CUDA-graph launch), "cheb_degree" (polynomial degree k >= 2 of
+ * FB_PRECOND_CHEBYSHEV, default 2 -> k SpMVs per CG iteration), "cheb_eig_ratio" (lmax / lmin of the interval, default 30), "cheb_power_iters" (power iterations that sharpen the
+ * Gershgorin bound of lmax, default 15, 0 = Gershgorin only),
  * "dof_order" (0 = deal.II first-touch numbering, 1 = Morton order of vertex coordinates),
  * "cg_profile" (see fb_last_solve_profile) */
 int         fb_set_option(fb_ctx* ctx, const char* key, double value);
