@@ -23,7 +23,6 @@ static int sync_check(fb_ctx* c, const char* what) {
 
 static void drop_graph(fb_ctx* c) {
     if (c->cg_graph) { cudaGraphExecDestroy(c->cg_graph); c->cg_graph = nullptr; }
-    if (c->mg_graph) { cudaGraphExecDestroy(c->mg_graph); c->mg_graph = nullptr; }
     c->cg_graph_n = 0;
 }
 
@@ -461,36 +460,20 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
                 if (sample >= 0) FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * sample + 2], s));
                 return FB_OK;
             };
-            // the first cg_profile iterations run un-graphed, each bracketed by events; NCCL's lazy set-up of the
-            // point-to-point and all-reduce kernels has happened above, so the loop body can be captured:
-            // check_every iterations (kernels + NCCL operations) = ONE cudaGraphLaunch per rank, which removes the
-            // ~0.1 ms of host launch gaps per iteration that the un-graphed loop showed at 4 GPUs
-            int n_prof = 0;
-            for (; prof && n_prof < c->cg_profile; ++n_prof)
-                if ((rc = iteration(n_prof))) return rc;
-            spmv += n_prof;
-            if (!c->mg_graph || c->mg_graph_key != lanes) {
-                if (c->mg_graph) { cudaGraphExecDestroy(c->mg_graph); c->mg_graph = nullptr; }
-                cudaGraph_t graph = nullptr;
-                const long before = c->launches;
-                FB_CUDA(c, cudaStreamSynchronize(s));
-                FB_CUDA(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-                int rc_cap = FB_OK;
-                for (int i = 0; i < check_every && !rc_cap; ++i) rc_cap = iteration(-1);
-                cudaError_t ec = cudaStreamEndCapture(s, &graph);
-                c->launches = before;
-                if (rc_cap) { if (graph) cudaGraphDestroy(graph); return rc_cap; }
-                FB_CUDA(c, ec);
-                FB_CUDA(c, cudaGraphInstantiate(&c->mg_graph, graph, 0));
-                cudaGraphDestroy(graph);
-                c->mg_graph_key = lanes;
-            }
+            // Host-issued loop, check_every iterations between two looks at the device-resident `done` flag.  (Capturing
+            // the iteration -- kernels + grouped ncclSend/ncclRecv + all-reduces -- into a CUDA graph was tried to remove
+            // the ~0.1 ms of launch gaps per iteration seen at 4 GPUs; the capture dead-locked on 2 x B200 with NCCL
+            // 2.28.9 and was backed out: DESIGN.md section 4.)
+            int n_prof = 0, launched = 0;
             while (true) {
                 FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
                 FB_CUDA(c, cudaStreamSynchronize(s));
                 if (h->done) break;
-                FB_CUDA(c, cudaGraphLaunch(c->mg_graph, s));
-                c->launches += 6L * check_every;
+                for (int i = 0; i < check_every; ++i, ++launched) {
+                    const bool sample = prof && launched < c->cg_profile;
+                    if ((rc = iteration(sample ? launched : -1))) return rc;
+                    if (sample) n_prof = launched + 1;
+                }
                 spmv += check_every;
             }
             if (n_prof > 0) {

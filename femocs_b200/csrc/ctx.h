@@ -152,7 +152,6 @@ struct fb_ctx {
     fb::DevBuf<int> d_cta_row, d_pers_flags;
     fb::DevBuf<long long> d_dbg; int cg_debug = 0, pers_ctas = 0;
     cudaGraphExec_t cg_graph = nullptr;
-    cudaGraphExec_t mg_graph = nullptr; int mg_graph_key = -1;      // partitioned CG: 16 iterations incl. the NCCL operations
     int cg_graph_precond = -1, cg_graph_n = 0;
     double last_solve_ms = 0; int last_iters = 0; long last_spmv = 0; int last_kernel = -1;
     double cheb_lmax = 0, cheb_ratio = 30.0, cheb_inv_theta = 0, cheb_c1[17] = {0}, cheb_c2[17] = {0};
