@@ -744,6 +744,103 @@ __global__ void __launch_bounds__(R / 2) k_spmv_jds(int n, int n_blocks, const i
     }
 }
 
+// Block-JDS SpMV with the NEXT block's window prefetched (option "spmv_kernel" 303).  Same tables and arithmetic as
+// k_spmv_jds<., 512>; the difference is the prologue: the window of the input vector and the diagonal offsets of the
+// block a CTA will process next are gathered with cp.async (8-byte / 4-byte, straight into the second shared-memory
+// buffer, no registers held) while the current block streams its matrix entries, so the two dependent L2 round
+// trips (window list -> vector entries) and the barrier of the staging phase are off the critical path of every
+// block but the first one of a CTA.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned) __cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned) __cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <bool INIT, int R>
+__global__ void __launch_bounds__(R / 2) k_spmv_jdsp(int n, int n_blocks, const int* __restrict__ jbase,
+                                                     const unsigned short* __restrict__ perm, const unsigned short* __restrict__ rlen,
+                                                     const int* __restrict__ jdp, const int* __restrict__ jd,
+                                                     const unsigned short* __restrict__ col16, const double* __restrict__ val,
+                                                     const int* __restrict__ win_off, const int* __restrict__ win_list,
+                                                     const double* __restrict__ xin, const double* __restrict__ rhs,
+                                                     const double* __restrict__ dinv, double* __restrict__ out,
+                                                     double* __restrict__ partial, unsigned* counter, CgScalars* __restrict__ cgs,
+                                                     double* __restrict__ alpha_out, int wcap, int jcap) {
+    if (!INIT && cgs->done) return;
+    constexpr int T = R / 2;
+    extern __shared__ double s_dyn[];
+    const int jstride = (jcap + 2 + 1) & ~1;                 // ints per offset buffer (even: keeps 8-byte alignment)
+    int* const s_jall = (int*) (s_dyn + 2 * (size_t) wcap);
+    const int tid = threadIdx.x;
+    // gather the window and the diagonal offsets of block b into buffer `buf` (asynchronous)
+    auto stage = [&](int b, int buf) {
+        const int w0 = __ldg(&win_off[b]), nw = __ldg(&win_off[b + 1]) - w0;
+        const int j0 = __ldg(&jdp[b]), nj = __ldg(&jdp[b + 1]) - j0;
+        double* sx = s_dyn + (size_t) buf * wcap; int* sj = s_jall + (size_t) buf * jstride;
+        for (int i0 = tid; i0 < nw; i0 += 4 * T) {           // four independent index loads, then four copies
+            int idx[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int i = i0 + u * T; idx[u] = (i < nw) ? __ldg(&win_list[w0 + i]) : -1; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (idx[u] >= 0) cp_async8(&sx[i0 + u * T], &xin[idx[u]]);
+        }
+        for (int i = tid; i < nj; i += T) cp_async4(&sj[i], &jd[j0 + i]);
+        cp_async_commit();
+    };
+    double acc[2] = {0, 0};
+    int buf = 0;
+    if ((int) blockIdx.x < n_blocks) stage(blockIdx.x, 0);
+    for (int b = blockIdx.x; b < n_blocks; b += gridDim.x, buf ^= 1) {
+        const int r0 = b * R;
+        const long base = __ldg(&jbase[b]);
+        const int sl0 = r0 + 2 * tid, sl1 = sl0 + 1;
+        const int len0 = sl0 < n ? (int) __ldg(&rlen[sl0]) : 0, len1 = sl1 < n ? (int) __ldg(&rlen[sl1]) : 0;
+        const int row0 = sl0 < n ? r0 + (int) __ldg(&perm[sl0]) : 0, row1 = sl1 < n ? r0 + (int) __ldg(&perm[sl1]) : 0;
+        cp_async_wait_all();
+        __syncthreads();             // buffer `buf` is complete; everybody has left the previous block (buffer buf ^ 1 is free)
+        const double* __restrict__ s_x = s_dyn + (size_t) buf * wcap;
+        const int* __restrict__ s_jd = s_jall + (size_t) buf * jstride;
+        const double2* __restrict__ vb = reinterpret_cast<const double2*>(val + base) + tid;
+        const ushort2* __restrict__ cb = reinterpret_cast<const ushort2*>(col16 + base) + tid;
+        double sum0 = 0, sum1 = 0;
+        double2 va[4], vb2[4];
+        ushort2 ca[4], cb2[4];
+#define FB_ISSUE(JJ, V, C)                                                                     \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u)                                          \
+            if ((JJ) + u < len0) { const int o = s_jd[(JJ) + u] >> 1; V[u] = __ldcg(&vb[o]); C[u] = __ldcg(&cb[o]); }
+#define FB_CONSUME(JJ, V, C)                                                                   \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                        \
+            if ((JJ) + u < len0) sum0 += V[u].x * s_x[C[u].x];                                 \
+            if ((JJ) + u < len1) sum1 += V[u].y * s_x[C[u].y];                                 \
+        }
+        FB_ISSUE(0, va, ca)
+        if (b + (int) gridDim.x < n_blocks) stage(b + gridDim.x, buf ^ 1);      // prefetch behind the first matrix loads
+        for (int j = 0; j < len0; j += 8) {
+            FB_ISSUE(j + 4, vb2, cb2)
+            FB_CONSUME(j, va, ca)
+            FB_ISSUE(j + 8, va, ca)
+            FB_CONSUME(j + 4, vb2, cb2)
+        }
+#undef FB_ISSUE
+#undef FB_CONSUME
+        if (INIT) {
+            if (sl0 < n) { const double g = sum0 - rhs[row0]; out[row0] = g; acc[0] += g * g * dinv[row0]; acc[1] += g * g; }
+            if (sl1 < n) { const double g = sum1 - rhs[row1]; out[row1] = g; acc[0] += g * g * dinv[row1]; acc[1] += g * g; }
+        } else {
+            if (sl0 < n) { out[row0] = sum0; acc[0] += __ldg(&xin[row0]) * sum0; }
+            if (sl1 < n) { out[row1] = sum1; acc[0] += __ldg(&xin[row1]) * sum1; }
+        }
+    }
+    cp_async_wait_all();
+    double tot[2];
+    if (reduce_publish<2>(acc, partial, counter, tot)) {
+        cg_finish_spmv<INIT>(cgs, tot, alpha_out);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Symmetric block-JDS SpMV: the matrix after the symmetric Dirichlet elimination (apply_boundary_values with
 // eliminate_columns, DealSolver.cpp:439) is symmetric, so only its strictly lower triangle is stored and
@@ -1184,6 +1281,17 @@ static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, 
         kern<<<g, (RR) / 2, smem, c->stream>>>(c->n_dofs, nb, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_jdp.p, c->d_jds_jd.p, \
                                          c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin, c->d_rhs.p, c->d_dinv.p, \
                                          out, part, counter, c->d_cg.p, alpha, c->win_cap, c->jds_maxlen); } while (0)
+        if (lanes == 303) {            // prefetching variant: two window / offset buffers
+            const size_t jstride = ((size_t) c->jds_maxlen + 2 + 1) & ~(size_t) 1;
+            const size_t smem2 = 2 * sizeof(double) * (size_t) c->win_cap + 2 * sizeof(int) * jstride;
+            auto kern = k_spmv_jdsp<INIT, 512>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2);
+            const int occ = std::max(1, std::min(6, (int) (200 * 1024 / (smem2 + 1024))));
+            const int g = std::min(nb, c->n_sm * occ);
+            kern<<<g, 256, smem2, c->stream>>>(c->n_dofs, nb, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_jdp.p, c->d_jds_jd.p,
+                                              c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin, c->d_rhs.p, c->d_dinv.p,
+                                              out, part, counter, c->d_cg.p, alpha, c->win_cap, c->jds_maxlen);
+        } else
         if (c->jds_R == 128) FB_JDS(128, 24); else if (c->jds_R == 512) FB_JDS(512, 6); else FB_JDS(256, 12);
 #undef FB_JDS
         c->launches++;
