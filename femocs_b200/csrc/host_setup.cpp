@@ -66,6 +66,14 @@ inline uint64_t spread21(uint64_t v) {          // interleave helper for 63-bit 
     return v;
 }
 
+// FB_VERBOSE=1: wall-clock laps of the host set-up on stderr
+struct Laps {
+    const char* what; double t0, t; bool on; std::string out;
+    explicit Laps(const char* w) : what(w), t0(omp_get_wtime()), t(t0), on(getenv("FB_VERBOSE") != nullptr) {}
+    void lap(const char* name) { if (!on) return; const double n = omp_get_wtime(); char b[64]; snprintf(b, sizeof b, " %s %.2f", name, 1e3 * (n - t)); out += b; t = n; }
+    ~Laps() { if (on) fprintf(stderr, "[fb] %s (ms):%s | total %.2f\n", what, out.c_str(), 1e3 * (omp_get_wtime() - t0)); }
+};
+
 }  // namespace
 
 // Phase 1: vertex compaction, orientation, boundary faces and the extremes of their centres (c->bb_mn/bb_mx).
@@ -73,6 +81,7 @@ inline uint64_t spread21(uint64_t v) {          // interleave helper for 63-bit 
 // (mark_boundary of the reference works on the global mesh).  c->part_n_owned >= 0 marks a partition: the
 // local vertices [0, part_n_owned) are owned, the rest are ghosts, and only faces touching an owned vertex count.
 int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {
+    Laps laps("import phase 1");
     c->mesh_ok = false;
     c->n_nodes = n_nodes; c->n_hex = n_hex;
     c->xyz.assign(xyz, xyz + 3 * (size_t) n_nodes);
@@ -81,6 +90,7 @@ int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* 
     for (size_t i = 0; i < c->hex8.size(); ++i)
         if (c->hex8[i] < 0 || c->hex8[i] >= n_nodes) return c->fail(FB_ERR_MESH, "hexahedron %zu references node %d", i / 8, c->hex8[i]);
 
+    laps.lap("copy+check");
     // ---- solver cells and order-preserving vertex compaction ----
     c->hex2cell.assign(n_hex, -1); c->cell2hex.clear();
     c->node2vert.assign(n_nodes, -1);
@@ -105,6 +115,7 @@ int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* 
         for (int k = 0; k < 8; ++k) cv[8 * (size_t) ce + UCD_TO_LEX[k]] = c->node2vert[h[k]];
     }
 
+    laps.lap("compaction");
     // ---- orientation (invert_all_cells_of_negative_grid) ----
     long n_neg = 0;
 #pragma omp parallel for schedule(static) reduction(+ : n_neg)
@@ -124,6 +135,7 @@ int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* 
         return c->fail(FB_ERR_MESH, "%ld of %d hexahedra have negative volume", n_neg, n_cells);
     }
 
+    laps.lap("orientation");
     // ---- vertex -> cells adjacency (CSR) ----
     std::vector<int>& v2c_off = c->h_v2c_off; std::vector<int>& v2c = c->h_v2c;
     v2c_off.assign(n_vert + 1, 0);
@@ -134,6 +146,7 @@ int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* 
     for (int ce = 0; ce < n_cells; ++ce)
         for (int k = 0; k < 8; ++k) v2c[fill[cv[8 * (size_t) ce + k]]++] = ce;     // ascending cell ids per vertex
 
+    laps.lap("v2c");
     // ---- boundary faces: a face is interior iff another cell holds all 4 of its vertices ----
     std::vector<unsigned char>& is_b = c->h_isb;
     is_b.assign(6 * (size_t) n_cells, 0);
@@ -169,6 +182,7 @@ int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* 
         }
         ctr[0] = s[0] / 4.0; ctr[1] = s[1] / 4.0; ctr[2] = s[2] / 4.0;
     };
+    laps.lap("faces");
     c->bfaces.clear();
     double mx[3] = {-1e16, -1e16, -1e16}, mn[3] = {1e16, 1e16, 1e16};
     for (int ce = 0; ce < n_cells; ++ce)
@@ -188,6 +202,7 @@ int fb_host_import_phase2(fb_ctx* c) {
     const int n_vert = c->n_vert, n_cells = c->n_cells;
     std::vector<int>& cv = c->h_cv; std::vector<int>& v2c_off = c->h_v2c_off; std::vector<int>& v2c = c->h_v2c;
     const double* mn = c->bb_mn; const double* mx = c->bb_mx;
+    Laps laps("import phase 2");
     auto face_centre = [&](int ce, int f, double ctr[3]) {      // TriaAccessor::center: vertex mean
         double s[3] = {0, 0, 0};
         for (int k = 0; k < 4; ++k) {
@@ -206,6 +221,7 @@ int fb_host_import_phase2(fb_ctx* c) {
         else bf.id = 2;                                                                           // copper_surface (bottom & other)
     }
 
+    laps.lap("face ids");
     // ---- DoF numbering ----
     c->vertex2dof.assign(n_vert, -1);
     int n_dofs = 0;
@@ -248,43 +264,46 @@ int fb_host_import_phase2(fb_ctx* c) {
 #pragma omp parallel for schedule(static)
     for (long i = 0; i < (long) cv.size(); ++i) c->cells_dof[i] = c->vertex2dof[cv[i]];
 
+    laps.lap("numbering");
     // ---- CSR sparsity: row r couples to every dof sharing a cell with it ----
+    // One pass: every thread builds the sorted column lists of its contiguous range of rows (static schedule) into
+    // its own arena; after the prefix sum of the row lengths each arena is one memcpy into the column array.
     c->rowptr.assign(n_dofs + 1, 0);
     {
-        std::vector<int> cnt(n_dofs, 0);
-#pragma omp parallel
+        const int nt = omp_get_max_threads();
+        std::vector<std::vector<int>> arena(nt);
+        std::vector<int> first_row(nt, -1), cnt(n_dofs, 0);
+#pragma omp parallel num_threads(nt)
         {
-            std::vector<int> buf;
-#pragma omp for schedule(dynamic, 2048)
+            const int t = omp_get_thread_num();
+            std::vector<int>& mine = arena[t];
+            mine.reserve((size_t) n_dofs / nt * 30 + 64);
+            std::vector<int> buf, stamp(n_all, -1);          // stamp[d] == r: dof d is already in the list of row r
+#pragma omp for schedule(static)
             for (int r = 0; r < n_dofs; ++r) {
+                if (first_row[t] < 0) first_row[t] = r;
                 const int v = c->dof2vertex[r];
                 buf.clear();
-                for (int q = v2c_off[v]; q < v2c_off[v + 1]; ++q)
-                    for (int k = 0; k < 8; ++k) buf.push_back(c->cells_dof[8 * (size_t) v2c[q] + k]);
+                for (int q = v2c_off[v]; q < v2c_off[v + 1]; ++q) {
+                    const int* cd = &c->cells_dof[8 * (size_t) v2c[q]];
+                    for (int k = 0; k < 8; ++k)
+                        if (stamp[cd[k]] != r) { stamp[cd[k]] = r; buf.push_back(cd[k]); }
+                }
                 std::sort(buf.begin(), buf.end());
-                cnt[r] = (int) (std::unique(buf.begin(), buf.end()) - buf.begin());
+                cnt[r] = (int) buf.size();
+                mine.insert(mine.end(), buf.begin(), buf.end());
             }
         }
         long tot = 0;
         for (int r = 0; r < n_dofs; ++r) { tot += cnt[r]; if (tot > 2147483647L) return c->fail(FB_ERR_MESH, "nnz exceeds 32-bit index range"); c->rowptr[r + 1] = (int) tot; }
         c->nnz = tot;
         c->col.resize(tot);
-#pragma omp parallel
-        {
-            std::vector<int> buf;
-#pragma omp for schedule(dynamic, 2048)
-            for (int r = 0; r < n_dofs; ++r) {
-                const int v = c->dof2vertex[r];
-                buf.clear();
-                for (int q = v2c_off[v]; q < v2c_off[v + 1]; ++q)
-                    for (int k = 0; k < 8; ++k) buf.push_back(c->cells_dof[8 * (size_t) v2c[q] + k]);
-                std::sort(buf.begin(), buf.end());
-                buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
-                std::copy(buf.begin(), buf.end(), c->col.begin() + c->rowptr[r]);
-            }
-        }
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+        for (int t = 0; t < nt; ++t)
+            if (first_row[t] >= 0) std::copy(arena[t].begin(), arena[t].end(), c->col.begin() + c->rowptr[first_row[t]]);
     }
 
+    laps.lap("sparsity");
     // ---- Dirichlet candidate dofs per boundary id (interpolate_boundary_values) ----
     std::vector<unsigned char> on_cu(n_all, 0), on_top(n_all, 0);
     for (const auto& bf : c->bfaces)
