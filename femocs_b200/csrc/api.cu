@@ -623,10 +623,8 @@ int fb_check_limits(fb_ctx* c, double lo, double hi, int* bad, double* mn, doubl
     cudaSetDevice(c->device);
     fb::launch_minmax(c);
     if (c->world > 1) {
-        int rc = FB_OK;
         FB_NCCL(c, fb::Nccl::get().AllReduce(c->d_minmax.p, c->d_minmax.p, 1, ncclDouble, ncclMin, (ncclComm_t) c->nccl_comm, c->stream));
         FB_NCCL(c, fb::Nccl::get().AllReduce(c->d_minmax.p + 1, c->d_minmax.p + 1, 1, ncclDouble, ncclMax, (ncclComm_t) c->nccl_comm, c->stream));
-        (void) rc;
     }
     double* h = (double*) c->pin_out.p;
     FB_CUDA(c, cudaMemcpyAsync(h, c->d_minmax.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -797,6 +795,27 @@ int fb_locate_interpolate(fb_ctx* c, int dim, int rank, long n, const double* x,
     if (cells_out) FB_CUDA(c, cudaMemcpyAsync(cells_out, final_cells, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (sol5_out) FB_CUDA(c, cudaMemcpyAsync(sol5_out, c->d_sol.p, 5 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     return sync_check(c, "fb_locate_interpolate");
+}
+
+int fb_locate_interpolate_chains(fb_ctx* c, int dim, int rank, long n_chains, long chain_len, const double* xyz,
+                                 int* cells_out, double* sol5_out) {
+    int rc = check_dim_rank(c, dim, rank);
+    if (rc) return rc;
+    FB_REQUIRE(c, chain_len >= 1 && n_chains >= 0, "fb_locate_interpolate_chains: invalid chain shape");
+    const long n = n_chains * chain_len;
+    if (n <= 0) return FB_OK;
+    FB_REQUIRE(c, xyz, "fb_locate_interpolate_chains: point array missing");
+    cudaSetDevice(c->device);
+    if ((rc = stage_points(c, n, xyz, xyz + 1, xyz + 2, 3))) return rc;
+    if ((rc = reserve_query(c, n))) return rc;
+    FB_CUDA(c, c->d_sol.alloc(5 * (size_t) n));
+    int* base = nullptr;
+    if ((rc = fb::launch_locate_chain(c, dim, rank, n, c->d_pts.p, &base, chain_len))) return rc;
+    int* final_cells = c->d_cellsA.p;
+    fb::launch_finish_interp(c, dim, rank, n, c->d_pts.p, base, 0, final_cells, c->d_sol.p);
+    if (cells_out) FB_CUDA(c, cudaMemcpyAsync(cells_out, final_cells, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (sol5_out) FB_CUDA(c, cudaMemcpyAsync(sol5_out, c->d_sol.p, 5 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return sync_check(c, "fb_locate_interpolate_chains");
 }
 
 int fb_interpolate(fb_ctx* c, int dim, int rank, long n, const double* x, const double* y, const double* z, int stride,

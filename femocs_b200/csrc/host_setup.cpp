@@ -199,7 +199,7 @@ int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* 
 // Phase 2: boundary ids from the (global) extremes, DoF numbering, sparsity of the owned rows, Dirichlet candidates.
 int fb_host_import_phase2(fb_ctx* c) {
     const double* xyz = c->xyz.data();
-    const int n_vert = c->n_vert, n_cells = c->n_cells;
+    const int n_vert = c->n_vert;
     std::vector<int>& cv = c->h_cv; std::vector<int>& v2c_off = c->h_v2c_off; std::vector<int>& v2c = c->h_v2c;
     const double* mn = c->bb_mn; const double* mx = c->bb_mx;
     Laps laps("import phase 2");

@@ -268,12 +268,13 @@ template <class Fam>
 __global__ void __launch_bounds__(128) k_chain_sweep(Tables T, long n, const double* __restrict__ pts, const int* __restrict__ scan,
                                                      const int* __restrict__ prev, int* __restrict__ next,
                                                      const unsigned char* __restrict__ dirty_prev, unsigned char* __restrict__ dirty_next,
-                                                     int first_guess, int first_sweep, int* __restrict__ changed) {
+                                                     int first_guess, int first_sweep, int* __restrict__ changed, long chain_len) {
     const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const bool need = first_sweep || (i > 0 && dirty_prev[i - 1]);
+    const bool start = chain_len > 0 ? (i % chain_len == 0) : (i == 0);     // first point of an independent chain
+    const bool need = first_sweep || (!start && dirty_prev[i - 1]);
     if (!need) { next[i] = prev[i]; dirty_next[i] = 0; return; }
-    const int guess = (i == 0) ? first_guess : abs(prev[i - 1]);
+    const int guess = start ? first_guess : abs(prev[i - 1]);
     int cell;
     if (!try_guess<Fam>(T, ldp(pts, i), guess, cell)) cell = scan[i];
     next[i] = cell;
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(128) k_chain_sweep(Tables T, long n, const dou
 template <class Fam>
 __global__ void __launch_bounds__(128) k_chain_fixpoint(Tables T, long n, const double* __restrict__ pts, const int* __restrict__ scan,
                                                         int* bufA, int* bufB, unsigned char* dirtyA, unsigned char* dirtyB,
-                                                        int first_guess, int* flags, int* __restrict__ out) {
+                                                        int first_guess, int* flags, int* __restrict__ out, long chain_len) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const long tid = (long) blockIdx.x * blockDim.x + threadIdx.x, stride = (long) gridDim.x * blockDim.x;
     const int* prev = scan; int* next = bufA;                  // the first sweep reads `scan`, which is never written
@@ -300,10 +301,13 @@ __global__ void __launch_bounds__(128) k_chain_fixpoint(Tables T, long n, const 
         bool any = false;
         for (long i = tid; i < n; i += stride) {
             // buffers written by other CTAs in the previous sweep are read through L2 (ld.global.cg)
-            const bool need = sweep == 0 || (i > 0 && __ldcg(&dprev[i - 1]));
+            // chain_len > 0: the points form independent chains of that length (EmissionReader::emission_line: every
+            // line of 32 points is a fresh SolutionReader, i.e. restarts from the first guess)
+            const bool start = chain_len > 0 ? (i % chain_len == 0) : (i == 0);
+            const bool need = sweep == 0 || (!start && __ldcg(&dprev[i - 1]));
             const int old = __ldcg(&prev[i]);
             if (!need) { next[i] = old; dcur[i] = 0; continue; }
-            const int guess = (i == 0) ? first_guess : abs(__ldcg(&prev[i - 1]));
+            const int guess = start ? first_guess : abs(__ldcg(&prev[i - 1]));
             int cell;
             if (!try_guess<Fam>(T, ldp(pts, i), guess, cell)) cell = scan[i];
             next[i] = cell;
@@ -883,7 +887,7 @@ void launch_pack_points(fb_ctx* c, long n, const double* x, const double* y, con
 // chained-guess location for n points already on the device: brute-force guess-free scan, then the
 // fix-point of the guess chain in one cooperative launch.  Result (base-family cells) in c->d_scan2.
 template <class Fam>
-static int chain_fixpoint(fb_ctx* c, const Tables& T, long n, const double* d_pts, int first_guess) {
+static int chain_fixpoint(fb_ctx* c, const Tables& T, long n, const double* d_pts, int first_guess, long chain_len) {
     auto kern = k_chain_fixpoint<Fam>;
     if (c->chain_blocks_per_sm == 0) {
         int nb = 0;
@@ -894,15 +898,15 @@ static int chain_fixpoint(fb_ctx* c, const Tables& T, long n, const double* d_pt
     const int grid = (int) std::min<long>(want, (long) c->chain_blocks_per_sm * c->n_sm);
     const double* a2 = d_pts; const int* a3 = c->d_scan.p; int* a4 = c->d_cellsA.p; int* a5 = c->d_cellsB.p;
     unsigned char* a6 = c->d_dirtyA.p; unsigned char* a7 = c->d_dirtyB.p; int a8 = first_guess; int* a9 = c->d_flag.p; int* a10 = c->d_scan2.p;
-    Tables t = T; long nn = n;
-    void* args[] = {&t, &nn, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10};
+    Tables t = T; long nn = n; long cl = chain_len;
+    void* args[] = {&t, &nn, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10, &cl};
     cudaError_t e = cudaLaunchCooperativeKernel((void*) kern, dim3(grid), dim3(128), args, 0, c->stream);
     if (e != cudaSuccess) return c->fail(FB_ERR_CUDA, "locate chain launch failed: %s", cudaGetErrorString(e));
     c->launches++;
     return FB_OK;
 }
 
-int launch_locate_chain(fb_ctx* c, int dim, int rank, long n, const double* d_pts, int** result) {
+int launch_locate_chain(fb_ctx* c, int dim, int rank, long n, const double* d_pts, int** result, long chain_len) {
     const Tables T = make_tables(c);
     // abs(-1) = 1 is the first guess of the reference loop (SolutionReader.cpp:145, InterpolatorCells.cpp:443);
     // hex/quad ranks divide it by 4/3 (:1539, :1955)
@@ -912,7 +916,8 @@ int launch_locate_chain(fb_ctx* c, int dim, int rank, long n, const double* d_pt
     else k_scan_cells<TetFam, 128><<<gs, 256, 0, c->stream>>>(T, n, d_pts, c->d_scan.p);
     c->launches++;
     cudaMemsetAsync(c->d_flag.p, 0, 4 * sizeof(int), c->stream);
-    const int rc = (dim == 2) ? chain_fixpoint<TriFam>(c, T, n, d_pts, first_guess) : chain_fixpoint<TetFam>(c, T, n, d_pts, first_guess);
+    const int rc = (dim == 2) ? chain_fixpoint<TriFam>(c, T, n, d_pts, first_guess, chain_len)
+                              : chain_fixpoint<TetFam>(c, T, n, d_pts, first_guess, chain_len);
     if (rc) return rc;
     *result = c->d_scan2.p;
     return FB_OK;

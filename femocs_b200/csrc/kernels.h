@@ -38,7 +38,7 @@ void launch_scatter(fb_ctx* c, int n, const int* idx, const double* src, double*
 // interp_kernels.cu
 void launch_extract(fb_ctx* c, int smoothen);
 void launch_pack_points(fb_ctx* c, long n, const double* x, const double* y, const double* z, int stride, double* out);
-int launch_locate_chain(fb_ctx* c, int dim, int rank, long n, const double* d_pts, int** result);
+int launch_locate_chain(fb_ctx* c, int dim, int rank, long n, const double* d_pts, int** result, long chain_len = 0);
 void launch_finish_interp(fb_ctx* c, int dim, int rank, long n, const double* d_pts, const int* d_base, int final_cells,
                           int* d_cells_out, double* d_sol);
 void launch_particle_cells(fb_ctx* c, long n, const double* d_pts, int* d_cells, bool after_move = false);

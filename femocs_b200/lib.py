@@ -46,6 +46,7 @@ SIGNATURES = {
     "fb_get_nodal_solutions": (C.c_int, [vp, vp]),
     "fb_set_nodal_solutions": (C.c_int, [vp, vp]),
     "fb_locate_interpolate": (C.c_int, [vp, C.c_int, C.c_int, C.c_long, vp, vp, vp, C.c_int, vp, vp]),
+    "fb_locate_interpolate_chains": (C.c_int, [vp, C.c_int, C.c_int, C.c_long, C.c_long, vp, vp, vp]),
     "fb_interpolate": (C.c_int, [vp, C.c_int, C.c_int, C.c_long, vp, vp, vp, C.c_int, vp, vp]),
     "fb_particle_cells": (C.c_int, [vp, C.c_long, vp, vp]),
     "fb_particle_field": (C.c_int, [vp, C.c_long, vp, vp, vp]),

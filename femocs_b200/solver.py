@@ -333,6 +333,16 @@ class SolutionReader:
                 _p(self.markers), _p(self.interpolation)))
         self.atoms_mapped_to_cells = True
 
+    # batched EmissionReader::emission_line look-ups (src/EmissionReader.cpp:51-61): `lines` is (n_lines, n_per_line, 3);
+    # every line is an independent guess chain (a fresh phis_on_line reader in the reference)
+    def interpolate_lines(self, lines):
+        lines = _f(lines)
+        assert lines.ndim == 3 and lines.shape[2] == 3
+        nl, npl = lines.shape[:2]
+        cells = np.zeros((nl, npl), np.int32); sol = np.zeros((nl, npl, 5))
+        self.ctx.check(self.ctx.L.fb_locate_interpolate_chains(self.ctx.h, self.dim, self.rank, nl, npl, _p(lines), _p(cells), _p(sol)))
+        return cells, sol
+
     # SolutionReader::calc_interpolation (src/SolutionReader.cpp:167-190)
     def calc_interpolation(self):
         if not self.atoms_mapped_to_cells:

@@ -197,6 +197,13 @@ int fb_interpolate(fb_ctx* ctx, int dim, int rank, long n,
                    const double* x, const double* y, const double* z, int stride,
                    const int* cells, double* sol5_out);
 
+/* void EmissionReader::emission_line(point, direction, rmax)     src/EmissionReader.cpp:51-61, batched:
+ *   n_chains independent point sequences of chain_len points each (xyz: n_chains * chain_len packed triples);
+ *   every sequence is located like a fresh SolutionReader (phis_on_line.reserve + calc_interpolation: the guess
+ *   chain restarts from the first guess at the first point of each line), all sequences in one call. */
+int fb_locate_interpolate_chains(fb_ctx* ctx, int dim, int rank, long n_chains, long chain_len,
+                                 const double* xyz, int* cells_out, double* sol5_out);
+
 /* int Pic<3>::update_point_cell(const SuperParticle&)           src/Pic.cpp:186-196
  *   cell_inout: solver cell index guess in, located solver cell (or -1) out. */
 int fb_particle_cells(fb_ctx* ctx, long n, const double* xyz, int* cell_inout);

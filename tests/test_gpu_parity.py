@@ -282,6 +282,30 @@ def test_particles_golden(name, fb, golden, gpu_interp):
     assert np.abs(E - g["pic_field"]).max() <= 1e-12 * np.abs(g["pic_field"]).max()
 
 
+@pytest.mark.parametrize("rank", [1, 3])
+def test_emission_lines_match_oracle(rank, fb, golden, gpu_interp, oracles):
+    """batched EmissionReader::emission_line look-ups (32 potential samples along every face normal, each line an
+    independent guess chain) == the oracle's chained locate run once per line: cells bit-exact"""
+    m = golden("mesh", "mdsmall"); o = oracles["mdsmall"]
+    c, s, it = gpu_interp["mdsmall"]
+    nod = hash_field(it.n_nodes, 5, 1)
+    it.set_solutions(nod); o.set_nodal(nod)
+    tri = m["tris"][::7][:120]
+    cent = m["nodes"][tri].mean(1); nrm = m["tri_norms"][::7][:120]
+    rmax = np.linspace(2.0, 40.0, len(tri))
+    t = np.linspace(1e-5, 1.0, 32)                                   # rmin = 1e-5 rmax (EmissionReader.cpp:52-58)
+    lines = cent[:, None, :] + nrm[:, None, :] * (rmax[:, None, None] * t[None, :, None])
+    r = fb.SolutionReader(it); r.set_preferences(False, 3, rank)
+    cells, sol = r.interpolate_lines(lines)
+    for k in range(len(lines)):
+        oc, os_ = o.locate_interpolate(3, rank, lines[k])
+        assert np.array_equal(cells[k], oc), "line %d" % k
+        assert np.abs(sol[k] - os_).max() <= 1e-12 * max(1.0, np.abs(os_).max())
+    # one chain over all points gives a different (chained) answer path but the batched call must not depend on batch order
+    cells2, _ = r.interpolate_lines(lines[::-1].copy())
+    assert np.array_equal(cells2[::-1], cells)
+
+
 @pytest.mark.parametrize("name", ["hemicone", "mdsmall"])
 def test_pic_push_golden(name, fb, golden, gpu_interp):
     """Pic::update_positions (+clear_lost) and Pic::update_velocities on the device against vectors produced with the
