@@ -677,7 +677,9 @@ __global__ void k_csr_to_jds(int n, int R, const int* __restrict__ rowptr, const
 
 // R rows per block, R / 2 threads: thread t owns the rows in slots 2t and 2t+1 (len0 >= len1) and fetches
 // their entries of a diagonal with ONE 16-byte value load and ONE 4-byte window-position load.
-template <bool INIT, int R>
+// CS: the matrix stream is read with ld.global.cs (evict-first) so that it does not push the input vector,
+// which the windows of neighbouring blocks re-read, out of L2 (option "spmv_kernel" 304).
+template <bool INIT, int R, bool CS>
 __global__ void __launch_bounds__(R / 2) k_spmv_jds(int n, int n_blocks, const int* __restrict__ jbase,
                                                     const unsigned short* __restrict__ perm, const unsigned short* __restrict__ rlen,
                                                     const int* __restrict__ jdp, const int* __restrict__ jd,
@@ -714,7 +716,7 @@ __global__ void __launch_bounds__(R / 2) k_spmv_jds(int n, int n_blocks, const i
         ushort2 ca[4], cb2[4];
 #define FB_ISSUE(JJ, V, C)                                                                     \
         _Pragma("unroll") for (int u = 0; u < 4; ++u)                                          \
-            if ((JJ) + u < len0) { const int o = s_jd[(JJ) + u]; V[u] = __ldcg(&vb[o]); C[u] = __ldcg(&cb[o]); }
+            if ((JJ) + u < len0) { const int o = s_jd[(JJ) + u]; V[u] = CS ? __ldcs(&vb[o]) : __ldcg(&vb[o]); C[u] = CS ? __ldcs(&cb[o]) : __ldcg(&cb[o]); }
 #define FB_CONSUME(JJ, V, C)                                                                   \
         _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                        \
             if ((JJ) + u < len0) sum0 += V[u].x * s_x[C[u].x];                                 \
@@ -1200,8 +1202,8 @@ void stream_block_shape(int kernel, int& chunk, int& maxrows) {
 
 int choose_lanes(const fb_ctx* c) {
     // 0 selects the row-block streaming kernel (option "spmv_kernel": -1 auto, 0 stream, else lanes per row)
-    if (c->spmv_kernel >= 0) return (c->world > 1 && c->spmv_kernel >= 310) ? 302 : c->spmv_kernel;
-    if (c->nnz >= 4000000) return 302;
+    if (c->spmv_kernel >= 0) return (c->world > 1 && c->spmv_kernel >= 310) ? 304 : c->spmv_kernel;
+    if (c->nnz >= 4000000) return 304;        // block-JDS, 512 rows per block, evict-first matrix stream
     const double avg = c->n_dofs ? (double) c->nnz / c->n_dofs : 1.0;
     if (avg > 48) return 32;
     if (avg > 20) return 8;
@@ -1274,13 +1276,22 @@ static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, 
         const int nb = c->jds_nb;
         const size_t smem = sizeof(double) * (size_t) c->win_cap + sizeof(int) * ((size_t) c->jds_maxlen + 2);
 #define FB_JDS(RR, OCC) do {                                                                                                        \
-        auto kern = k_spmv_jds<INIT, RR>;                                                                                           \
+        auto kern = k_spmv_jds<INIT, RR, false>;                                                                                           \
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);                                        \
         const int occ = std::max(1, std::min((OCC), (int) (200 * 1024 / (smem + 1024))));                                           \
         const int g = std::min(nb, c->n_sm * occ);                                                                                  \
         kern<<<g, (RR) / 2, smem, c->stream>>>(c->n_dofs, nb, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_jdp.p, c->d_jds_jd.p, \
                                          c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin, c->d_rhs.p, c->d_dinv.p, \
                                          out, part, counter, c->d_cg.p, alpha, c->win_cap, c->jds_maxlen); } while (0)
+        if (lanes == 304) {            // evict-first matrix stream
+            auto kern = k_spmv_jds<INIT, 512, true>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            const int occ = std::max(1, std::min(6, (int) (200 * 1024 / (smem + 1024))));
+            const int g = std::min(nb, c->n_sm * occ);
+            kern<<<g, 256, smem, c->stream>>>(c->n_dofs, nb, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_jdp.p, c->d_jds_jd.p,
+                                              c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin, c->d_rhs.p, c->d_dinv.p,
+                                              out, part, counter, c->d_cg.p, alpha, c->win_cap, c->jds_maxlen);
+        } else
         if (lanes == 303) {            // prefetching variant: two window / offset buffers
             const size_t jstride = ((size_t) c->jds_maxlen + 2 + 1) & ~(size_t) 1;
             const size_t smem2 = 2 * sizeof(double) * (size_t) c->win_cap + 2 * sizeof(int) * jstride;
@@ -1390,7 +1401,7 @@ cudaError_t cheb_prepare(fb_ctx* c, int lanes) {
             // sharpen: power iteration (lower bound) x 1.2, never above the Gershgorin bound
             unsigned* counter = (unsigned*) (c->d_partial.p + c->d_partial.n - 8);
             const int g = grid_for(c, c->n_dofs, 256);
-            const int pl = (lanes >= 310) ? 302 : lanes;
+            const int pl = (lanes >= 310) ? 304 : lanes;
             k_power_init<<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_cheb_p.p);
             for (int i = 0; i < c->cheb_power_iters; ++i) {
                 spmv_dispatch<false>(c, pl, c->d_cheb_p.p, c->d_h.p, (double*) (c->d_cg.p + 1) + 3);
@@ -1416,7 +1427,7 @@ cudaError_t cheb_prepare(fb_ctx* c, int lanes) {
         rho = rho_new;
     }
     c->cheb_k = k;
-    c->cheb_lanes = (lanes >= 310) ? 302 : lanes;       // the symmetric layout accumulates into a zeroed vector: not used here
+    c->cheb_lanes = (lanes >= 310) ? 304 : lanes;       // the symmetric layout accumulates into a zeroed vector: not used here
     return cudaSuccess;
 }
 
