@@ -223,6 +223,11 @@ def run_b200(args):
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line, the JSON: whatever native libraries print there while we run (NCCL announces
+    # its version on stdout at communicator creation) is sent to stderr at the file-descriptor level
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- femocs_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -370,11 +375,14 @@ def run_b200(args):
                 "value": o.n_dofs * abs(it) / dt / 1e9, "unit": "GDoF/s per CG iteration", "cores": cpu_threads(), "kind": "port",
                 "sample": "X base mesh (refinement level 0: %d DoF) -- one step: setup + assemble + SSOR(1.2)-CG to abs 1e-9, %d iterations, %.1f s; "
                           "SSOR sweeps serial as in deal.II, vmult on %d threads" % (o.n_dofs, it, dt, cpu_threads())}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
 
 def native_step(fb, torch, args):
