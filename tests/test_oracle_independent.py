@@ -46,7 +46,7 @@ def _boundary_faces(hexs):
     return fv[cnt[inv.reshape(-1)] == 1]
 
 
-def _solve(m, field):
+def _solve(m, field, anode_potential=None):
     nodes = m["nodes"]; hexs = m["hexs"][m["hex_markers"] > 0].astype(np.int64)
     n = len(nodes)
     Ke, vol = _stiffness(nodes, hexs)
@@ -73,9 +73,13 @@ def _solve(m, field):
             np.add.at(b, bf[top].reshape(-1), (ws * wt * field * dA[:, None] * N[None, :]).reshape(-1))
     used = np.zeros(n, bool); used[hexs.reshape(-1)] = True
     fixed = np.zeros(n, bool); fixed[bf[copper].reshape(-1)] = True
-    free = used & ~fixed
     phi = np.zeros(n)
-    phi[free] = spla.spsolve(K[free][:, free].tocsc(), b[free])           # Dirichlet value 0: no lift
+    if anode_potential is not None:          # Dirichlet anode (append_dirichlet on vacuum_top, later call wins on shared dofs)
+        b[:] = 0.0
+        fixed[bf[top].reshape(-1)] = True
+        phi[bf[top].reshape(-1)] = anode_potential
+    free = used & ~fixed
+    phi[free] = spla.spsolve(K[free][:, free].tocsc(), b[free] - (K[free][:, fixed] @ phi[fixed]))
     return K, b, phi, used, vol
 
 
@@ -99,3 +103,9 @@ def test_oracle_arithmetic_matches_an_independent_derivation(name, golden):
     # potential: direct solve of the reduced system vs the oracle's eliminate-and-CG
     ref = o.export_solution()
     assert np.abs(ref - phi[v2n]).max() <= 1e-9 * np.abs(ref).max()
+    # Dirichlet anode (anode_BC = dirichlet): V0 on the top plane, 0 on copper, no Neumann load
+    _, _, phi_d, _, _ = _solve(m, 0.0, anode_potential=7.5)
+    o.setup(0.0, 7.5, True); o.assemble(True)
+    assert o.solve(10000, 1e-12, 1.2, 0) > 0
+    ref = o.export_solution()
+    assert np.abs(ref - phi_d[v2n]).max() <= 1e-9 * np.abs(ref).max()
