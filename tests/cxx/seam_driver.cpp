@@ -77,7 +77,20 @@ int main(int argc, char** argv) {
         fields.export_results(n, "elfield_norm", Enorm.data());
         std::vector<int> flag(n, 0); fields.export_flags(n, flag.data());
         std::vector<double> sol; poisson_solver.export_solution(sol);
+        // one PIC push through the Pic seam (make_pic_step, ProjectRunaway.cpp:492-511): update_positions, then update_velocities
+        std::vector<double> ppos = b.d["pic_pos"], pvel = b.d["pic_vel"];
+        std::vector<int> pcell = b.i["pic_cells"];
+        int n_lost = 0;
+        if (!pcell.empty()) {
+            Pic pic(&vacuum_interpolator);
+            const long np = (long) pcell.size();
+            n_lost = pic.update_positions(np, ppos.data(), pvel.data(), pcell.data(), b.d["pic_dt"][0], b.d["pic_box"].data(), true);
+            const long kept = np - n_lost;
+            ppos.resize(3 * kept); pvel.resize(3 * kept); pcell.resize(kept);
+            pic.update_velocities(kept, ppos.data(), pcell.data(), pvel.data(), b.d["pic_dt"][0], b.d["pic_dt"][1]);
+        }
         std::ofstream f(argv[2], std::ios::binary);
+        put(f, "pic_pos", ppos); put(f, "pic_vel", pvel); put(f, "pic_cells", pcell); put(f, "pic_lost", std::vector<int>{n_lost});
         put(f, "ncg", std::vector<int>{ncg, (int) out_of_limits, (int) ctx.kernel_launches()});
         put(f, "stat", std::vector<double>{poisson_solver.stat.sol_min, poisson_solver.stat.sol_max, fields.E_max});
         put(f, "phi_vertex", sol); put(f, "markers", fields.markers); put(f, "E", E); put(f, "phi", phi); put(f, "Enorm", Enorm); put(f, "flag", flag);
