@@ -167,6 +167,16 @@ def oracle_x_step(o):
     return it, dt
 
 
+def oracle_x_jacobi(o):
+    """the same system with the GPU path's own algorithm (Jacobi-PCG) on the host: the oracle's CG with the OpenMP
+    vmult on all cores -- the like-for-like CPU number SURVEY.md section 8d asks for next to the SSOR port"""
+    o.setup(-E0, 0.0, False)
+    o.assemble(True)
+    t = time.perf_counter()
+    it = o.solve(N_CG, CG_TOL, 1.2, 1)
+    return it, time.perf_counter() - t
+
+
 def cpu_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -375,6 +385,10 @@ def run_b200(args):
                 "value": o.n_dofs * abs(it) / dt / 1e9, "unit": "GDoF/s per CG iteration", "cores": cpu_threads(), "kind": "port",
                 "sample": "X base mesh (refinement level 0: %d DoF) -- one step: setup + assemble + SSOR(1.2)-CG to abs 1e-9, %d iterations, %.1f s; "
                           "SSOR sweeps serial as in deal.II, vmult on %d threads" % (o.n_dofs, it, dt, cpu_threads())}
+            itj, dtj = oracle_x_jacobi(o)
+            line["cpu_baseline"]["jacobi_pcg_all_cores"] = {
+                "value": o.n_dofs * abs(itj) / dtj / 1e9, "unit": "GDoF/s per CG iteration", "iterations": itj, "solve_s": dtj,
+                "cores": cpu_threads(), "note": "same algorithm as the GPU path (Jacobi-PCG, abs 1e-9) on the same base mesh, solve only"}
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
