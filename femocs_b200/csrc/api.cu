@@ -191,6 +191,28 @@ int fb_plan_get(const fb_ctx* c, int* local2global, int* owner, int* send_off, i
     if (top_flag) { std::fill(top_flag, top_flag + c->n_cols, 0); for (int d : c->top_dofs) top_flag[d] = 1; }
     return FB_OK;
 }
+// host-only: the block-JDS tables of the HBM SpMV for the plan's sparsity (CPU tests of fb_host_jds_build)
+int fb_plan_jds(fb_ctx* c, int R, int max_window, int sym, long* sizes6) {
+    FB_REQUIRE(c, c->host_only && c->mesh_ok, "fb_plan_jds: needs a plan context after fb_plan_phase2");
+    FB_REQUIRE(c, R == 128 || R == 256 || R == 512, "fb_plan_jds: R must be 128, 256 or 512");
+    if (!fb_host_jds_build(c, R, max_window, sym != 0)) return c->fail(FB_ERR_ARG, "fb_plan_jds: a window exceeds max_window or a row is too long");
+    sizes6[0] = c->jds_nb; sizes6[1] = c->jds_size; sizes6[2] = c->win_off[c->jds_nb]; sizes6[3] = c->jds_maxlen; sizes6[4] = c->win_max;
+    sizes6[5] = (long) c->jds_jd.size();
+    return FB_OK;
+}
+int fb_plan_jds_get(const fb_ctx* c, unsigned short* perm, unsigned short* len, unsigned short* slot, int* jdp, int* jd, int* base,
+                    unsigned short* col16, int* win_off, int* win_list) {
+    if (perm) std::copy(c->jds_perm.begin(), c->jds_perm.end(), perm);
+    if (len) std::copy(c->jds_len.begin(), c->jds_len.end(), len);
+    if (slot) std::copy(c->jds_slot.begin(), c->jds_slot.end(), slot);
+    if (jdp) std::copy(c->jds_jdp.begin(), c->jds_jdp.end(), jdp);
+    if (jd) std::copy(c->jds_jd.begin(), c->jds_jd.end(), jd);
+    if (base) std::copy(c->jds_base.begin(), c->jds_base.end(), base);
+    if (col16) std::copy(c->col16.begin(), c->col16.begin() + c->jds_size, col16);
+    if (win_off) std::copy(c->win_off.begin(), c->win_off.end(), win_off);
+    if (win_list) std::copy(c->win_list.begin(), c->win_list.end(), win_list);
+    return FB_OK;
+}
 void* fb_get_stream(fb_ctx* c) { return (void*) c->stream; }
 
 // ------------------------------------------------------------------------------------------

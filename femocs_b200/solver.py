@@ -506,3 +506,17 @@ class PartitionPlan:
         a["send_idx"] = a["send_idx"][:self.n_send]
         self.__dict__.update(a)
         return self
+
+    def jds(self, R=512, max_window=8192, sym=False):
+        """block-JDS tables of the HBM SpMV for this plan's sparsity (fb_host_jds_build), as numpy arrays"""
+        sz = np.zeros(6, np.int64)
+        self._check(self.L.fb_plan_jds(self.h, int(R), int(max_window), int(sym), _p(sz)))
+        nb, size, nwin, maxlen, wmax, njd = [int(v) for v in sz]
+        t = dict(R=R, nb=nb, size=size, maxlen=maxlen, win_max=wmax,
+                 perm=np.zeros(nb * R, np.uint16), len=np.zeros(nb * R, np.uint16), slot=np.zeros(self.n_rows, np.uint16),
+                 jdp=np.zeros(nb + 1, np.int32), jd=np.zeros(njd, np.int32), base=np.zeros(nb + 1, np.int32),
+                 col16=np.zeros(size, np.uint16), win_off=np.zeros(nb + 1, np.int32), win_list=np.zeros(max(1, nwin), np.int32))
+        self._check(self.L.fb_plan_jds_get(self.h, _p(t["perm"]), _p(t["len"]), _p(t["slot"]), _p(t["jdp"]), _p(t["jd"]), _p(t["base"]),
+                                           _p(t["col16"]), _p(t["win_off"]), _p(t["win_list"])))
+        t["win_list"] = t["win_list"][:nwin]
+        return t

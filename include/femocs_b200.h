@@ -89,6 +89,11 @@ int fb_plan_phase2(fb_ctx* plan, const double* bbox6_global);
 int fb_plan_sizes(const fb_ctx* plan, long* out8);
 int fb_plan_get(const fb_ctx* plan, int* local2global, int* owner, int* send_off, int* send_idx, int* recv_off, int* rowptr, int* col,
                 int* cells_dof, int* local_cell2global, int* copper_flag, int* top_flag);
+/* host-only: block-JDS tables (R rows per block; sym != 0: lower triangle only) of the plan's sparsity.
+ * sizes6 = {blocks, stored slots incl. padding, window entries, longest row, largest window, diagonal offsets} */
+int fb_plan_jds(fb_ctx* plan, int R, int max_window, int sym, long* sizes6);
+int fb_plan_jds_get(const fb_ctx* plan, unsigned short* perm, unsigned short* len, unsigned short* slot, int* jdp, int* jd,
+                    int* base, unsigned short* col16, int* win_off, int* win_list);
 
 /* ---------------------------------------------------------------------------------------
  * bool DealSolver<3>::import_mesh(vector<Point<3>> vertices, vector<CellData<3>> cells)
