@@ -122,7 +122,7 @@ def _worker(rank, world, port, mesh_name, out_q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,mesh", [(2, "mdsmall"), (4, "hemicone"), (3, "mdsmall")])
+@pytest.mark.parametrize("world,mesh", [(2, "mdsmall"), (4, "hemicone"), (3, "mdsmall"), (8, "mdbig")])
 def test_partition_plan_gloo(world, mesh):
     import torch.multiprocessing as mp
     from femocs_b200 import build
