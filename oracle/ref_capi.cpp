@@ -264,6 +264,18 @@ void ref_interp_known_cells(int dim, int rank, int n, const double* xyz, const i
     }
 }
 
+// SolutionReader::export_results (SolutionReader.cpp:303-398) of the reference itself: atoms with the given ids and
+// interpolated Solutions, exported under `label` into data (n_points entries, 3 n_points for the vector label).
+// Returns the reference's return value (0 ok, 1 nothing to export).
+int ref_export_results(int n, const int* ids, const double* sol5, int n_points, const char* label, double* data) {
+    SolutionReader sr(S->interp.get(), LABELS.elfield, LABELS.charge_density, LABELS.potential);
+    sr.reserve(n);
+    for (int i = 0; i < n; ++i) sr.append(Atom(ids[i], Point3(0, 0, 0), 0));
+    for (int i = 0; i < n; ++i)          // reserve() has sized the interpolation vector
+        sr.set_interpolation(i, Solution(Vec3(sol5[5*i], sol5[5*i+1], sol5[5*i+2]), sol5[5*i+3], sol5[5*i+4]));
+    return sr.export_results(n_points, label, data);
+}
+
 // Pic::update_point_cell (Pic.cpp:186-196): solver-cell guess in, solver-cell (or -1) out
 void ref_particle_cells(int n, const double* xyz, int* cell_inout) {
     Interpolator& I = *S->interp;

@@ -228,6 +228,14 @@ class RefLib:
         self.lib.ref_interp_known_cells(dim, rank, n, xyz.reshape(-1), np.ascontiguousarray(cells, np.int32), sol.reshape(-1))
         return sol
 
+    def export_results(self, ids, sol5, n_points, label, data):
+        """the reference's own SolutionReader::export_results (label-case append / overwrite rule) on `data` in place"""
+        ids = np.ascontiguousarray(ids, np.int32); sol5 = np.ascontiguousarray(sol5, np.float64)
+        assert data.dtype == np.float64 and data.flags.c_contiguous
+        self.lib.ref_export_results.restype = C.c_int
+        return self.lib.ref_export_results(len(ids), ids.ctypes.data_as(C.c_void_p), sol5.ctypes.data_as(C.c_void_p), int(n_points),
+                                           label.encode(), data.ctypes.data_as(C.c_void_p))
+
     def particle_cells(self, xyz, guess):
         xyz = np.ascontiguousarray(xyz, np.float64)
         cells = np.ascontiguousarray(guess, np.int32).copy()

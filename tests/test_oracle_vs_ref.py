@@ -39,3 +39,31 @@ def test_oracle_matches_reference_code(preset):
     sd = np.zeros(o.n_dofs); sd[v2d] = phi; o.set_solution(sd)
     for sm in (0, 1):
         assert np.array_equal(r.extract_solution(phi, np.zeros_like(phi), sm, len(m["nodes"])), o.extract_solution(sm))
+
+
+def test_export_results_mirror_matches_reference_code():
+    """SolutionReader::export_results (label-case append / overwrite, id filtering; SolutionReader.cpp:269-398) of the
+    compiled reference against the host mirror femocs_b200.SolutionReader.export_results on the same atoms"""
+    import types
+    import femocs_b200 as fb
+    r = reflib.RefLib()
+    r.generate("hemicone")
+    rng = np.random.default_rng(3)
+    n, n_points = 300, 260
+    ids = rng.permutation(n).astype(np.int32) - 15              # some ids < 0 and some >= n_points: skipped by both
+    ids[5] = ids[6]                                             # a repeated id: appended twice / last one wins
+    sol = rng.normal(size=(n, 5))
+    mirror = fb.SolutionReader(types.SimpleNamespace(ctx=None))
+    mirror.points = np.zeros((n, 3)); mirror.ids = ids; mirror.interpolation = sol; mirror.markers = np.zeros(n, np.int32)
+    for label in ("elfield", "ELFIELD", "Elfield", "elfield_norm", "ELFIELD_NORM", "charge_density", "CHARGE_DENSITY",
+                  "potential", "POTENTIAL"):
+        width = 3 if label.lower() == "elfield" else 1
+        a = rng.normal(size=n_points * width); b = a.copy()
+        assert r.export_results(ids, sol, n_points, label, a) == 0
+        assert mirror.export_results(n_points, label, b) == 0
+        assert np.array_equal(a, b), label
+    # nothing to export -> 1 (check_return), data untouched
+    empty = fb.SolutionReader(types.SimpleNamespace(ctx=None))
+    a = np.ones(4)
+    assert empty.export_results(4, "elfield_norm", a) == 1 and np.all(a == 1)
+    assert r.export_results(np.zeros(0, np.int32), np.zeros((0, 5)), 4, "elfield_norm", a) == 1 and np.all(a == 1)
