@@ -21,6 +21,7 @@
 #include "TetgenMesh.h"
 #include "Interpolator.h"
 #include "SolutionReader.h"
+#include "ParticleSpecies.h"
 
 #include <cstring>
 #include <memory>
@@ -274,6 +275,28 @@ int ref_export_results(int n, const int* ids, const double* sol5, int n_points, 
     for (int i = 0; i < n; ++i)          // reserve() has sized the interpolation vector
         sr.set_interpolation(i, Solution(Vec3(sol5[5*i], sol5[5*i+1], sol5[5*i+2]), sol5[5*i+3], sol5[5*i+4]));
     return sr.export_results(n_points, label, data);
+}
+
+// periodic_image (Macros.cpp:41-48), element-wise
+void ref_periodic_image(int n, const double* p, double pmax, double pmin, double* out) {
+    for (int i = 0; i < n; ++i) out[i] = periodic_image(p[i], pmax, pmin);
+}
+
+// ParticleSpecies::clear_lost (ParticleSpecies.cpp:16-31) on particles (pos, vel, cell): survivors written back in place,
+// returns the number of lost particles
+int ref_clear_lost(int n, double* pos3, double* vel3, int* cell) {
+    ParticleSpecies ps(-17.5882, -180.9512268, 0.01);
+    ps.reserve(n);
+    for (int i = 0; i < n; ++i)
+        ps.inject_particle(Point3(pos3[3*i], pos3[3*i+1], pos3[3*i+2]), Vec3(vel3[3*i], vel3[3*i+1], vel3[3*i+2]), cell[i]);
+    const int lost = ps.clear_lost();
+    for (int i = 0; i < ps.size(); ++i) {
+        const SuperParticle& sp = ps[i];
+        pos3[3*i] = sp.pos.x; pos3[3*i+1] = sp.pos.y; pos3[3*i+2] = sp.pos.z;
+        vel3[3*i] = sp.vel.x; vel3[3*i+1] = sp.vel.y; vel3[3*i+2] = sp.vel.z;
+        cell[i] = sp.cell;
+    }
+    return lost;
 }
 
 // Pic::update_point_cell (Pic.cpp:186-196): solver-cell guess in, solver-cell (or -1) out

@@ -236,6 +236,20 @@ class RefLib:
         return self.lib.ref_export_results(len(ids), ids.ctypes.data_as(C.c_void_p), sol5.ctypes.data_as(C.c_void_p), int(n_points),
                                            label.encode(), data.ctypes.data_as(C.c_void_p))
 
+    def periodic_image(self, p, pmax, pmin):
+        p = np.ascontiguousarray(p, np.float64); out = np.zeros_like(p)
+        self.lib.ref_periodic_image.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+        self.lib.ref_periodic_image(len(p), p.ctypes.data_as(C.c_void_p), float(pmax), float(pmin), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def clear_lost(self, pos, vel, cells):
+        """ParticleSpecies::clear_lost of the reference: returns (pos, vel, cells, n_lost) of the survivors"""
+        pos = np.array(pos, np.float64, copy=True); vel = np.array(vel, np.float64, copy=True); cells = np.array(cells, np.int32, copy=True)
+        self.lib.ref_clear_lost.restype = C.c_int
+        lost = self.lib.ref_clear_lost(len(cells), pos.ctypes.data_as(C.c_void_p), vel.ctypes.data_as(C.c_void_p), cells.ctypes.data_as(C.c_void_p))
+        k = len(cells) - lost
+        return pos[:k], vel[:k], cells[:k], lost
+
     def particle_cells(self, xyz, guess):
         xyz = np.ascontiguousarray(xyz, np.float64)
         cells = np.ascontiguousarray(guess, np.int32).copy()

@@ -67,3 +67,28 @@ def test_export_results_mirror_matches_reference_code():
     a = np.ones(4)
     assert empty.export_results(4, "elfield_norm", a) == 1 and np.all(a == 1)
     assert r.export_results(np.zeros(0, np.int32), np.zeros((0, 5)), 4, "elfield_norm", a) == 1 and np.all(a == 1)
+
+
+def test_pic_push_pieces_match_reference_code():
+    """the two pieces of the PIC push that compile from the reference without the solver -- periodic_image
+    (Macros.cpp:41-48) and ParticleSpecies::clear_lost (ParticleSpecies.cpp:16-31) -- against oracle/pic.py"""
+    from oracle import pic
+    r = reflib.RefLib()
+    rng = np.random.default_rng(11)
+    p = rng.uniform(-30.0, 30.0, size=5000)
+    p[:6] = [-10.0, 10.0, -10.0 - 1e-13, 10.0 + 1e-13, 0.0, 25.0]       # exactly on / just past the box faces
+    assert np.array_equal(r.periodic_image(p, 10.0, -10.0), pic.periodic_image(p, 10.0, -10.0))
+
+    class Keep:                                   # a locator that keeps the incoming cell: only the bookkeeping is tested
+        def particle_cells(self, xyz, guess):
+            return np.asarray(guess, np.int32).copy()
+
+    n = 4000
+    pos = rng.normal(size=(n, 3)); vel = rng.normal(size=(n, 3))
+    cells = rng.integers(-1, 50, size=n).astype(np.int32)                # about 2 % carry cell == -1
+    p_ref, v_ref, c_ref, lost_ref = r.clear_lost(pos, vel, cells)
+    box = (-1e9, 1e9, -1e9, 1e9, -1e9, 1e9)
+    p_o, v_o, c_o, lost_o = pic.update_positions(Keep(), pos, np.zeros_like(vel), cells, 1.0, box, True)   # zero velocity: pure clear_lost
+    assert lost_ref == lost_o == int((cells == -1).sum()) and lost_ref > 0
+    assert np.array_equal(c_ref, c_o) and np.array_equal(p_ref, p_o)
+    assert np.array_equal(v_ref, vel[cells != -1])                       # survivors keep their order
