@@ -402,7 +402,7 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
         int lanes = fb::choose_lanes(c);
         while (lanes >= 300) {                     // block-JDS SpMV: tables once per mesh, values once per assemble
             const bool sym = lanes >= 310;         // 310/311: symmetric layout (lower triangle only)
-            const int R = sym ? (lanes == 311 ? 256 : 512) : ((lanes == 301) ? 128 : ((lanes >= 302 && lanes <= 304) ? 512 : 256));
+            const int R = sym ? (lanes == 311 ? 256 : 512) : ((lanes == 301) ? 128 : ((lanes >= 302 && lanes <= 305) ? 512 : 256));
             if (!c->jds_ready || c->jds_R != R || c->jds_sym != sym) {
                 drop_graph(c);
                 // window capacity: shared memory holds the input window (and, symmetric layout, its accumulators)

@@ -679,7 +679,20 @@ __global__ void k_csr_to_jds(int n, int R, const int* __restrict__ rowptr, const
 // their entries of a diagonal with ONE 16-byte value load and ONE 4-byte window-position load.
 // CS: the matrix stream is read with ld.global.cs (evict-first) so that it does not push the input vector,
 // which the windows of neighbouring blocks re-read, out of L2 (option "spmv_kernel" 304).
-template <bool INIT, int R, bool CS>
+// evict-first loads as volatile asm: ptxas keeps them in program order, which pins the software pipeline of the main
+// loop (issue the next four diagonals, THEN consume the previous four) instead of leaving it to the scheduler's
+// heuristics -- an unrelated edit once sank the loads behind the consumes and cost 0.8 ms per launch
+__device__ __forceinline__ double2 ld_cs_v2(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ ushort2 ld_cs_us2(const ushort2* p) {
+    unsigned w;
+    asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(w) : "l"(p));
+    return make_ushort2((unsigned short) (w & 0xffffu), (unsigned short) (w >> 16));
+}
+template <bool INIT, int R, int CS>
 __global__ void __launch_bounds__(R / 2) k_spmv_jds(int n, int n_blocks, const int* __restrict__ jbase,
                                                     const unsigned short* __restrict__ perm, const unsigned short* __restrict__ rlen,
                                                     const int* __restrict__ jdp, const int* __restrict__ jd,
@@ -716,7 +729,9 @@ __global__ void __launch_bounds__(R / 2) k_spmv_jds(int n, int n_blocks, const i
         ushort2 ca[4], cb2[4];
 #define FB_ISSUE(JJ, V, C)                                                                     \
         _Pragma("unroll") for (int u = 0; u < 4; ++u)                                          \
-            if ((JJ) + u < len0) { const int o = s_jd[(JJ) + u]; V[u] = CS ? __ldcs(&vb[o]) : __ldcg(&vb[o]); C[u] = CS ? __ldcs(&cb[o]) : __ldcg(&cb[o]); }
+            if ((JJ) + u < len0) { const int o = s_jd[(JJ) + u];                                     \
+                if (CS == 2) { V[u] = ld_cs_v2(&vb[o]); C[u] = ld_cs_us2(&cb[o]); }                     \
+                else { V[u] = CS ? __ldcs(&vb[o]) : __ldcg(&vb[o]); C[u] = CS ? __ldcs(&cb[o]) : __ldcg(&cb[o]); } }
 #define FB_CONSUME(JJ, V, C)                                                                   \
         _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                        \
             if ((JJ) + u < len0) sum0 += V[u].x * s_x[C[u].x];                                 \
@@ -1276,15 +1291,24 @@ static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, 
         const int nb = c->jds_nb;
         const size_t smem = sizeof(double) * (size_t) c->win_cap + sizeof(int) * ((size_t) c->jds_maxlen + 2);
 #define FB_JDS(RR, OCC) do {                                                                                                        \
-        auto kern = k_spmv_jds<INIT, RR, false>;                                                                                           \
+        auto kern = k_spmv_jds<INIT, RR, 0>;                                                                                           \
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);                                        \
         const int occ = std::max(1, std::min((OCC), (int) (200 * 1024 / (smem + 1024))));                                           \
         const int g = std::min(nb, c->n_sm * occ);                                                                                  \
         kern<<<g, (RR) / 2, smem, c->stream>>>(c->n_dofs, nb, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_jdp.p, c->d_jds_jd.p, \
                                          c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin, c->d_rhs.p, c->d_dinv.p, \
                                          out, part, counter, c->d_cg.p, alpha, c->win_cap, c->jds_maxlen); } while (0)
+        if (lanes == 305) {            // evict-first matrix stream, loads pinned in program order (volatile asm)
+            auto kern = k_spmv_jds<INIT, 512, 2>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            const int occ = std::max(1, std::min(6, (int) (200 * 1024 / (smem + 1024))));
+            const int g = std::min(nb, c->n_sm * occ);
+            kern<<<g, 256, smem, c->stream>>>(c->n_dofs, nb, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_jdp.p, c->d_jds_jd.p,
+                                              c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin, c->d_rhs.p, c->d_dinv.p,
+                                              out, part, counter, c->d_cg.p, alpha, c->win_cap, c->jds_maxlen);
+        } else
         if (lanes == 304) {            // evict-first matrix stream
-            auto kern = k_spmv_jds<INIT, 512, true>;
+            auto kern = k_spmv_jds<INIT, 512, 1>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
             const int occ = std::max(1, std::min(6, (int) (200 * 1024 / (smem + 1024))));
             const int g = std::min(nb, c->n_sm * occ);

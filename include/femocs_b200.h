@@ -260,8 +260,8 @@ int fb_last_solve_stats(const fb_ctx* ctx, double* solve_ms, int* iterations, lo
  * vector-update kernels over the sampled (live) iterations */
 int fb_last_solve_profile(const fb_ctx* ctx, double* spmv_ms_avg, double* vector_ms_avg, int* n_samples);
 /* which SpMV kernel the last fb_poisson_solve ran (option "spmv_kernel" codes: -2 = single cooperative launch
- * k_cg_persistent, 2..32 = CSR lanes per row, 100.. = row-block streaming, 200.. = windowed streaming, 300..304 =
- * block-JDS (304, the default for HBM-sized systems: matrix stream read evict-first), 310/311 = symmetric block-JDS
+ * k_cg_persistent, 2..32 = CSR lanes per row, 100.. = row-block streaming, 200.. = windowed streaming, 300..305 =
+ * block-JDS (304, the default for HBM-sized systems: matrix stream read evict-first; 305: same with the load order pinned), 310/311 = symmetric block-JDS
  * storing the lower triangle only) */
 int fb_last_solve_kernel(const fb_ctx* ctx);
 /* the context's cudaStream_t (for callers that record their own events around fb_*_dev calls) */

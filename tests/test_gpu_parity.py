@@ -107,7 +107,7 @@ def test_solution_matches_oracle(name, fb, ctx, golden, oracles):
     assert s.solve(n_cg=5) == -5
 
 
-@pytest.mark.parametrize("kernel", [0, 100, 101, 102, 103, 200, 201, 202, 203, 204, 300, 301, 302, 303, 304, 310, 311, 2, 8, 32])
+@pytest.mark.parametrize("kernel", [0, 100, 101, 102, 103, 200, 201, 202, 203, 204, 300, 301, 302, 303, 304, 305, 310, 311, 2, 8, 32])
 def test_spmv_kernel_variants_agree(kernel, fb, golden, oracles):
     """every SpMV kernel of the multi-kernel CG (windowed / plain row-block streaming variants, lanes-per-row
     variants) gives the oracle's solution"""
