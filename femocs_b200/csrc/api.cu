@@ -191,6 +191,33 @@ int fb_plan_get(const fb_ctx* c, int* local2global, int* owner, int* send_off, i
     if (top_flag) { std::fill(top_flag, top_flag + c->n_cols, 0); for (int d : c->top_dofs) top_flag[d] = 1; }
     return FB_OK;
 }
+// host-only: the interpolator tables of fb_interp_initialize (bit-exact precompute of the reference's cell classes),
+// for CPU parity tests.  The plan context imports the COMPLETE mesh here (no partition): call on a fresh fb_plan_create.
+// Layouts: tet17 = {det0, d[4][4]} per tetrahedron, tri16 = {vert0, edge1, edge2, pvec, norm, maxd} per triangle,
+// hex24 = f0..f7 per hexahedron.
+int fb_plan_interp_tables(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex,
+                          const int* node_marker, const int* tet4, const int* tet_nbr4, const int* tet_marker, int n_tet,
+                          const int* tri3, const double* tri_norm3, int n_tri, const int* quad4, int n_quad,
+                          double* tet17, double* tet_cent3, int* tet_mark, double* hex24, double* tri16, double* tri_cent3,
+                          int* qtet10, int* qtri6) {
+    FB_REQUIRE(c, c->host_only, "fb_plan_interp_tables: not a plan context");
+    FB_REQUIRE(c, 4L * n_tet == n_hex, "fb_plan_interp_tables: expected 4 hexahedra per tetrahedron");
+    const int rc = fb_host_import_mesh(c, xyz, n_nodes, hex8, hex_marker, n_hex);
+    if (rc) return rc;
+    fb_interp_tables T;
+    fb_host_interp_tables(c, node_marker, tet4, tet_nbr4, tet_marker, n_tet, tri3, tri_norm3, n_tri, quad4, n_quad, T);
+    static_assert(sizeof(fb::TetRec) == 17 * 8 && sizeof(fb::TriRec) == 16 * 8 && sizeof(fb::HexRec) == 24 * 8, "record layouts");
+    if (tet17) memcpy(tet17, T.tet.data(), T.tet.size() * sizeof(fb::TetRec));
+    if (tet_cent3) std::copy(T.tet_cent.begin(), T.tet_cent.end(), tet_cent3);
+    if (tet_mark) std::copy(T.tet_mark.begin(), T.tet_mark.end(), tet_mark);
+    if (hex24) memcpy(hex24, T.hex.data(), T.hex.size() * sizeof(fb::HexRec));
+    if (tri16 && n_tri > 0) memcpy(tri16, T.tri.data(), T.tri.size() * sizeof(fb::TriRec));
+    if (tri_cent3 && n_tri > 0) std::copy(T.tri_cent.begin(), T.tri_cent.end(), tri_cent3);
+    if (qtet10) std::copy(T.qtet.begin(), T.qtet.end(), qtet10);
+    if (qtri6 && n_tri > 0) std::copy(T.qtri.begin(), T.qtri.end(), qtri6);
+    return FB_OK;
+}
+
 // host-only: the block-JDS tables of the HBM SpMV for the plan's sparsity (CPU tests of fb_host_jds_build)
 int fb_plan_jds(fb_ctx* c, int R, int max_window, int sym, long* sizes6) {
     FB_REQUIRE(c, c->host_only && c->mesh_ok, "fb_plan_jds: needs a plan context after fb_plan_phase2");

@@ -62,6 +62,8 @@ SIGNATURES = {
     "fb_last_solve_stats": (C.c_int, [vp, c_double_p, c_int_p, c_long_p]),
     "fb_last_solve_profile": (C.c_int, [vp, c_double_p, c_double_p, c_int_p]),
     "fb_last_solve_kernel": (C.c_int, [vp]),
+    "fb_plan_interp_tables": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_int,
+                                        vp, vp, vp, vp, vp, vp, vp, vp]),
     "fb_plan_jds": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
     "fb_plan_jds_get": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "fb_get_stream": (vp, [vp]),

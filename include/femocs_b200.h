@@ -89,6 +89,14 @@ int fb_plan_phase2(fb_ctx* plan, const double* bbox6_global);
 int fb_plan_sizes(const fb_ctx* plan, long* out8);
 int fb_plan_get(const fb_ctx* plan, int* local2global, int* owner, int* send_off, int* send_idx, int* recv_off, int* rowptr, int* col,
                 int* cells_dof, int* local_cell2global, int* copper_flag, int* top_flag);
+/* host-only: the tables fb_interp_initialize uploads (src/InterpolatorCells.cpp:523-629, 1205-1267, 1585-1637,
+ * 1151-1173, 1873-1895), computed for the complete mesh on a fresh plan context; CPU parity tests compare them bit
+ * for bit.  tet17 = {det0, d[4][4]}, tri16 = {vert0, edge1, edge2, pvec, norm, maxd}, hex24 = f0..f7. */
+int fb_plan_interp_tables(fb_ctx* plan, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex,
+                          const int* node_marker, const int* tet4, const int* tet_nbr4, const int* tet_marker, int n_tet,
+                          const int* tri3, const double* tri_norm3, int n_tri, const int* quad4, int n_quad,
+                          double* tet17, double* tet_cent3, int* tet_mark, double* hex24, double* tri16, double* tri_cent3,
+                          int* qtet10, int* qtri6);
 /* host-only: block-JDS tables (R rows per block; sym != 0: lower triangle only) of the plan's sparsity.
  * sizes6 = {blocks, stored slots incl. padding, window entries, longest row, largest window, diagonal offsets} */
 int fb_plan_jds(fb_ctx* plan, int R, int max_window, int sym, long* sizes6);

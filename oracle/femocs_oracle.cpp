@@ -1083,6 +1083,31 @@ void fo_interp_initialize(void* h, const int* node_marker, const int* tet4, cons
 
 // Interpolator.cpp:172-190 extract_solution(fem, smoothen): store_solution (:103-123),
 // store_elfield (:125-140), average_nodal_fields (:142-170)
+// the precomputed cell tables, flattened like the product's device records (tests compare them bit for bit):
+// tet17 = {det0, det1[4], det2[4], det3[4], det4[4]}, tri16 = {vert0, edge1, edge2, pvec, norm, max_distance}, hex24 = f0..f7
+void fo_get_tables(void* h, double* tet17, double* tet_cent3, int* tet_mark, double* hex24, double* tri16, double* tri_cent3,
+                   int* qtet10, int* qtri6) {
+    const Oracle& o = *(Oracle*) h;
+    for (int t = 0; t < o.n_tet; ++t) {
+        double* r = tet17 + 17 * (size_t) t;
+        r[0] = o.t_det0[t];
+        for (int k = 0; k < 4; ++k) { const V4& d = o.t_det[k][t]; r[1 + 4 * k] = d.x; r[2 + 4 * k] = d.y; r[3 + 4 * k] = d.z; r[4 + 4 * k] = d.w; }
+        tet_cent3[3 * t] = o.t_cent[t].x; tet_cent3[3 * t + 1] = o.t_cent[t].y; tet_cent3[3 * t + 2] = o.t_cent[t].z;
+        tet_mark[t] = o.t_mark[t];
+        for (int k = 0; k < 10; ++k) qtet10[10 * (size_t) t + k] = o.qtet[t][k];
+    }
+    for (int c = 0; c < o.n_hex; ++c)
+        for (int k = 0; k < 8; ++k) { const V3& f = o.h_f[k][c]; double* r = hex24 + 24 * (size_t) c + 3 * k; r[0] = f.x; r[1] = f.y; r[2] = f.z; }
+    for (int t = 0; t < o.n_tri; ++t) {
+        double* r = tri16 + 16 * (size_t) t;
+        const V3* v[5] = {&o.r_vert0[t], &o.r_edge1[t], &o.r_edge2[t], &o.r_pvec[t], &o.r_norm[t]};
+        for (int k = 0; k < 5; ++k) { r[3 * k] = v[k]->x; r[3 * k + 1] = v[k]->y; r[3 * k + 2] = v[k]->z; }
+        r[15] = o.r_maxd[t];
+        tri_cent3[3 * t] = o.r_cent[t].x; tri_cent3[3 * t + 1] = o.r_cent[t].y; tri_cent3[3 * t + 2] = o.r_cent[t].z;
+        for (int k = 0; k < 6; ++k) qtri6[6 * (size_t) t + k] = o.qtri[t][k];
+    }
+}
+
 void fo_extract_solution(void* h, int smoothen) {
     Oracle& o = *(Oracle*) h;
     for (int i = 0; i < o.n_nodes; ++i) {

@@ -165,6 +165,17 @@ class Oracle:
             len(m["tris"]), _i(m["quads"]).reshape(-1), _i(m["quad2hex"]).reshape(-1), len(m["quads"]),
             float(m["edgemax"][0]), _i(m["voro_off"]), _i(m["voro_list"]) if len(m["voro_list"]) else np.zeros(1, np.int32),
             len(m["voro_off"]) - 1)
+        self.n_tet, self.n_tri, self.n_hex = len(m["tets"]), len(m["tris"]), 4 * len(m["tets"])
+
+    def tables(self):
+        """precomputed cell tables in the product's record layouts (see fo_get_tables)"""
+        nt, nh, nr = self.n_tet, self.n_hex, self.n_tri
+        t = dict(tet=np.zeros((nt, 17)), tet_cent=np.zeros((nt, 3)), tet_mark=np.zeros(nt, np.int32), hex=np.zeros((nh, 24)),
+                 tri=np.zeros((max(nr, 1), 16)), tri_cent=np.zeros((max(nr, 1), 3)), qtet=np.zeros((nt, 10), np.int32),
+                 qtri=np.zeros((max(nr, 1), 6), np.int32))
+        self.L.fo_get_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+        self.L.fo_get_tables(self.h, *[t[k].ctypes.data_as(C.c_void_p) for k in ("tet", "tet_cent", "tet_mark", "hex", "tri", "tri_cent", "qtet", "qtri")])
+        return t
 
     def extract_solution(self, smoothen=False):
         self.L.fo_extract_solution(self.h, int(smoothen))
