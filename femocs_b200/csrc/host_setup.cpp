@@ -526,6 +526,7 @@ void fb_host_interp_tables(const fb_ctx* c, const int* node_marker, const int* t
                            const int* quad4, int n_quad, fb_interp_tables& T) {
     const int n_nodes = c->n_nodes, n_hex = c->n_hex;
     auto node = [&](int i) { return V{c->xyz[3 * (size_t) i], c->xyz[3 * (size_t) i + 1], c->xyz[3 * (size_t) i + 2]}; };
+    Laps laps("interp tables");
 
     // ---------------- tetrahedra (:523-629) ----------------
     T.tet.resize(n_tet); T.tet_cent.resize(3 * (size_t) n_tet); T.tet_mark.resize(n_tet);
@@ -582,6 +583,7 @@ void fb_host_interp_tables(const fb_ctx* c, const int* node_marker, const int* t
     T.tet_nbr.resize(T.tet_nbr_off[n_tet]);
     for (int t = 0; t < n_tet; ++t) std::copy(nbr[t].begin(), nbr[t].end(), T.tet_nbr.begin() + T.tet_nbr_off[t]);
 
+    laps.lap("tets");
     // ---------------- hexahedra (:1205-1267) ----------------
     T.hex.resize(n_hex);
 #pragma omp parallel for schedule(static)
@@ -601,6 +603,7 @@ void fb_host_interp_tables(const fb_ctx* c, const int* node_marker, const int* t
         for (int k = 0; k < 8; ++k) { T.hex[h].f[k][0] = f[k].x; T.hex[h].f[k][1] = f[k].y; T.hex[h].f[k][2] = f[k].z; }
     }
 
+    laps.lap("hexs");
     // ---------------- triangles (:1585-1637) ----------------
     T.tri.resize(n_tri); T.tri_cent.resize(3 * (size_t) n_tri);
     std::vector<std::vector<int>> n2r(n_nodes);
@@ -632,6 +635,7 @@ void fb_host_interp_tables(const fb_ctx* c, const int* node_marker, const int* t
     T.tri_nbr.resize(T.tri_nbr_off[n_tri]);
     for (int t = 0; t < n_tri; ++t) std::copy(rnbr[t].begin(), rnbr[t].end(), T.tri_nbr.begin() + T.tri_nbr_off[t]);
 
+    laps.lap("tris");
     // ---------------- quadratic cells (:1151-1173, :1873-1895) ----------------
     auto common = [](const int* a, int na, const int* b, int nb) {
         for (int i = 0; i < na; ++i) for (int j = 0; j < nb; ++j) if (a[i] == b[j]) return a[i];
@@ -666,6 +670,7 @@ void fb_host_interp_tables(const fb_ctx* c, const int* node_marker, const int* t
         q[3] = common(en[0], ne[0], en[1], ne[1]); q[4] = common(en[1], ne[1], en[2], ne[2]); q[5] = common(en[2], ne[2], en[0], ne[0]);
     }
 
+    laps.lap("quadratic");
     // ---------------- node -> (vacuum hex, local node) CSR (Interpolator.cpp:60-76) ----------------
     T.n2c_off.assign(n_nodes + 1, 0);
     for (int h = 0; h < n_hex; ++h)
