@@ -92,3 +92,26 @@ def test_pic_push_pieces_match_reference_code():
     assert lost_ref == lost_o == int((cells == -1).sum()) and lost_ref > 0
     assert np.array_equal(c_ref, c_o) and np.array_equal(p_ref, p_o)
     assert np.array_equal(v_ref, vel[cells != -1])                       # survivors keep their order
+
+
+def test_known_cell_interpolation_linhex_locate_and_nodal_gradients_match_reference_code():
+    """the remaining cell-class entry points of the compiled reference against the oracle, bit for bit:
+    interp_solution with given cells (SolutionReader.cpp:167-190), LinearHexahedra::locate_cell (:1536-1562),
+    LinearHexahedra::interp_gradient(hex, node) (:425-439, :1462-1505)"""
+    r = reflib.RefLib()
+    m = r.generate("mdsmall")
+    o = Oracle(); o.import_mesh(m["nodes"], m["hexs"], m["hex_markers"]); o.interp_initialize(m)
+    rng = np.random.default_rng(21)
+    sol5 = rng.normal(size=(len(m["nodes"]), 5))
+    r.set_nodal(sol5); o.set_nodal(sol5)
+    lo = m["nodes"].min(0); hi = m["nodes"].max(0)
+    pts = np.vstack([m["surf_atoms"][::3], rng.uniform(lo, hi, size=(800, 3))])
+    for dim in (2, 3):
+        for rank in (1, 2, 3):
+            cells, _ = r.locate_interpolate(dim, rank, pts)
+            assert np.array_equal(r.interp_known_cells(dim, rank, pts, cells), o.interpolate(dim, rank, pts, cells))
+    guess = rng.integers(0, len(m["hexs"]), size=len(pts)).astype(np.int32)
+    assert np.array_equal(r.linhex_locate(pts, guess), o.linhex_locate(pts, guess))
+    vac = np.flatnonzero(m["hex_markers"] > 0)
+    hexs = rng.choice(vac, size=3000).astype(np.int32); nodes = rng.integers(0, 8, size=3000).astype(np.int32)
+    assert np.array_equal(r.nodal_gradient(hexs, nodes), o.nodal_gradient(hexs, nodes))
