@@ -109,3 +109,30 @@ def test_oracle_arithmetic_matches_an_independent_derivation(name, golden):
     assert o.solve(10000, 1e-12, 1.2, 0) > 0
     ref = o.export_solution()
     assert np.abs(ref - phi_d[v2n]).max() <= 1e-9 * np.abs(ref).max()
+
+
+def test_space_charge_rhs_from_reference_pinned_weights(golden):
+    """PoissonSolver::assemble_space_charge_fast (PoissonSolver.cpp:299-319) re-derived: the right-hand side gained by
+    adding particles = scatter of (shape function x charge factor) over the 8 vertices of each particle's cell, with the
+    shape functions taken from the oracle entry point that tests/test_oracle_vs_ref.py pins to the compiled reference;
+    constrained (Dirichlet) rows keep their boundary value"""
+    m = golden("mesh", "mdsmall"); g = golden("interp", "mdsmall")
+    o = Oracle(); o.import_mesh(m["nodes"], m["hexs"], m["hex_markers"]); o.interp_initialize(m)
+    ok = g["pic_ok"]
+    pts = g["points"][ok]; cells = g["pic_cells"][ok]
+    cf = -180.9512268 * 0.01
+    o.setup(0.5, 0.0, False); o.assemble(True)
+    rhs0 = o.vectors()[0].copy()
+    o.setup(0.5, 0.0, False); o.assemble(True, pts, cells, cf)
+    rhs1, _, v2d, _ = o.vectors()
+    w = o.particle_weights(pts, cells)              # shape_funs_dealii (InterpolatorCells.cpp:1355-1358): deal.II vertex order
+    dofs = v2d[o.cells()[cells]]                    # (n, 8) DoFs of each particle's cell, same (lexicographic) order
+    expect = np.zeros(o.n_dofs)
+    np.add.at(expect, dofs.reshape(-1), (w * cf).reshape(-1))
+    rp, col, val, save = o.csr()
+    constrained = np.array([rp[r + 1] - rp[r] >= 1 and np.count_nonzero(val[rp[r]:rp[r + 1]]) == 1 for r in range(o.n_dofs)])
+    free = ~constrained
+    assert free.sum() > 0.5 * o.n_dofs
+    scale = np.abs(expect).max()
+    assert np.abs((rhs1 - rhs0)[free] - expect[free]).max() <= 1e-12 * scale
+    assert np.array_equal(rhs1[constrained], rhs0[constrained])
