@@ -44,3 +44,33 @@ def test_b200_arm_refuses_to_run_without_a_gpu():
         pytest.skip("GPU present")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3"], capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_synthetic_pic_workload_is_consistent(golden):
+    """config 3 particles of bench.py: every electron lies in the solver cell it claims (checked with the oracle's
+    reference-pinned LinearHexahedra search), within 50 A + a cell of the apex, deterministic for a seed"""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle.oracle import Oracle
+    m = golden("mesh", "mdsmall")
+    pos, vel, cells = bench.pic_particles(m, 3000)
+    pos2, _, cells2 = bench.pic_particles(m, 3000)
+    assert np.array_equal(pos, pos2) and np.array_equal(cells, cells2)
+    o = Oracle(); o.import_mesh(m["nodes"], m["hexs"], m["hex_markers"]); o.interp_initialize(m)
+    assert np.array_equal(o.particle_cells(pos, cells), cells)
+    apex = m["surf_atoms"][np.argmax(m["surf_atoms"][:, 2])]
+    assert np.linalg.norm(pos - apex, axis=1).max() < 60.0
+    assert abs(vel.std() - 0.1) < 0.01
+
+
+def test_synthetic_x_particles_lie_in_their_cells():
+    """config 4 electrons of bench.py (trilinear images of natural coordinates): inside the hexahedron they name"""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from femocs_b200 import synth
+    nodes, hexs, mk = bench.load_x_mesh(0)
+    pxyz, pcell = bench.synth_particles(nodes, hexs, 2000)
+    lo = nodes[hexs[pcell]].min(1); hi = nodes[hexs[pcell]].max(1)
+    assert np.all(pxyz >= lo - 1e-9) and np.all(pxyz <= hi + 1e-9) and pcell.min() >= 0 and pcell.max() < len(hexs)
