@@ -34,6 +34,8 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.fo_create.restype = C.c_void_p
         L.fo_destroy.argtypes = [C.c_void_p]
+        L.fo_set_num_threads.argtypes = [C.c_int]
+        L.fo_get_max_threads.restype = C.c_int
         L.fo_import_mesh.argtypes = [C.c_void_p, _dp, C.c_int, _ip, _ip, C.c_int]
         L.fo_setup.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int]
         L.fo_assemble.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_long, C.c_double]
