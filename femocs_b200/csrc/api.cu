@@ -165,6 +165,19 @@ int fb_plan_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, c
     for (int d = 0; d < 3; ++d) { bbox6[d] = c->bb_mn[d]; bbox6[3 + d] = c->bb_mx[d]; }
     return FB_OK;
 }
+// host-only: the UN-partitioned import of fb_import_mesh (vertex compaction, orientation, boundary ids, first-touch
+// numbering, sparsity) on a plan context; fb_plan_sizes / fb_plan_get / fb_plan_jds then describe the complete system
+int fb_plan_import(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {
+    FB_REQUIRE(c, c->host_only, "fb_plan_import: not a plan context");
+    const int rc = fb_host_import_mesh(c, xyz, n_nodes, hex8, hex_marker, n_hex);
+    if (rc) return rc;
+    c->n_vert_global = c->n_vert; c->n_cells_global = c->n_cells; c->n_dofs_global = c->n_dofs;
+    c->part_l2g.resize(c->n_vert); for (int v = 0; v < c->n_vert; ++v) c->part_l2g[v] = v;
+    c->part_owner.assign(c->n_vert, 0);
+    c->part_cell_g.resize(c->n_cells); for (int k = 0; k < c->n_cells; ++k) c->part_cell_g[k] = k;
+    c->send_off.assign(c->world + 1, 0); c->recv_off.assign(c->world + 1, 0); c->send_idx.clear();
+    return FB_OK;
+}
 int fb_plan_phase2(fb_ctx* c, const double* bbox6_global) {
     FB_REQUIRE(c, c->host_only, "fb_plan_phase2: not a plan context");
     for (int d = 0; d < 3; ++d) { c->bb_mn[d] = bbox6_global[d]; c->bb_mx[d] = bbox6_global[3 + d]; }
@@ -253,13 +266,19 @@ int fb_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, c
     if (c->world > 1) {
         // partitioned import: local sub-mesh, extremes of the boundary-face centres reduced over the ranks
         FB_REQUIRE(c, c->nccl_comm, "fb_import_mesh: fb_comm_init has not been called");
-        if ((rc = fb_host_partition_phase1(c, xyz, n_nodes, hex8, hex_marker, n_hex))) return rc;
-        double* hb = (double*) c->pin_out.p;                 // [max(mx), max(-mn)]
-        for (int d = 0; d < 3; ++d) { hb[d] = c->bb_mx[d]; hb[3 + d] = -c->bb_mn[d]; }
-        FB_CUDA(c, cudaMemcpyAsync(c->d_red.p, hb, 6 * sizeof(double), cudaMemcpyHostToDevice, s));
-        if ((rc = allreduce(c, c->d_red.p, 6, ncclMax))) return rc;
-        FB_CUDA(c, cudaMemcpyAsync(hb, c->d_red.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        // a rank-local failure (e.g. "rank owns no vertices") must not leave the other ranks waiting in the collective:
+        // the error flag travels with the extremes and every rank leaves with the same verdict
+        const int rc_local = fb_host_partition_phase1(c, xyz, n_nodes, hex8, hex_marker, n_hex);
+        const std::string err_local = c->err;
+        double* hb = (double*) c->pin_out.p;                 // [max(mx), max(-mn), failed]
+        for (int d = 0; d < 3; ++d) { hb[d] = rc_local ? -1e300 : c->bb_mx[d]; hb[3 + d] = rc_local ? -1e300 : -c->bb_mn[d]; }
+        hb[6] = rc_local ? 1.0 : 0.0;
+        FB_CUDA(c, cudaMemcpyAsync(c->d_red.p, hb, 7 * sizeof(double), cudaMemcpyHostToDevice, s));
+        if ((rc = allreduce(c, c->d_red.p, 7, ncclMax))) return rc;
+        FB_CUDA(c, cudaMemcpyAsync(hb, c->d_red.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
         FB_CUDA(c, cudaStreamSynchronize(s));
+        if (hb[6] != 0.0)
+            return rc_local ? c->fail(rc_local, "%s", err_local.c_str()) : c->fail(FB_ERR_MESH, "fb_import_mesh: the mesh import failed on another rank");
         for (int d = 0; d < 3; ++d) { c->bb_mx[d] = hb[d]; c->bb_mn[d] = -hb[3 + d]; }
         if ((rc = fb_host_import_phase2(c))) return rc;
     } else {
@@ -287,7 +306,18 @@ int fb_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, c
     FB_CUDA(c, c->d_vertex2dof.upload(c->vertex2dof, s));
     FB_CUDA(c, c->d_cell2hex.upload(c->cell2hex, s));
     FB_CUDA(c, c->d_hex2cell.upload(c->hex2cell, s));
-    FB_CUDA(c, c->d_val.alloc(c->nnz)); FB_CUDA(c, c->d_val_save.alloc(c->nnz));
+    {   // Dirichlet candidates (copper, then top) and the number of owned constrained rows in either anode mode
+        std::vector<int> all(c->copper_dofs);
+        all.insert(all.end(), c->top_dofs.begin(), c->top_dofs.end());
+        if (all.empty()) all.push_back(0);
+        FB_CUDA(c, c->d_bc_dofs.upload(all, s));
+        std::vector<unsigned char> mark(c->n_cols, 0);
+        for (int d : c->copper_dofs) mark[d] = 1;
+        c->n_dirichlet_cu = (int) std::count(mark.begin(), mark.begin() + c->n_dofs, (unsigned char) 1);
+        for (int d : c->top_dofs) mark[d] = 1;
+        c->n_dirichlet_cu_top = (int) std::count(mark.begin(), mark.begin() + c->n_dofs, (unsigned char) 1);
+    }
+    FB_CUDA(c, c->d_val_save.alloc(c->nnz));
     FB_CUDA(c, c->d_diagpos.alloc(n));
     for (fb::DevBuf<double>* b : {&c->d_rhs, &c->d_x, &c->d_g, &c->d_d, &c->d_h, &c->d_dinv, &c->d_z, &c->d_w, &c->d_bcval})
         FB_CUDA(c, b->alloc(n));
@@ -325,24 +355,17 @@ static int assemble_impl(fb_ctx* c, int first_time, const double* d_pxyz, const 
     cudaStream_t s = c->stream;
     const int n = c->n_dofs;
     if (first_time || !c->matrix_ok) {
-        // stiffness matrix -> val_save (the reference's system_matrix_save)
+        // stiffness matrix -> val_save (the reference's system_matrix_save).  It is never modified afterwards: the
+        // Dirichlet conditions are a mask (k_bc_prepare), so a later assemble(false) has no matrix work at all
+        // (the reference copies the saved matrix back and eliminates again, PoissonSolver.cpp:157-159,178-192).
         FB_CUDA(c, cudaMemsetAsync(c->d_val_save.p, 0, c->nnz * sizeof(double), s));
-        fb::launch_assemble_stiffness(c, nullptr);
+        fb::launch_assemble_stiffness(c);
         // boundary values: copper = 0 (+ anode = V0 in Dirichlet mode); map semantics: later wins
         FB_CUDA(c, cudaMemsetAsync(c->d_bcflag.p, 0, c->n_cols * sizeof(int), s));
         FB_CUDA(c, cudaMemsetAsync(c->d_bcval.p, 0, c->n_cols * sizeof(double), s));
-        fb::DevBuf<int> tmp;
-        std::vector<int> all(c->copper_dofs);
-        all.insert(all.end(), c->top_dofs.begin(), c->top_dofs.end());
-        FB_CUDA(c, tmp.upload(all, s));
-        fb::launch_set_bc(c, tmp.p, (int) c->copper_dofs.size(), 0.0);
-        std::vector<unsigned char> mark(c->n_cols, 0);
-        for (int d : c->copper_dofs) mark[d] = 1;
-        if (c->anode_dirichlet) {
-            fb::launch_set_bc(c, tmp.p + c->copper_dofs.size(), (int) c->top_dofs.size(), c->applied_potential);
-            for (int d : c->top_dofs) mark[d] = 1;
-        }
-        c->n_dirichlet = (int) std::count(mark.begin(), mark.begin() + n, (unsigned char) 1);
+        fb::launch_set_bc(c, c->d_bc_dofs.p, (int) c->copper_dofs.size(), 0.0);
+        if (c->anode_dirichlet) fb::launch_set_bc(c, c->d_bc_dofs.p + c->copper_dofs.size(), (int) c->top_dofs.size(), c->applied_potential);
+        c->n_dirichlet = c->anode_dirichlet ? c->n_dirichlet_cu_top : c->n_dirichlet_cu;
         if (c->world > 1) {
             // a ghost dof may be constrained through a face this rank does not hold: take flag and value from the owner
             fb::launch_flags_to_double(c, c->d_z.p);
@@ -351,19 +374,18 @@ static int assemble_impl(fb_ctx* c, int first_time, const double* d_pxyz, const 
             fb::launch_double_to_ghost_flags(c, c->d_z.p);
             if ((rc = halo_exchange(c, c->d_bcval.p))) return rc;
         }
-        fb::launch_apply_bc_matrix(c);      // val, Dirichlet lift (kept in d_w), dinv, diagpos
+        fb::launch_bc_prepare(c);           // dinv (0 on constrained rows), diagpos
         c->jds_val_dirty = true;
         c->cheb_lmax = 0;                   // Gershgorin bound of the new matrix is computed by the next Chebyshev solve
-        FB_CUDA(c, cudaStreamSynchronize(s));   // tmp goes out of scope
         c->matrix_ok = true;
     }
-    // right-hand side: Neumann faces (or nothing), space charge, then Dirichlet lift
+    // right-hand side: Neumann faces (or nothing), space charge; constrained dofs take their value in the solution
     FB_CUDA(c, cudaMemsetAsync(c->d_rhs.p, 0, n * sizeof(double), s));
     if (!c->anode_dirichlet) fb::launch_neumann(c);
     if (n_parts > 0) {
         fb::launch_space_charge(c, n_parts, d_pxyz, d_pcell, charge_factor);
     }
-    fb::launch_apply_bc_rhs(c);
+    fb::launch_bc_solution(c);          // (partitioned: the solve exchanges the halo of x before the initial residual)
     c->assembled = true;
     return FB_OK;
 }
@@ -427,6 +449,7 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
         }
     } else {
         int lanes = fb::choose_lanes(c);
+        if (cheb && lanes >= 310) lanes = 304;      // the Chebyshev steps multiply by the FULL matrix: the symmetric (lower-triangle) layout cannot serve them
         while (lanes >= 300) {                     // block-JDS SpMV: tables once per mesh, values once per assemble
             const bool sym = lanes >= 310;         // 310/311: symmetric layout (lower triangle only)
             const int R = sym ? (lanes == 311 ? 256 : 512) : ((lanes == 301) ? 128 : ((lanes >= 302 && lanes <= 305) ? 512 : 256));
@@ -687,13 +710,9 @@ int fb_check_limits(fb_ctx* c, double lo, double hi, int* bad, double* mn, doubl
 int fb_get_cell_volumes(fb_ctx* c, double* vol) {
     FB_REQUIRE(c, c->mesh_ok && vol, "fb_get_cell_volumes: no mesh");
     cudaSetDevice(c->device);
-    // volumes come out of the assembly kernel (sum of JxW); run it into a scratch matrix
-    fb::DevBuf<double> v, scratch;
-    FB_CUDA(c, v.alloc(c->n_cells)); FB_CUDA(c, scratch.alloc(c->nnz));
-    double* keep = c->d_val_save.p;
-    c->d_val_save.p = scratch.p;
-    fb::launch_assemble_stiffness(c, v.p);
-    c->d_val_save.p = keep;
+    fb::DevBuf<double> v;
+    FB_CUDA(c, v.alloc(c->n_cells));
+    fb::launch_cell_volumes(c, v.p);
     FB_CUDA(c, cudaMemcpyAsync(vol, v.p, c->n_cells * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     return sync_check(c, "fb_get_cell_volumes");
 }
@@ -707,9 +726,20 @@ int fb_get_system(fb_ctx* c, int* rowptr, int* col, double* val, double* val_sav
     if (vertex2dof) std::copy(c->vertex2dof.begin(), c->vertex2dof.end(), vertex2dof);
     if (vertex2node) std::copy(c->vert2node.begin(), c->vert2node.end(), vertex2node);
     cudaStream_t s = c->stream;
-    if (val) FB_CUDA(c, cudaMemcpyAsync(val, c->d_val.p, c->nnz * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (val_save) FB_CUDA(c, cudaMemcpyAsync(val_save, c->d_val_save.p, c->nnz * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (rhs) FB_CUDA(c, cudaMemcpyAsync(rhs, c->d_rhs.p, c->n_dofs * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (val || rhs) {
+        // the solver keeps K and the raw right-hand side and applies the Dirichlet conditions as a mask; the ELIMINATED
+        // matrix and the lifted right-hand side of the reference (MatrixTools::apply_boundary_values) are produced here,
+        // on demand, for the tests that compare them with the oracle
+        FB_REQUIRE(c, c->assembled, "fb_get_system: val / rhs need an assembled system");
+        fb::DevBuf<double> tv, tr, tl, td; fb::DevBuf<int> tp;
+        FB_CUDA(c, tv.alloc(c->nnz)); FB_CUDA(c, tr.alloc(c->n_dofs)); FB_CUDA(c, tl.alloc(c->n_dofs)); FB_CUDA(c, td.alloc(c->n_dofs));
+        FB_CUDA(c, tp.alloc(c->n_dofs));
+        fb::launch_materialize_eliminated(c, tv.p, tr.p, tl.p, td.p, tp.p);
+        if (val) FB_CUDA(c, cudaMemcpyAsync(val, tv.p, c->nnz * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (rhs) FB_CUDA(c, cudaMemcpyAsync(rhs, tr.p, c->n_dofs * sizeof(double), cudaMemcpyDeviceToHost, s));
+        FB_CUDA(c, cudaStreamSynchronize(s));
+    }
     if (sol) FB_CUDA(c, cudaMemcpyAsync(sol, c->d_x.p, c->n_dofs * sizeof(double), cudaMemcpyDeviceToHost, s));
     return sync_check(c, "fb_get_system");
 }

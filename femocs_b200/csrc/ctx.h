@@ -138,7 +138,9 @@ struct fb_ctx {
     fb::DevBuf<int> d_rowptr, d_col, d_diagpos, d_rowblk, d_win_off, d_win_list;
     fb::DevBuf<unsigned short> d_col16, d_jds_perm, d_jds_len, d_jds_slot;
     fb::DevBuf<int> d_jds_jdp, d_jds_jd, d_jds_base; fb::DevBuf<double> d_val_jds, d_diag;
-    fb::DevBuf<double> d_val, d_val_save;
+    fb::DevBuf<double> d_val_save;           // K before boundary conditions (the reference's system_matrix_save); never rewritten between assemblies
+    fb::DevBuf<int> d_bc_dofs;               // Dirichlet candidates: copper dofs, then top dofs (uploaded once per mesh)
+    int n_dirichlet_cu = 0, n_dirichlet_cu_top = 0;      // owned constrained rows: copper only / copper + top
     fb::DevBuf<double> d_rhs, d_x, d_g, d_d, d_h, d_dinv, d_z, d_w;
     fb::DevBuf<int> d_topfaces;              // 4 dof ids per top (Neumann) face
     fb::DevBuf<int> d_bcflag; fb::DevBuf<double> d_bcval;

@@ -128,9 +128,11 @@ int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* 
         if (hex_volume(v) < 0) ++n_neg;
     }
     if (n_neg == n_cells) {
+        // deal.II 9.2 swaps vertices i <-> i + 4 of the OLD-STYLE (UCD) numbering the cells arrive in; through
+        // UCD_TO_LEX these are the lexicographic pairs (0,2) (1,3) (4,6) (5,7)
 #pragma omp parallel for schedule(static)
         for (int ce = 0; ce < n_cells; ++ce)
-            for (int k = 0; k < 4; ++k) std::swap(cv[8 * (size_t) ce + k], cv[8 * (size_t) ce + k + 4]);
+            for (int k : {0, 1, 4, 5}) std::swap(cv[8 * (size_t) ce + k], cv[8 * (size_t) ce + k + 2]);
     } else if (n_neg > 0) {
         return c->fail(FB_ERR_MESH, "%ld of %d hexahedra have negative volume", n_neg, n_cells);
     }

@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(128) k_smooth(int n_voro, const int* __restric
 }
 
 // ---- PIC particles --------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_particle_cells(Tables T, long n, const double* __restrict__ pts, const int* __restrict__ cell2hex,
+__global__ void __launch_bounds__(128) k_particle_cells(Tables T, long n, const double* __restrict__ pts, const int* __restrict__ cell2hex, int n_cells,
                                                         const int* __restrict__ hex2cell, int* __restrict__ cell_inout,
                                                         int* __restrict__ needy_count, int* __restrict__ needy_idx, int lost_marker) {
     const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
@@ -664,7 +664,9 @@ __global__ void __launch_bounds__(128) k_particle_cells(Tables T, long n, const 
     const P3 p = ldp(pts, i);
     const int c = cell_inout[i];
     if (c == lost_marker) { cell_inout[i] = -1; return; }     // left the simulation box in k_pic_move: no search (Pic.cpp:177-180)
-    const int guess = c < 0 ? 0 : cell2hex[c];
+    // a stale cell id from before a re-mesh (Pic.cpp:188-191 anticipates it; deal2femocs answers -2 past the end of its
+    // map, InterpolatorCells.h:437-448) is no guess at all: start from cell 0 like a negative one
+    const int guess = (c < 0 || c >= n_cells) ? 0 : cell2hex[c];
     int tet;
     // hex_locate (:1536-1562): tetrahedron from the guess / its neighbours; particles that left the neighbourhood
     // are deferred to the block-cooperative scan of k_particle_scanned
@@ -688,11 +690,13 @@ __global__ void __launch_bounds__(256) k_particle_scanned(Tables T, const double
     }
 }
 
-__global__ void __launch_bounds__(128) k_particle_field(Tables T, long n, const double* __restrict__ pts, const int* __restrict__ cell2hex,
+__global__ void __launch_bounds__(128) k_particle_field(Tables T, long n, const double* __restrict__ pts, const int* __restrict__ cell2hex, int n_cells,
                                                         const int* __restrict__ cells, double* __restrict__ E3) {
     const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const P3 E = hex_point_gradient(T, ldp(pts, i), cell2hex[cells[i]]);
+    const int c = cells[i];
+    if (c < 0 || c >= n_cells) { E3[3 * i] = 0.0; E3[3 * i + 1] = 0.0; E3[3 * i + 2] = 0.0; return; }      // no cell, no field (never out of bounds)
+    const P3 E = hex_point_gradient(T, ldp(pts, i), cell2hex[c]);
     E3[3 * i] = E.x; E3[3 * i + 1] = E.y; E3[3 * i + 2] = E.z;
 }
 
@@ -723,11 +727,13 @@ __global__ void __launch_bounds__(256) k_pic_move(long n, double* __restrict__ p
 }
 
 // Pic<3>::update_velocities (src/Pic.cpp:198-209): vel += interp_gradient(pos, deal2femocs(cell)) * (dt q/m)
-__global__ void __launch_bounds__(128) k_pic_velocities(Tables T, long n, const double* __restrict__ pts, const int* __restrict__ cell2hex,
+__global__ void __launch_bounds__(128) k_pic_velocities(Tables T, long n, const double* __restrict__ pts, const int* __restrict__ cell2hex, int n_cells,
                                                         const int* __restrict__ cells, double* __restrict__ vel, double dt_q_over_m) {
     const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const P3 E = hex_point_gradient(T, ldp(pts, i), cell2hex[cells[i]]);
+    const int c = cells[i];
+    if (c < 0 || c >= n_cells) return;          // a particle without a valid cell is not accelerated (never out of bounds)
+    const P3 E = hex_point_gradient(T, ldp(pts, i), cell2hex[c]);
     vel[3 * i] += E.x * dt_q_over_m; vel[3 * i + 1] += E.y * dt_q_over_m; vel[3 * i + 2] += E.z * dt_q_over_m;
 }
 
@@ -940,7 +946,7 @@ void launch_particle_cells(fb_ctx* c, long n, const double* d_pts, int* d_cells,
     const Tables T = make_tables(c);
     c->d_needy.alloc((size_t) n + 1);
     cudaMemsetAsync(c->d_needy.p, 0, sizeof(int), c->stream);
-    k_particle_cells<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(T, n, d_pts, c->d_cell2hex.p, c->d_hex2cell.p, d_cells,
+    k_particle_cells<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(T, n, d_pts, c->d_cell2hex.p, c->n_cells, c->d_hex2cell.p, d_cells,
                                                                          c->d_needy.p, c->d_needy.p + 1, after_move ? FB_PIC_LOST : (int) 0x80000000);
     k_particle_scanned<<<(unsigned) std::min<long>(n, 8L * c->n_sm), 256, 0, c->stream>>>(T, d_pts, c->d_hex2cell.p, c->d_needy.p, c->d_needy.p + 1, d_cells);
     c->launches += 2;
@@ -948,7 +954,7 @@ void launch_particle_cells(fb_ctx* c, long n, const double* d_pts, int* d_cells,
 
 void launch_particle_field(fb_ctx* c, long n, const double* d_pts, const int* d_cells, double* d_E) {
     const Tables T = make_tables(c);
-    k_particle_field<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(T, n, d_pts, c->d_cell2hex.p, d_cells, d_E);
+    k_particle_field<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(T, n, d_pts, c->d_cell2hex.p, c->n_cells, d_cells, d_E);
     c->launches++;
 }
 
@@ -959,7 +965,7 @@ void launch_pic_move(fb_ctx* c, long n, double* d_pos, const double* d_vel, int*
 
 void launch_pic_velocities(fb_ctx* c, long n, const double* d_pos, const int* d_cells, double* d_vel, double dt_q_over_m) {
     const Tables T = make_tables(c);
-    k_pic_velocities<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(T, n, d_pos, c->d_cell2hex.p, d_cells, d_vel, dt_q_over_m);
+    k_pic_velocities<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(T, n, d_pos, c->d_cell2hex.p, c->n_cells, d_cells, d_vel, dt_q_over_m);
     c->launches++;
 }
 

@@ -9,11 +9,13 @@ namespace fb {
 // poisson_kernels.cu
 int choose_lanes(const fb_ctx* c);
 void stream_block_shape(int kernel, int& chunk, int& maxrows);
-void launch_assemble_stiffness(fb_ctx* c, double* d_cell_vol);
+void launch_assemble_stiffness(fb_ctx* c);
+void launch_cell_volumes(fb_ctx* c, double* d_cell_vol);
 void launch_neumann(fb_ctx* c);
 void launch_set_bc(fb_ctx* c, const int* d_dofs, int n, double value);
-void launch_apply_bc_matrix(fb_ctx* c);
-void launch_apply_bc_rhs(fb_ctx* c);
+void launch_bc_prepare(fb_ctx* c);
+void launch_bc_solution(fb_ctx* c);
+void launch_materialize_eliminated(fb_ctx* c, double* d_val_out, double* d_rhs_out, double* d_lift, double* d_diag_inv, int* d_diagpos_tmp);
 void launch_csr_to_jds(fb_ctx* c);
 void launch_cg_init(fb_ctx* c, int lanes);
 void launch_cg_iteration(fb_ctx* c, int lanes);

@@ -127,38 +127,27 @@ __global__ void k_cg_scalars_update(CgScalars* cgs, double* beta_out) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Q1 stiffness assembly: one thread per hexahedron, 2x2x2 Gauss, MappingQ1.
+// Q1 stiffness assembly, 2x2x2 Gauss, MappingQ1:
 //   K_e(i,j) = sum_q JxW_q grad N_i(q) . grad N_j(q)       (PoissonSolver.cpp:249-255)
-// scattered into the CSR matrix with FP64 atomics (summation order across cells is not fixed:
-// ~1e-16 relative run-to-run variation, far below the 1e-8 parity bar).
+// Two phases per block of 128 hexahedra:
+//   A. one thread per hexahedron integrates the upper triangle of K_e in registers (FP64 pipe, no memory traffic
+//      beyond 8 indices + 24 coordinates) and parks it in shared memory;
+//   B. the block re-maps itself to 8 lanes per hexahedron: lane i owns ROW dof_i of the global matrix, walks that row's
+//      sorted column list ONCE (independent, sector-contiguous loads) and adds its 8 entries where the columns match.
+//      The 8 atomics of a lane land in one contiguous row segment.
+// (Round 1 had every thread do 64 binary searches of ~5 dependent loads each: 26.9 ms for 2.24e7 hexahedra, 0.09 of the
+// HBM roofline; the scatter, not the arithmetic, was the cost.)  Summation order across cells is not fixed (FP64
+// atomics): ~1e-16 relative run-to-run variation, far below the 1e-8 parity bar.
 // Algorithmic bytes per hex: 32 B connectivity + 192 B coordinates + 64 x 8 B adds.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ int find_col(const int* __restrict__ col, int lo, int hi, int c) {
-    while (lo < hi) {                       // columns are sorted within a row
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(&col[mid]) < c) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
+constexpr int ASM_BLOCK = 128;
+constexpr int ASM_STRIDE = 37;        // 36 upper-triangle entries + 1: odd stride in doubles = conflict-free per half-warp
 
-__global__ void __launch_bounds__(128) k_assemble_stiffness(int n_cells, int n_rows, const int* __restrict__ cells,
-                                                           const double* __restrict__ vxyz,
-                                                           const int* __restrict__ rowptr, const int* __restrict__ col,
-                                                           double* __restrict__ val, double* __restrict__ cell_vol) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_cells) return;
-    int dof[8];
-    double X[8], Y[8], Z[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        dof[i] = __ldg(&cells[8 * (size_t) c + i]);
-        X[i] = __ldg(&vxyz[3 * (size_t) dof[i]]); Y[i] = __ldg(&vxyz[3 * (size_t) dof[i] + 1]); Z[i] = __ldg(&vxyz[3 * (size_t) dof[i] + 2]);
-    }
-    double Ke[36];      // upper triangle, row-major: (i,j), j >= i
+__device__ __forceinline__ void hex_stiffness(const double (&X)[8], const double (&Y)[8], const double (&Z)[8], double (&Ke)[36], double& vol) {
 #pragma unroll
     for (int k = 0; k < 36; ++k) Ke[k] = 0;
     const double ga = 0.5 * (1.0 - 0.57735026918962576451), gb = 0.5 * (1.0 + 0.57735026918962576451);
-    double vol = 0;
+    vol = 0;
 #pragma unroll 1
     for (int q = 0; q < 8; ++q) {
         const double xi = (q & 1) ? gb : ga, eta = (q & 2) ? gb : ga, zeta = (q & 4) ? gb : ga;
@@ -202,21 +191,72 @@ __global__ void __launch_bounds__(128) k_assemble_stiffness(int n_cells, int n_r
 #pragma unroll
             for (int j = i; j < 8; ++j, ++k) Ke[k] += JxW * (G[i][0] * G[j][0] + G[i][1] * G[j][1] + G[i][2] * G[j][2]);
     }
-    if (cell_vol) cell_vol[c] = vol;
-    int k = 0;
+}
+
+// cell volumes alone (DealSolver::get_cell_vol, DealSolver.cpp:169-173 = sum of JxW)
+__global__ void __launch_bounds__(ASM_BLOCK) k_cell_volumes(int n_cells, const int* __restrict__ cells, const double* __restrict__ vxyz,
+                                                            double* __restrict__ cell_vol) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    double X[8], Y[8], Z[8], Ke[36], vol;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        // rows >= n_rows belong to another rank (ghost dofs of a partitioned mesh): that rank assembles them
-        const int ri = dof[i];
-        const bool own_i = ri < n_rows;
-        const int lo_i = own_i ? __ldg(&rowptr[ri]) : 0, hi_i = own_i ? __ldg(&rowptr[ri + 1]) : 0;
+        const int d = __ldg(&cells[8 * (size_t) c + i]);
+        X[i] = __ldg(&vxyz[3 * (size_t) d]); Y[i] = __ldg(&vxyz[3 * (size_t) d + 1]); Z[i] = __ldg(&vxyz[3 * (size_t) d + 2]);
+    }
+    hex_stiffness(X, Y, Z, Ke, vol);
+    cell_vol[c] = vol;
+}
+
+__global__ void __launch_bounds__(ASM_BLOCK) k_assemble_stiffness(int n_cells, int n_rows, const int* __restrict__ cells,
+                                                                 const double* __restrict__ vxyz,
+                                                                 const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                                 double* __restrict__ val) {
+    __shared__ double s_ke[ASM_BLOCK * ASM_STRIDE];
+    __shared__ int s_dof[ASM_BLOCK * 8];
+    const int tid = threadIdx.x;
+    const int c = blockIdx.x * ASM_BLOCK + tid;
+    // ---- phase A: element matrix of hexahedron c ----
+    if (c < n_cells) {
+        double X[8], Y[8], Z[8], Ke[36], vol;
 #pragma unroll
-        for (int j = i; j < 8; ++j, ++k) {
-            if (own_i) atomicAdd(&val[find_col(col, lo_i, hi_i, dof[j])], Ke[k]);
-            if (j != i) {
-                const int rj = dof[j];
-                if (rj < n_rows) atomicAdd(&val[find_col(col, __ldg(&rowptr[rj]), __ldg(&rowptr[rj + 1]), ri)], Ke[k]);
-            }
+        for (int i = 0; i < 8; ++i) {
+            const int d = __ldg(&cells[8 * (size_t) c + i]);
+            s_dof[8 * tid + i] = d;
+            X[i] = __ldg(&vxyz[3 * (size_t) d]); Y[i] = __ldg(&vxyz[3 * (size_t) d + 1]); Z[i] = __ldg(&vxyz[3 * (size_t) d + 2]);
+        }
+        hex_stiffness(X, Y, Z, Ke, vol);
+#pragma unroll
+        for (int k = 0; k < 36; ++k) s_ke[tid * ASM_STRIDE + k] = Ke[k];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_dof[8 * tid + i] = -1;
+    }
+    __syncthreads();
+    // ---- phase B: lane i of an 8-lane group adds row i of one element matrix to global row dof_i ----
+    const int lane = tid & 7, sub = tid >> 3;
+#pragma unroll 1
+    for (int pass = 0; pass < ASM_BLOCK / 16; ++pass) {
+        const int h = pass * 16 + sub;
+        int d[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = s_dof[8 * h + j];
+        const int r = d[lane];
+        // rows >= n_rows belong to another rank (ghost dofs of a partitioned mesh): that rank assembles them
+        if (r < 0 || r >= n_rows) continue;
+        double kv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int a = min(lane, j), b = max(lane, j);
+            kv[j] = s_ke[h * ASM_STRIDE + (a * 8 - (a * (a - 1)) / 2 + (b - a))];
+        }
+        const int lo = __ldg(&rowptr[r]), hi = __ldg(&rowptr[r + 1]);
+        int found = 0;
+        for (int k = lo; k < hi && found < 8; ++k) {
+            const int cc = __ldg(&col[k]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (cc == d[j]) { atomicAdd(&val[k], kv[j]); ++found; }
         }
     }
 }
@@ -296,14 +336,37 @@ __global__ void __launch_bounds__(256) k_apply_bc_matrix(int n, const int* __res
     }
 }
 
-// rhs finalisation: b_c = a_cc v_c on constrained rows, b_r -= lift_r elsewhere; x_c = v_c
-__global__ void k_apply_bc_rhs(int n, const int* __restrict__ flag, const double* __restrict__ bcval,
-                               const double* __restrict__ dinv, const double* __restrict__ lift,
-                               double* __restrict__ rhs, double* __restrict__ x) {
-    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
-        if (flag[i]) { rhs[i] = bcval[i] / dinv[i]; x[i] = bcval[i]; }
-        else rhs[i] -= lift[i];
+// rhs finalisation of the ELIMINATED system (test hook fb_get_system only): b_c = a_cc v_c on constrained rows,
+// b_r -= lift_r elsewhere
+__global__ void k_eliminated_rhs(int n, const int* __restrict__ flag, const double* __restrict__ bcval,
+                                 const double* __restrict__ diag_inv, const double* __restrict__ lift,
+                                 const double* __restrict__ rhs_raw, double* __restrict__ rhs_out) {
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x)
+        rhs_out[i] = flag[i] ? bcval[i] / diag_inv[i] : rhs_raw[i] - lift[i];
+}
+
+// Dirichlet conditions as a MASK on the immutable stiffness matrix K (the reference eliminates rows and columns of a
+// copy, DealSolver.cpp:437-440 / PoissonSolver.cpp:157-159; here K is never rewritten):
+//   dinv_r = 1 / K_rr on free rows and 0 on constrained rows.  The solver starts from x_c = v_c, so the initial residual
+//   g = K x - b of a free row already contains the lift sum_c K_rc v_c; every kernel that writes g forces g_c = 0 where
+//   dinv_c = 0, hence z_c = d_c = 0 for the whole solve, x_c stays v_c, and the products K_rc d_c vanish exactly: the
+//   iterates are those of the eliminated system (up to the summation order inside a row).
+// One thread per row: binary search of the diagonal (columns sorted), also kept as diagpos for the symmetric layout.
+__global__ void k_bc_prepare(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
+                             const int* __restrict__ flag, double* __restrict__ dinv, int* __restrict__ diagpos) {
+    for (long r = (long) blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long) gridDim.x * blockDim.x) {
+        int lo = rowptr[r], hi = rowptr[r + 1];
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[mid] < (int) r) lo = mid + 1; else hi = mid; }
+        diagpos[r] = lo;
+        dinv[r] = flag[r] ? 0.0 : 1.0 / val[lo];
     }
+}
+
+// x_c = v_c on constrained dofs (the right-hand side of a constrained row is never read)
+__global__ void k_bc_solution(int n, const int* __restrict__ flag, const double* __restrict__ bcval, double* __restrict__ rhs,
+                              double* __restrict__ x) {
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x)
+        if (flag[i]) { x[i] = bcval[i]; rhs[i] = 0.0; }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -335,8 +398,8 @@ __global__ void __launch_bounds__(256) k_spmv_dot(int n, const int* __restrict__
 #pragma unroll
         for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, LANES);
         if (lane == 0 && valid) {
-            if (INIT) {                      // g = A x - b ; accumulate g.(Dinv g) and g.g
-                const double g = s - rhs[r];
+            if (INIT) {                      // g = A x - b (0 on constrained rows: dinv = 0); accumulate g.(Dinv g) and g.g
+                const double g = dinv[r] != 0.0 ? s - rhs[r] : 0.0;
                 out[r] = g;
                 acc[0] += g * g * dinv[r];
                 acc[1] += g * g;
@@ -400,7 +463,7 @@ __global__ void __launch_bounds__(THREADS) k_spmv_stream(int n_blocks, const int
             for (int j = lo; j < hi; ++j) sum += s_prod[j];
             const int r = r0 + tid;
             if (INIT) {
-                const double g = sum - rhs[r];
+                const double g = dinv[r] != 0.0 ? sum - rhs[r] : 0.0;
                 out[r] = g;
                 acc[0] += g * g * dinv[r];
                 acc[1] += g * g;
@@ -439,7 +502,8 @@ __global__ void __launch_bounds__(256, 6) k_update(int n, const double* __restri
         const double2 dd = __ldg(&d2[i]), di = __ldg(&i2[i]), hh = h2[i];
         double2 xx = x2[i], gg = g2[i];
         xx.x += alpha * dd.x; xx.y += alpha * dd.y;
-        gg.x += alpha * hh.x; gg.y += alpha * hh.y;
+        // constrained rows (dinv = 0) keep g = 0: the rows of K are not eliminated, see k_bc_prepare
+        gg.x = di.x != 0.0 ? gg.x + alpha * hh.x : 0.0; gg.y = di.y != 0.0 ? gg.y + alpha * hh.y : 0.0;
         x2[i] = xx; g2[i] = gg;
         if (ZERO_H) h2[i] = make_double2(0.0, 0.0);   // the symmetric SpMV accumulates into h with reductions: hand it a zeroed vector
         if (CHEB) {                                   // first Chebyshev step: p = Dinv g / theta, z = p
@@ -452,7 +516,7 @@ __global__ void __launch_bounds__(256, 6) k_update(int n, const double* __restri
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const int i = n - 1;
         x[i] += alpha * d[i];
-        const double gi = g[i] + alpha * h[i];
+        const double gi = dinv[i] != 0.0 ? g[i] + alpha * h[i] : 0.0;
         g[i] = gi;
         if (ZERO_H) h[i] = 0.0;
         if (CHEB) { const double pp = dinv[i] * gi * inv_theta; cheb_p[i] = pp; cheb_z[i] = pp; }
@@ -498,11 +562,11 @@ __global__ void __launch_bounds__(256) k_gershgorin(int n, const int* __restrict
 // Power iteration on Dinv A for a sharper lmax than the Gershgorin bound: v <- Dinv A v (unnormalised: <= lmax^its
 // growth), Rayleigh quotient (v.Av) / (v.Dv) of the similar symmetric matrix D^-1/2 A D^-1/2 -- a lower bound that
 // converges from below, hence the safety factor applied by cheb_prepare.
-__global__ void k_power_init(int n, double* __restrict__ v) {
+__global__ void k_power_init(int n, const double* __restrict__ dinv, double* __restrict__ v) {
     for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
         unsigned x = (unsigned) i * 2654435761u + 12345u;          // deterministic pseudo-random start in [-0.5, 0.5)
         x ^= x >> 16; x *= 2246822519u; x ^= x >> 13;
-        v[i] = (double) x * (1.0 / 4294967296.0) - 0.5;
+        v[i] = dinv[i] != 0.0 ? (double) x * (1.0 / 4294967296.0) - 0.5 : 0.0;      // constrained dofs stay out of the iteration
     }
 }
 __global__ void __launch_bounds__(256) k_power_step(int n, const double* __restrict__ h, const double* __restrict__ dinv,
@@ -511,8 +575,7 @@ __global__ void __launch_bounds__(256) k_power_step(int n, const double* __restr
     double acc[2] = {0, 0};
     for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
         const double vi = v[i], hi = h[i], di = dinv[i];
-        acc[0] += vi * hi;
-        acc[1] += vi * vi / di;
+        if (di != 0.0) { acc[0] += vi * hi; acc[1] += vi * vi / di; }
         v[i] = di * hi;
     }
     double tot[2];
@@ -631,7 +694,7 @@ __global__ void __launch_bounds__(THREADS) k_spmv_window(int n_blocks, const int
             for (int j = lo; j < hi; ++j) sum += s_prod[j];
             const int r = r0 + tid;
             if (INIT) {
-                const double g = sum - rhs[r];
+                const double g = dinv[r] != 0.0 ? sum - rhs[r] : 0.0;
                 out[r] = g;
                 acc[0] += g * g * dinv[r];
                 acc[1] += g * g;
@@ -747,8 +810,8 @@ __global__ void __launch_bounds__(R / 2) k_spmv_jds(int n, int n_blocks, const i
 #undef FB_ISSUE
 #undef FB_CONSUME
         if (INIT) {
-            if (sl0 < n) { const double g = sum0 - rhs[row0]; out[row0] = g; acc[0] += g * g * dinv[row0]; acc[1] += g * g; }
-            if (sl1 < n) { const double g = sum1 - rhs[row1]; out[row1] = g; acc[0] += g * g * dinv[row1]; acc[1] += g * g; }
+            if (sl0 < n) { const double di = dinv[row0]; const double g = di != 0.0 ? sum0 - rhs[row0] : 0.0; out[row0] = g; acc[0] += g * g * di; acc[1] += g * g; }
+            if (sl1 < n) { const double di = dinv[row1]; const double g = di != 0.0 ? sum1 - rhs[row1] : 0.0; out[row1] = g; acc[0] += g * g * di; acc[1] += g * g; }
         } else {
             if (sl0 < n) { out[row0] = sum0; acc[0] += __ldg(&xin[row0]) * sum0; }
             if (sl1 < n) { out[row1] = sum1; acc[0] += __ldg(&xin[row1]) * sum1; }
@@ -844,8 +907,8 @@ __global__ void __launch_bounds__(R / 2) k_spmv_jdsp(int n, int n_blocks, const 
 #undef FB_ISSUE
 #undef FB_CONSUME
         if (INIT) {
-            if (sl0 < n) { const double g = sum0 - rhs[row0]; out[row0] = g; acc[0] += g * g * dinv[row0]; acc[1] += g * g; }
-            if (sl1 < n) { const double g = sum1 - rhs[row1]; out[row1] = g; acc[0] += g * g * dinv[row1]; acc[1] += g * g; }
+            if (sl0 < n) { const double di = dinv[row0]; const double g = di != 0.0 ? sum0 - rhs[row0] : 0.0; out[row0] = g; acc[0] += g * g * di; acc[1] += g * g; }
+            if (sl1 < n) { const double di = dinv[row1]; const double g = di != 0.0 ? sum1 - rhs[row1] : 0.0; out[row1] = g; acc[0] += g * g * di; acc[1] += g * g; }
         } else {
             if (sl0 < n) { out[row0] = sum0; acc[0] += __ldg(&xin[row0]) * sum0; }
             if (sl1 < n) { out[row1] = sum1; acc[0] += __ldg(&xin[row1]) * sum1; }
@@ -1102,7 +1165,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_cg_persistent(const int* __restr
     rowsums();
     double acc[2] = {0, 0}, tot[2];
     for (int r = tid; r < nr; r += THREADS) {
-        const double g = s_h[r] - rhs[r0 + r];
+        const double g = s_dinv[r] != 0.0 ? s_h[r] - rhs[r0 + r] : 0.0;      // constrained rows: see k_bc_prepare
         s_g[r] = g;
         __stcg(&z_g[r0 + r], __dmul_rn(s_dinv[r], g));
         acc[0] += g * g * s_dinv[r];
@@ -1131,7 +1194,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_cg_persistent(const int* __restr
         acc[0] = 0; acc[1] = 0;
         for (int r = tid; r < nr; r += THREADS) {
             s_x[r] += alpha * s_d[r];
-            const double g = s_g[r] + alpha * s_h[r];
+            const double g = s_dinv[r] != 0.0 ? s_g[r] + alpha * s_h[r] : 0.0;
             s_g[r] = g;
             __stcg(&z_g[r0 + r], __dmul_rn(s_dinv[r], g));
             acc[0] += g * g * s_dinv[r];
@@ -1226,10 +1289,14 @@ int choose_lanes(const fb_ctx* c) {
     return 2;
 }
 
-void launch_assemble_stiffness(fb_ctx* c, double* d_cell_vol) {
-    const int block = 128;
-    k_assemble_stiffness<<<(c->n_cells + block - 1) / block, block, 0, c->stream>>>(
-        c->n_cells, c->n_dofs, c->d_cells.p, c->d_vxyz.p, c->d_rowptr.p, c->d_col.p, c->d_val_save.p, d_cell_vol);
+void launch_assemble_stiffness(fb_ctx* c) {
+    k_assemble_stiffness<<<(c->n_cells + ASM_BLOCK - 1) / ASM_BLOCK, ASM_BLOCK, 0, c->stream>>>(
+        c->n_cells, c->n_dofs, c->d_cells.p, c->d_vxyz.p, c->d_rowptr.p, c->d_col.p, c->d_val_save.p);
+    c->launches++;
+}
+
+void launch_cell_volumes(fb_ctx* c, double* d_cell_vol) {
+    k_cell_volumes<<<(c->n_cells + ASM_BLOCK - 1) / ASM_BLOCK, ASM_BLOCK, 0, c->stream>>>(c->n_cells, c->d_cells.p, c->d_vxyz.p, d_cell_vol);
     c->launches++;
 }
 
@@ -1246,23 +1313,31 @@ void launch_set_bc(fb_ctx* c, const int* d_dofs, int n, double value) {
     c->launches++;
 }
 
-void launch_apply_bc_matrix(fb_ctx* c) {
-    const int g = grid_for(c, (long) c->n_dofs * 8, 256);
-    k_apply_bc_matrix<8><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_rowptr.p, c->d_col.p, c->d_val_save.p, c->d_val.p,
-                                                   c->d_bcflag.p, c->d_bcval.p, c->d_w.p, c->d_dinv.p, c->d_diagpos.p);
+void launch_bc_prepare(fb_ctx* c) {          // dinv (0 on constrained rows), diagpos
+    k_bc_prepare<<<grid_for(c, c->n_dofs, 256), 256, 0, c->stream>>>(c->n_dofs, c->d_rowptr.p, c->d_col.p, c->d_val_save.p, c->d_bcflag.p,
+                                                                     c->d_dinv.p, c->d_diagpos.p);
     c->launches++;
+}
+
+// test hook (fb_get_system): the system as the reference holds it after apply_boundary_values -- rows and columns of
+// the constrained dofs eliminated, right-hand side lifted.  Not used by the solver.
+void launch_materialize_eliminated(fb_ctx* c, double* d_val_out, double* d_rhs_out, double* d_lift, double* d_diag_inv, int* d_diagpos_tmp) {
+    const int g = grid_for(c, (long) c->n_dofs * 8, 256);
+    k_apply_bc_matrix<8><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_rowptr.p, c->d_col.p, c->d_val_save.p, d_val_out,
+                                                   c->d_bcflag.p, c->d_bcval.p, d_lift, d_diag_inv, d_diagpos_tmp);
+    k_eliminated_rhs<<<grid_for(c, c->n_dofs, 256), 256, 0, c->stream>>>(c->n_dofs, c->d_bcflag.p, c->d_bcval.p, d_diag_inv, d_lift, c->d_rhs.p, d_rhs_out);
+    c->launches += 2;
 }
 
 void launch_csr_to_jds(fb_ctx* c) {
     const int g = grid_for(c, (long) c->n_dofs * 8, 256);
     k_csr_to_jds<<<g, 256, 0, c->stream>>>(c->n_dofs, c->jds_R, c->d_rowptr.p, c->d_jds_slot.p, c->d_jds_base.p, c->d_jds_jdp.p, c->d_jds_jd.p,
-                                           c->d_val.p, c->d_val_jds.p, c->jds_sym ? c->d_diagpos.p : nullptr, c->d_diag.p);
+                                           c->d_val_save.p, c->d_val_jds.p, c->jds_sym ? c->d_diagpos.p : nullptr, c->d_diag.p);
     c->launches++;
 }
 
-void launch_apply_bc_rhs(fb_ctx* c) {
-    const int g = grid_for(c, c->n_dofs, 256);
-    k_apply_bc_rhs<<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_bcflag.p, c->d_bcval.p, c->d_dinv.p, c->d_w.p, c->d_rhs.p, c->d_x.p);
+void launch_bc_solution(fb_ctx* c) {
+    k_bc_solution<<<grid_for(c, c->n_dofs, 256), 256, 0, c->stream>>>(c->n_dofs, c->d_bcflag.p, c->d_bcval.p, c->d_rhs.p, c->d_x.p);
     c->launches++;
 }
 
@@ -1340,7 +1415,7 @@ static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, 
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);                                        \
         const int occ = std::max(1, std::min((OCC), (int) (220 * 1024 / (smem + 4 * ((T) + 1) + 1024))));                           \
         const int g = std::min(nb, c->n_sm * occ);                                                                                  \
-        kern<<<g, T, smem, c->stream>>>(nb, c->d_rowblk.p, c->d_rowptr.p, c->d_col16.p, c->d_val.p, c->d_win_off.p, c->d_win_list.p, \
+        kern<<<g, T, smem, c->stream>>>(nb, c->d_rowblk.p, c->d_rowptr.p, c->d_col16.p, c->d_val_save.p, c->d_win_off.p, c->d_win_list.p, \
                                         xin, c->d_rhs.p, c->d_dinv.p, out, part, counter, c->d_cg.p, alpha, c->win_cap); } while (0)
         switch (lanes) {
             case 201: FB_WINDOW(256, 16, 8); break;
@@ -1356,7 +1431,7 @@ static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, 
     if (lanes == 0 || lanes >= 100) {           // row-block streaming kernel (variants 100.. are tuning points)
         const int nb = c->n_rowblk;
 #define FB_STREAM(T, P, OCC) do { const int g = std::min(nb, c->n_sm * (OCC));                                                     \
-        k_spmv_stream<INIT, T, P><<<g, T, 0, c->stream>>>(nb, c->d_rowblk.p, c->d_rowptr.p, c->d_col.p, c->d_val.p, xin, c->d_rhs.p, \
+        k_spmv_stream<INIT, T, P><<<g, T, 0, c->stream>>>(nb, c->d_rowblk.p, c->d_rowptr.p, c->d_col.p, c->d_val_save.p, xin, c->d_rhs.p, \
                                                          c->d_dinv.p, out, part, counter, c->d_cg.p, alpha); } while (0)
         switch (lanes) {
             case 100: FB_STREAM(256, 4, 8); break;
@@ -1370,7 +1445,7 @@ static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, 
         return;
     }
     const int g = grid_for(c, (long) c->n_dofs * lanes, 256);
-#define FB_SPMV(L) k_spmv_dot<L, INIT><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_rowptr.p, c->d_col.p, c->d_val.p, xin, \
+#define FB_SPMV(L) k_spmv_dot<L, INIT><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_rowptr.p, c->d_col.p, c->d_val_save.p, xin, \
                                                               c->d_rhs.p, c->d_dinv.p, out, part, counter, c->d_cg.p, alpha)
     switch (lanes) {
         case 32: FB_SPMV(32); break;
@@ -1414,7 +1489,7 @@ cudaError_t cheb_prepare(fb_ctx* c, int lanes) {
     if (c->cheb_lmax <= 0) {
         unsigned long long* bits = (unsigned long long*) c->d_minmax.p;
         cudaMemsetAsync(bits, 0, sizeof(unsigned long long), c->stream);
-        k_gershgorin<<<grid_for(c, (long) c->n_dofs * 8, 256), 256, 0, c->stream>>>(c->n_dofs, c->d_rowptr.p, c->d_val.p, c->d_dinv.p, bits);
+        k_gershgorin<<<grid_for(c, (long) c->n_dofs * 8, 256), 256, 0, c->stream>>>(c->n_dofs, c->d_rowptr.p, c->d_val_save.p, c->d_dinv.p, bits);
         c->launches++;
         double lmax = 0;
         e = cudaMemcpyAsync(&lmax, bits, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
@@ -1426,7 +1501,7 @@ cudaError_t cheb_prepare(fb_ctx* c, int lanes) {
             unsigned* counter = (unsigned*) (c->d_partial.p + c->d_partial.n - 8);
             const int g = grid_for(c, c->n_dofs, 256);
             const int pl = (lanes >= 310) ? 304 : lanes;
-            k_power_init<<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_cheb_p.p);
+            k_power_init<<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_dinv.p, c->d_cheb_p.p);
             for (int i = 0; i < c->cheb_power_iters; ++i) {
                 spmv_dispatch<false>(c, pl, c->d_cheb_p.p, c->d_h.p, (double*) (c->d_cg.p + 1) + 3);
                 k_power_step<<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_h.p, c->d_dinv.p, c->d_cheb_p.p, c->d_partial.p, counter, c->d_minmax.p);
@@ -1512,7 +1587,7 @@ static cudaError_t launch_persistent_pt(fb_ctx* c, size_t smem) {
     auto kern = k_cg_persistent<512, PT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
-    const int* a0 = c->d_cta_row.p; const int* a1 = c->d_rowptr.p; const int* a2 = c->d_col.p; const double* a3 = c->d_val.p;
+    const int* a0 = c->d_cta_row.p; const int* a1 = c->d_rowptr.p; const int* a2 = c->d_col.p; const double* a3 = c->d_val_save.p;
     const double* a4 = c->d_rhs.p; const double* a5 = c->d_dinv.p; double* a6 = c->d_x.p; double* a7 = c->d_d.p;
     double* a8 = c->d_partial.p; int* a8b = c->d_pers_flags.p; CgScalars* a9 = c->d_cg.p; int a10 = c->pers_cap, a11 = c->pers_rmax;
     long long* a12 = c->cg_debug ? c->d_dbg.p : nullptr;

@@ -27,6 +27,7 @@ SIGNATURES = {
     "fb_plan_create": (vp, [C.c_int, C.c_int]),
     "fb_plan_phase1": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "fb_plan_phase2": (C.c_int, [vp, vp]),
+    "fb_plan_import": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int]),
     "fb_plan_sizes": (C.c_int, [vp, vp]),
     "fb_plan_get": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "fb_import_mesh": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int]),

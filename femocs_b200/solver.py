@@ -490,9 +490,18 @@ class PartitionPlan:
         self._check(self.L.fb_plan_phase1(self.h, _p(nodes), len(nodes), _p(hexs), _p(hex_markers), len(hexs), _p(bbox)))
         return bbox                      # local (min xyz, max xyz) of the boundary-face centres
 
+    def import_whole(self, nodes, hexs, hex_markers):
+        """the un-partitioned host import of fb_import_mesh (world 1): complete numbering and sparsity"""
+        nodes = _f(nodes); hexs = _i(hexs); hex_markers = _i(hex_markers)
+        self._check(self.L.fb_plan_import(self.h, _p(nodes), len(nodes), _p(hexs), _p(hex_markers), len(hexs)))
+        return self._collect()
+
     def phase2(self, bbox_global):
         b = _f(bbox_global)
         self._check(self.L.fb_plan_phase2(self.h, _p(b)))
+        return self._collect()
+
+    def _collect(self):
         sz = np.zeros(8, np.int64)
         self.L.fb_plan_sizes(self.h, _p(sz))
         (self.n_rows, self.n_cols, self.nnz, self.n_cells, self.n_send, self.n_ghost, self.n_vert_global, self.n_cells_global) = [int(v) for v in sz]

@@ -86,6 +86,9 @@ int fb_get_partition(const fb_ctx* ctx, long* out10);
 fb_ctx* fb_plan_create(int rank, int world);
 int fb_plan_phase1(fb_ctx* plan, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex, double* bbox6);
 int fb_plan_phase2(fb_ctx* plan, const double* bbox6_global);
+/* host-only, un-partitioned: everything fb_import_mesh does on the host (vertex compaction, orientation, boundary ids,
+ * first-touch DoF numbering, sparsity) on a plan context; fb_plan_sizes / fb_plan_get then describe the complete system */
+int fb_plan_import(fb_ctx* plan, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
 int fb_plan_sizes(const fb_ctx* plan, long* out8);
 int fb_plan_get(const fb_ctx* plan, int* local2global, int* owner, int* send_off, int* send_idx, int* recv_off, int* rowptr, int* col,
                 int* cells_dof, int* local_cell2global, int* copper_flag, int* top_flag);

@@ -227,7 +227,7 @@ int import_mesh(Oracle& o, const double* xyz, int n_nodes, const int* hex8, cons
     if (n_cells == 0) return 1;
 
     // GridReordering::invert_all_cells_of_negative_grid (DealSolver.cpp:198): if the cells have
-    // negative measure, swap vertex i <-> i+4.  Tethex guarantees positive measure
+    // negative measure, swap vertex i <-> i+4 of the old-style numbering.  Tethex guarantees positive measure
     // (Tethex.cpp:1565-1592), so this is expected to be a no-op; it is decided per grid.
     {
         int n_neg = 0;
@@ -236,8 +236,8 @@ int import_mesh(Oracle& o, const double* xyz, int n_nodes, const int* hex8, cons
             for (int q = 0; q < 8; ++q) { cell_geometry(o, c, q, JxW, g); vol += JxW; }
             if (vol < 0) ++n_neg;
         }
-        if (n_neg == n_cells)
-            for (auto& c : o.cells) for (int k = 0; k < 4; ++k) std::swap(c[k], c[k + 4]);
+        if (n_neg == n_cells)       // swap of UCD vertices i <-> i + 4 (deal.II 9.2 grid_reordering.cc) = lexicographic (0,2) (1,3) (4,6) (5,7)
+            for (auto& c : o.cells) for (int k : {0, 1, 4, 5}) std::swap(c[k], c[k + 2]);
         else if (n_neg > 0) return 2;   // deal.II would throw -> import_mesh returns false
     }
 

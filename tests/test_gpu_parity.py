@@ -483,3 +483,78 @@ def test_large_refined_mesh_properties(fb, golden):
     fine_on_coarse = phi1[inv[:n_coarse]]
     assert _rel(fine_on_coarse, coarse) < 0.05
     c.close()
+
+
+# ------------------------------------------------------------------------------------------
+# round 2: mask-based Dirichlet conditions, Chebyshev x SpMV variants, stale particle cells
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", [0, 8, 100, 200, 300, 304, 305, 310, 311])
+def test_chebyshev_with_every_spmv_layout(kernel, fb, golden, oracles):
+    """FB_PRECOND_CHEBYSHEV multiplies by the full matrix k - 1 times per iteration: with the symmetric (lower
+    triangle) layouts 310 / 311 selected the solver must switch to the full block-JDS layout, not multiply by L"""
+    m = golden("mesh", "mdsmall"); o = oracles["mdsmall"]
+    c = fb.Context(0)
+    c.set_option("cg_persistent", 0)
+    c.set_option("spmv_kernel", kernel)
+    c.set_option("cheb_degree", 3)
+    s = fb.PoissonSolver(c, fb.FieldConfig(cg_tolerance=1e-11, precond=fb.PRECOND_CHEBYSHEV))
+    s.import_mesh(m["nodes"], m["hexs"], m["hex_markers"])
+    s.setup(0.5, 0.0); s.assemble(True)
+    it = s.solve()
+    assert it > 0
+    if kernel >= 310:
+        assert s.solve_kernel() == 304
+    o.setup(0.5, 0.0, False); o.assemble(True); o.solve(10000, 1e-11, 1.2, 0)
+    assert _rel(s.export_solution(), o.export_solution()) < REL
+    # then Jacobi on the same context and layout (the symmetric kernel accumulates into h: it must start from zero)
+    s.conf.precond = fb.PRECOND_JACOBI
+    s.setup(0.5, 0.0); s.assemble(True)
+    assert s.solve() > it
+    assert _rel(s.export_solution(), o.export_solution()) < REL
+    c.close()
+
+
+def test_pic_step_does_no_matrix_work(fb, golden, oracles):
+    """assemble(false) (every PIC step but the first, ProjectRunaway.cpp:497) leaves the stiffness matrix and its
+    block-JDS copy alone: the Dirichlet conditions are a mask, not an elimination of a restored copy"""
+    m = golden("mesh", "mdsmall"); o = oracles["mdsmall"]
+    for persistent in (1, 0):
+        c = fb.Context(0)
+        c.set_option("cg_persistent", persistent)
+        if not persistent:
+            c.set_option("spmv_kernel", 304)
+        s = fb.PoissonSolver(c, fb.FieldConfig(cg_tolerance=1e-11))
+        s.import_mesh(m["nodes"], m["hexs"], m["hex_markers"])
+        s.setup(0.5, 0.0); s.assemble(True)
+        assert s.solve() > 0
+        n0 = c.kernel_launches
+        s.assemble(False)
+        assert c.kernel_launches - n0 == 2              # Neumann faces + constrained values; nothing per non-zero
+        n1 = c.kernel_launches
+        assert s.solve(cg_tolerance=1e-8) == 0          # warm start: initial residual only
+        assert c.kernel_launches - n1 <= 3
+        # a different applied field on the same matrix (assemble(false) after setup keeps K: reference restores its copy)
+        o.setup(0.5, 0.0, False); o.assemble(True); o.solve(10000, 1e-11, 1.2, 0)
+        assert _rel(s.export_solution(), o.export_solution()) < REL
+        g = s.get_system()                              # eliminated system materialised on demand
+        rp, col, val, save = o.csr()
+        assert np.abs(g["val"] - val).max() <= 1e-12 * np.abs(save).max()
+        assert np.abs(g["rhs"] - o.vectors()[0]).max() <= 1e-12 * np.abs(o.vectors()[0]).max()
+        c.close()
+
+
+def test_stale_particle_cells_are_not_dereferenced(fb, golden, gpu_interp):
+    """cell ids left over from a larger mesh (Pic.cpp:188-191) are treated as 'no guess' by the search and give no
+    field / no acceleration -- never an out-of-bounds read of the cell maps"""
+    g = golden("interp", "hemicone")
+    c, s, it = gpu_interp["hemicone"]
+    it.set_solutions(hash_field(it.n_nodes, 5, 1))
+    pic = fb.Pic(it)
+    pts = g["points"]; n = len(pts)
+    stale = np.full(n, 2 ** 30, np.int32)
+    fresh = pic.update_point_cells(pts, np.zeros(n, np.int32))
+    assert np.array_equal(pic.update_point_cells(pts, stale), fresh)
+    E = pic.fields(pts[:50], stale[:50])
+    assert np.all(E == 0)
+    v = pic.update_velocities(pts[:50], np.ones((50, 3)), stale[:50], 0.5, -17.5882)
+    assert np.all(v == 1)

@@ -1,0 +1,41 @@
+"""Host-side mesh import (femocs_b200/csrc/host_setup.cpp through the host-only plan entry points) against the
+oracle and against itself on edge cases.  No GPU needed."""
+import numpy as np
+import pytest
+
+from femocs_b200 import PartitionPlan, synth
+from oracle.oracle import Oracle
+
+
+def _plan(nodes, hexs, mk):
+    return PartitionPlan(0, 1).import_whole(nodes, hexs, mk)
+
+
+def test_all_negative_mesh_is_flipped_like_deal_ii():
+    """GridReordering::invert_all_cells_of_negative_grid (DealSolver.cpp:198): every cell of a grid with negative
+    measure has its old-style vertices i and i + 4 swapped.  Swapping them in the INPUT of a positive mesh therefore
+    yields, after the import, exactly the cells of the positive mesh: same dofs per cell, same sparsity."""
+    nodes, hexs, mk = synth.box_mesh(4, 3, 5, 2.0, 1.5, 2.5, jitter=0.15)
+    neg = hexs.copy()
+    neg[:, :4], neg[:, 4:] = hexs[:, 4:], hexs[:, :4]
+    a = _plan(nodes, hexs, mk); b = _plan(nodes, neg, mk)
+    assert np.array_equal(a.cells_dof, b.cells_dof)
+    assert np.array_equal(a.rowptr, b.rowptr) and np.array_equal(a.col, b.col)
+    assert np.array_equal(a.copper, b.copper) and np.array_equal(a.top, b.top)
+    # the oracle restates the same rule
+    o1 = Oracle(); o1.import_mesh(nodes, hexs, mk)
+    o2 = Oracle(); o2.import_mesh(nodes, neg, mk)
+    assert np.array_equal(o1.cells(), o2.cells())
+    v2d = o1.vectors()[2]
+    assert np.array_equal(v2d[o1.cells()], a.cells_dof)
+
+
+def test_mixed_orientation_is_refused():
+    nodes, hexs, mk = synth.box_mesh(3, 3, 3)
+    bad = hexs.copy()
+    bad[0, :4], bad[0, 4:] = hexs[0, 4:], hexs[0, :4]
+    from femocs_b200 import FemocsB200Error
+    with pytest.raises(FemocsB200Error):
+        _plan(nodes, bad, mk)
+    with pytest.raises(RuntimeError):
+        Oracle().import_mesh(nodes, bad, mk)
