@@ -260,6 +260,7 @@ int fb_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, c
     FB_REQUIRE(c, xyz && hex8 && hex_marker && n_nodes > 0 && n_hex > 0, "fb_import_mesh: empty mesh");
     cudaSetDevice(c->device);
     c->setup_ok = c->assembled = c->matrix_ok = c->interp_ok = false;
+    c->n_mesh_faces = c->n_mesh_edges = -1; c->d_vert_lastcell.release();
     drop_graph(c);
     cudaStream_t s = c->stream;
     int rc;
@@ -678,6 +679,44 @@ int fb_export_charge_dens(fb_ctx* c, double* rho_vertex) {
     // (outside the hot path); otherwise it is reinit'ed to zeros, which is what export returns.
     FB_REQUIRE(c, c->mesh_ok && rho_vertex, "fb_export_charge_dens: no mesh");
     std::fill(rho_vertex, rho_vertex + c->n_vert, 0.0);
+    return FB_OK;
+}
+
+int fb_export_solution_grad(fb_ctx* c, double* grad3) {
+    FB_REQUIRE(c, c->mesh_ok && grad3, "fb_export_solution_grad: no mesh");
+    FB_REQUIRE(c, c->world == 1, "fb_export_solution_grad: un-partitioned meshes only");
+    cudaSetDevice(c->device);
+    if (c->d_vert_lastcell.n < (size_t) c->n_vert || c->d_vert_lastcell.p == nullptr) {
+        std::vector<int> lc;
+        fb_host_vertex_lastcell(c, lc);
+        FB_CUDA(c, c->d_vert_lastcell.upload(lc, c->stream));
+        FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    FB_CUDA(c, c->d_sol.alloc(3 * (size_t) c->n_vert));
+    fb::launch_solution_grad(c, c->d_sol.p);
+    FB_CUDA(c, cudaMemcpyAsync(grad3, c->d_sol.p, 3 * (size_t) c->n_vert * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return sync_check(c, "fb_export_solution_grad");
+}
+
+int fb_get_mesh_counts(fb_ctx* c, long* n_faces, long* n_edges) {
+    FB_REQUIRE(c, c->mesh_ok, "fb_get_mesh_counts: no mesh");
+    if (c->n_mesh_edges < 0) {
+        c->n_mesh_faces = (6L * c->n_cells + (long) c->bfaces.size()) / 2;      // every interior face is shared by two cells
+        c->n_mesh_edges = fb_host_count_edges(c);
+    }
+    if (n_faces) *n_faces = c->n_mesh_faces;
+    if (n_edges) *n_edges = c->n_mesh_edges;
+    return FB_OK;
+}
+
+int fb_get_solver_mesh(fb_ctx* c, double* xyz_vertex, int* cells_ucd8) {
+    FB_REQUIRE(c, c->mesh_ok, "fb_get_solver_mesh: no mesh");
+    if (xyz_vertex)
+        for (int v = 0; v < c->n_vert; ++v)
+            for (int d = 0; d < 3; ++d) xyz_vertex[3 * (size_t) v + d] = c->xyz[3 * (size_t) c->vert2node[v] + d];
+    if (cells_ucd8)
+        for (int ce = 0; ce < c->n_cells; ++ce)
+            for (int k = 0; k < 8; ++k) cells_ucd8[8 * (size_t) ce + k] = c->node2vert[c->hex8[8 * (size_t) c->cell2hex[ce] + k]];
     return FB_OK;
 }
 

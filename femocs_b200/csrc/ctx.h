@@ -147,6 +147,8 @@ struct fb_ctx {
     fb::DevBuf<double> d_partial;            // block partials for dot products
     fb::DevBuf<fb::CgScalars> d_cg;
     fb::DevBuf<int> d_vertex2dof;            // n_vert
+    fb::DevBuf<int> d_vert_lastcell;         // n_vert: 8 * vertex2cell + vertex2node (DealSolver.cpp:317-341), uploaded on first use
+    long n_mesh_faces = -1, n_mesh_edges = -1;   // counted on first use (fb_get_mesh_counts)
     fb::DevBuf<int> d_cell2hex, d_hex2cell;
     fb::DevBuf<double> d_minmax;
     // persistent cooperative CG (native meshes): row slice per CTA
@@ -200,6 +202,8 @@ struct fb_ctx {
     } while (0)
 
 // implemented in host_setup.cpp
+long fb_host_count_edges(const fb_ctx* c);
+void fb_host_vertex_lastcell(const fb_ctx* c, std::vector<int>& out);
 bool fb_host_row_blocks(fb_ctx* c, int chunk, int maxrows);
 bool fb_host_col_windows(fb_ctx* c, int max_window);
 bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym);

@@ -328,6 +328,28 @@ int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* he
     return rc ? rc : fb_host_import_phase2(c);
 }
 
+// tria->n_active_lines(): distinct vertex pairs along the 12 edges of every cell (to_str(), DealSolver.h:107-117)
+long fb_host_count_edges(const fb_ctx* c) {
+    static const int E[12][2] = {{0, 1}, {2, 3}, {4, 5}, {6, 7}, {0, 2}, {1, 3}, {4, 6}, {5, 7}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+    const size_t nc = (size_t) c->n_cells;
+    std::vector<uint64_t> keys(12 * nc);
+#pragma omp parallel for schedule(static)
+    for (long ce = 0; ce < (long) nc; ++ce)
+        for (int e = 0; e < 12; ++e) {
+            const uint64_t a = (uint64_t) c->cells_dof[8 * (size_t) ce + E[e][0]], b = (uint64_t) c->cells_dof[8 * (size_t) ce + E[e][1]];
+            keys[12 * (size_t) ce + e] = a < b ? (a << 32 | b) : (b << 32 | a);
+        }
+    std::sort(keys.begin(), keys.end());
+    return (long) (std::unique(keys.begin(), keys.end()) - keys.begin());
+}
+
+// vertex2cell / vertex2node of DealSolver::calc_vertex2dof (DealSolver.cpp:317-341): cells in order, the last one wins
+void fb_host_vertex_lastcell(const fb_ctx* c, std::vector<int>& out) {
+    out.assign(c->n_vert, 0);
+    for (int ce = 0; ce < c->n_cells; ++ce)
+        for (int k = 0; k < 8; ++k) out[c->dof2vertex[c->cells_dof[8 * (size_t) ce + k]]] = 8 * ce + k;
+}
+
 // Row blocks of the streaming SpMV: whole rows, <= chunk non-zeros and <= maxrows rows per block.
 // Returns false when a single row is longer than the chunk (the per-row kernel must be used).
 bool fb_host_row_blocks(fb_ctx* c, int chunk, int maxrows) {

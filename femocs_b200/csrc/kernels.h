@@ -34,6 +34,7 @@ void launch_cg_update_only(fb_ctx* c);
 void launch_cg_direction_only(fb_ctx* c);
 cudaError_t launch_cg_persistent(fb_ctx* c);
 void launch_minmax(fb_ctx* c);
+void launch_solution_grad(fb_ctx* c, double* d_grad3);
 void launch_gather(fb_ctx* c, int n, const int* idx, const double* src, double* dst);
 void launch_scatter(fb_ctx* c, int n, const int* idx, const double* src, double* dst);
 

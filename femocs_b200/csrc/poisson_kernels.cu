@@ -1217,6 +1217,46 @@ __global__ void __launch_bounds__(THREADS, 1) k_cg_persistent(const int* __restr
     if (blockIdx.x == 0 && tid == 0) { cgs->gh = gh; cgs->res2 = res2; cgs->it = it; cgs->done = done; }
 }
 
+// DealSolver::export_solution_grad (DealSolver.cpp:280-301): for vertex v, MINUS the gradient of the solution at Gauss
+// point number vertex2node[v] of cell vertex2cell[v] (FEValues::get_function_gradients at the QGauss<3>(2) points,
+// lexicographic order) -- the reference indexes the quadrature points with the local vertex number.
+__global__ void __launch_bounds__(128) k_solution_grad(int n_vert, const int* __restrict__ lastcell, const int* __restrict__ cells,
+                                                       const double* __restrict__ vxyz, const double* __restrict__ x,
+                                                       double* __restrict__ grad3) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_vert) return;
+    const int code = lastcell[v], c = code >> 3, q = code & 7;
+    double X[8], Y[8], Z[8], phi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int d = cells[8 * (size_t) c + i];
+        X[i] = vxyz[3 * (size_t) d]; Y[i] = vxyz[3 * (size_t) d + 1]; Z[i] = vxyz[3 * (size_t) d + 2]; phi[i] = x[d];
+    }
+    const double ga = 0.5 * (1.0 - 0.57735026918962576451), gb = 0.5 * (1.0 + 0.57735026918962576451);
+    const double xi = (q & 1) ? gb : ga, eta = (q & 2) ? gb : ga, zeta = (q & 4) ? gb : ga;
+    double dN[8][3], J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const double fx = (i & 1) ? xi : 1.0 - xi, fy = (i & 2) ? eta : 1.0 - eta, fz = (i & 4) ? zeta : 1.0 - zeta;
+        const double sx = (i & 1) ? 1.0 : -1.0, sy = (i & 2) ? 1.0 : -1.0, sz = (i & 4) ? 1.0 : -1.0;
+        dN[i][0] = sx * fy * fz; dN[i][1] = fx * sy * fz; dN[i][2] = fx * fy * sz;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) { J[0][e] += X[i] * dN[i][e]; J[1][e] += Y[i] * dN[i][e]; J[2][e] += Z[i] * dN[i][e]; }
+    }
+    const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][0] * J[2][2] - J[1][2] * J[2][0], c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    const double id = 1.0 / (J[0][0] * c00 - J[0][1] * c01 + J[0][2] * c02);
+    double inv[3][3];
+    inv[0][0] = c00 * id;  inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id; inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+    inv[1][0] = -c01 * id; inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id; inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+    inv[2][0] = c02 * id;  inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id; inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+    double g[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) g[d] += phi[i] * (dN[i][0] * inv[0][d] + dN[i][1] * inv[1][d] + dN[i][2] * inv[2][d]);
+    grad3[3 * (size_t) v] = -g[0]; grad3[3 * (size_t) v + 1] = -g[1]; grad3[3 * (size_t) v + 2] = -g[2];
+}
+
 // min/max of the solution (DealSolver::check_limits)
 __global__ void __launch_bounds__(256) k_minmax(int n, const double* __restrict__ x, double* __restrict__ partial,
                                                 unsigned* counter, double* __restrict__ out2) {
@@ -1688,6 +1728,11 @@ void launch_cg_update_only(fb_ctx* c) {
 void launch_cg_direction_only(fb_ctx* c) {
     const int g = grid_for(c, c->n_dofs, 256);
     k_direction<false><<<g, 256, 0, c->stream>>>(c->n_dofs, c->d_g.p, c->d_dinv.p, c->d_d.p, c->d_cg.p, beta_ptr(c));
+    c->launches++;
+}
+
+void launch_solution_grad(fb_ctx* c, double* d_grad3) {
+    k_solution_grad<<<(c->n_vert + 127) / 128, 128, 0, c->stream>>>(c->n_vert, c->d_vert_lastcell.p, c->d_cells.p, c->d_vxyz.p, c->d_x.p, d_grad3);
     c->launches++;
 }
 

@@ -38,6 +38,9 @@ SIGNATURES = {
     "fb_export_solution": (C.c_int, [vp, vp]),
     "fb_export_charge_dens": (C.c_int, [vp, vp]),
     "fb_import_solution": (C.c_int, [vp, vp]),
+    "fb_export_solution_grad": (C.c_int, [vp, vp]),
+    "fb_get_mesh_counts": (C.c_int, [vp, c_long_p, c_long_p]),
+    "fb_get_solver_mesh": (C.c_int, [vp, vp, vp]),
     "fb_check_limits": (C.c_int, [vp, C.c_double, C.c_double, c_int_p, c_double_p, c_double_p]),
     "fb_get_cell_volumes": (C.c_int, [vp, vp]),
     "fb_get_system": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -233,6 +233,25 @@ class PoissonSolver:
         self.ctx.check(self.ctx.L.fb_export_charge_dens(self.ctx.h, _p(out)))
         return out
 
+    # DealSolver::export_solution_grad (src/DealSolver.cpp:280-301): MINUS the gradient at Gauss point vertex2node[v] of
+    # cell vertex2cell[v], one triple per solver vertex
+    def export_solution_grad(self):
+        out = np.zeros((self.n_vertices, 3))
+        self.ctx.check(self.ctx.L.fb_export_solution_grad(self.ctx.h, _p(out)))
+        return out
+
+    # (#faces, #edges) of the solver mesh, as printed by operator<< (include/DealSolver.h:107-117)
+    def mesh_counts(self):
+        a = C.c_long(0); b = C.c_long(0)
+        self.ctx.check(self.ctx.L.fb_get_mesh_counts(self.ctx.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # solver vertices and cells (old-style vertex order) as written by write("*.vtk") / write("*.msh")
+    def solver_mesh(self):
+        xyz = np.zeros((self.n_vertices, 3)); cells = np.zeros((self.n_cells, 8), np.int32)
+        self.ctx.check(self.ctx.L.fb_get_solver_mesh(self.ctx.h, _p(xyz), _p(cells)))
+        return xyz, cells
+
     def import_solution(self, phi_vertex):
         phi = _f(phi_vertex)
         assert len(phi) == self.n_vertices
@@ -247,7 +266,8 @@ class PoissonSolver:
         return float(self.get_cell_volumes()[i])
 
     def to_str(self):
-        return "#elems=%d, #nodes=%d, #dofs=%d" % (self.n_cells, self.n_vertices, self.n_dofs)
+        nf, ne = self.mesh_counts()
+        return "#elems=%d, #faces=%d, #edges=%d, #nodes=%d, #dofs=%d" % (self.n_cells, nf, ne, self.n_vertices, self.n_dofs)
 
     # test hook: assembled system in DoF numbering
     def get_system(self):

@@ -153,6 +153,11 @@ int fb_poisson_solve(fb_ctx* ctx, int max_iter, double abs_tol, int precond,
  * both in solver-vertex order, n_vertices values. */
 int fb_export_solution(fb_ctx* ctx, double* phi_vertex);
 int fb_export_charge_dens(fb_ctx* ctx, double* rho_vertex);
+/* void DealSolver::export_solution_grad(vector<Tensor<1,3>>&)    src/DealSolver.cpp:280-301
+ *   grad3[3 v .. 3 v + 2] = MINUS the gradient of the solution, taken -- exactly as the reference does -- at Gauss point
+ *   number vertex2node[v] of cell vertex2cell[v] (the LAST cell, in cell order, that holds vertex v; :317-341), not at
+ *   the vertex itself.  n_vertices triples. */
+int fb_export_solution_grad(fb_ctx* ctx, double* grad3_vertex);
 /* void DealSolver::import_solution(const vector<double>*)       src/DealSolver.cpp:303-315 */
 int fb_import_solution(fb_ctx* ctx, const double* phi_vertex);
 
@@ -162,6 +167,13 @@ int fb_check_limits(fb_ctx* ctx, double lo, double hi, int* out_of_limits,
 
 /* double DealSolver::get_cell_vol(i) / int get_n_cells()        src/DealSolver.cpp:169-173 */
 int fb_get_cell_volumes(fb_ctx* ctx, double* vol_cells);
+
+/* operator<<(ostream&, const DealSolver&) / to_str()             include/DealSolver.h:107-117
+ *   #faces and #edges of the solver mesh (tria->n_active_faces(), n_active_lines()); counted on the host on first use */
+int fb_get_mesh_counts(fb_ctx* ctx, long* n_faces, long* n_edges);
+/* the solver mesh as deal.II holds it (for write("*.vtk|msh"), src/DealSolver.cpp:351-366): coordinates of the
+ * n_vertices solver vertices and the 8 vertex ids of every solver cell in old-style (UCD) order */
+int fb_get_solver_mesh(fb_ctx* ctx, double* xyz_vertex, int* cells_ucd8);
 
 /* test / integration hooks: the assembled system in DoF numbering (host copies).
  * Any pointer may be NULL. */

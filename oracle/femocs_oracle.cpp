@@ -1066,6 +1066,40 @@ void fo_export_solution(void* h, double* phi_vertex) {
 }
 // PoissonSolver.cpp:141-149 export_charge_dens: charge_density is reinit'ed to zero unless a file is
 // being written (PoissonSolver.cpp:198-207); file output is outside the hot path -> zeros
+// DealSolver.cpp:280-301 export_solution_grad with :317-341 calc_vertex2dof: vertex2cell / vertex2node are overwritten cell
+// by cell (the last cell holding the vertex wins); the gradient of the solution is evaluated at the QGauss<3>(2) points
+// of that cell and the one with index vertex2node[v] is taken (the reference indexes quadrature points by local vertex)
+void fo_export_solution_grad(void* h, double* grad3_vertex) {
+    Oracle& o = *(Oracle*) h;
+    const int n_vert = (int) o.vert2node.size();
+    std::vector<int> v2cell(n_vert, 0), v2node(n_vert, 0);
+    for (int c = 0; c < (int) o.cells.size(); ++c)
+        for (int i = 0; i < 8; ++i) { v2cell[o.cells[c][i]] = c; v2node[o.cells[c][i]] = i; }
+    for (int v = 0; v < n_vert; ++v) {
+        double JxW; V3 g[8];
+        cell_geometry(o, v2cell[v], v2node[v], JxW, g);
+        V3 s;
+        for (int k = 0; k < 8; ++k) s = s + g[k] * o.sol[o.vertex2dof[o.cells[v2cell[v]][k]]];
+        grad3_vertex[3 * v] = -1.0 * s.x; grad3_vertex[3 * v + 1] = -1.0 * s.y; grad3_vertex[3 * v + 2] = -1.0 * s.z;
+    }
+}
+// operator<<(ostream&, const DealSolver&) counts (DealSolver.h:107-117): #faces, #edges of the solver mesh
+void fo_mesh_counts(void* h, long* n_faces, long* n_edges) {
+    Oracle& o = *(Oracle*) h;
+    static const int E[12][2] = {{0, 1}, {2, 3}, {4, 5}, {6, 7}, {0, 2}, {1, 3}, {4, 6}, {5, 7}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+    std::set<std::pair<int, int>> edges;
+    std::set<std::array<int, 4>> faces;
+    for (const auto& c : o.cells) {
+        for (const auto& e : E) edges.insert({std::min(c[e[0]], c[e[1]]), std::max(c[e[0]], c[e[1]])});
+        for (int f = 0; f < 6; ++f) {
+            std::array<int, 4> k;
+            for (int v = 0; v < 4; ++v) k[v] = c[FACE_VERTS[f][v]];
+            std::sort(k.begin(), k.end());
+            faces.insert(k);
+        }
+    }
+    *n_faces = (long) faces.size(); *n_edges = (long) edges.size();
+}
 void fo_export_charge_dens(void* h, double* rho_vertex) {
     Oracle& o = *(Oracle*) h;
     for (size_t v = 0; v < o.vertex2dof.size(); ++v) rho_vertex[v] = 0.0;

@@ -48,6 +48,8 @@ def lib():
         L.fo_get_cells.argtypes = [C.c_void_p, _ip]
         L.fo_export_solution.argtypes = [C.c_void_p, _dp]
         L.fo_export_charge_dens.argtypes = [C.c_void_p, _dp]
+        L.fo_export_solution_grad.argtypes = [C.c_void_p, _dp]
+        L.fo_mesh_counts.argtypes = [C.c_void_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]
         L.fo_check_limits.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.fo_cell_vol.argtypes = [C.c_void_p, C.c_int]
         L.fo_cell_vol.restype = C.c_double
@@ -145,6 +147,16 @@ class Oracle:
         phi = np.zeros(self.n_vertices)
         self.L.fo_export_solution(self.h, phi)
         return phi
+
+    def export_solution_grad(self):
+        g = np.zeros((self.n_vertices, 3))
+        self.L.fo_export_solution_grad(self.h, g.reshape(-1))
+        return g
+
+    def mesh_counts(self):
+        a = C.c_long(0); b = C.c_long(0)
+        self.L.fo_mesh_counts(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def export_charge_dens(self):
         rho = np.zeros(self.n_vertices)

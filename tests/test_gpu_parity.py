@@ -558,3 +558,25 @@ def test_stale_particle_cells_are_not_dereferenced(fb, golden, gpu_interp):
     assert np.all(E == 0)
     v = pic.update_velocities(pts[:50], np.ones((50, 3)), stale[:50], 0.5, -17.5882)
     assert np.all(v == 1)
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_export_solution_grad_counts_and_mesh_export(name, fb, ctx, golden, oracles):
+    """DealSolver::export_solution_grad, the #faces / #edges of operator<< and the mesh behind write('*.vtk'|'*.msh')"""
+    m = golden("mesh", name); o = oracles[name]
+    s = fb.PoissonSolver(ctx)
+    s.import_mesh(m["nodes"], m["hexs"], m["hex_markers"])
+    phi = hash_field(s.n_vertices, 1, 3)[:, 0]
+    s.import_solution(phi)
+    _, _, v2d, v2n = o.vectors()
+    sol = np.zeros(o.n_dofs); sol[v2d] = phi
+    o.set_solution(sol)
+    ref = o.export_solution_grad()
+    assert np.abs(s.export_solution_grad() - ref).max() <= 1e-11 * np.abs(ref).max()
+    assert s.mesh_counts() == o.mesh_counts()
+    nf, ne = o.mesh_counts()
+    assert s.to_str() == "#elems=%d, #faces=%d, #edges=%d, #nodes=%d, #dofs=%d" % (o.n_cells, nf, ne, o.n_vertices, o.n_dofs)
+    xyz, cells = s.solver_mesh()
+    assert np.array_equal(xyz, m["nodes"][v2n])
+    vac = m["hex_markers"] > 0
+    assert np.array_equal(xyz[cells], m["nodes"][m["hexs"][vac]])

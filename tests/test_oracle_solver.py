@@ -104,3 +104,23 @@ def test_native_mesh_solve(golden):
     rhs, sol, _, _ = o.vectors()
     A = sp.csr_matrix((val, col, rp))
     assert np.linalg.norm(A @ sol - rhs) <= 1e-9
+
+
+def test_export_solution_grad_is_the_gauss_point_gradient():
+    """DealSolver::export_solution_grad (DealSolver.cpp:280-301): a linear potential has the same gradient at every
+    point, so whatever Gauss point the reference picks, the result is minus that gradient; face / edge counts of
+    operator<< (DealSolver.h:107-117) on a structured box are known in closed form"""
+    from femocs_b200 import synth
+    nx, ny, nz = 4, 3, 5
+    nodes, hexs, mk = synth.box_mesh(nx, ny, nz, 2.0, 1.5, 2.5, jitter=0.2)
+    o = Oracle(); o.import_mesh(nodes, hexs, mk)
+    _, _, v2d, v2n = o.vectors()
+    a = np.array([0.3, -0.7, 1.1])
+    phi = nodes[v2n] @ a + 2.0
+    sol = np.zeros(o.n_dofs); sol[v2d] = phi
+    o.set_solution(sol)
+    g = o.export_solution_grad()
+    assert np.abs(g + a).max() < 1e-12
+    nf, ne = o.mesh_counts()
+    assert nf == (nx + 1) * ny * nz + nx * (ny + 1) * nz + nx * ny * (nz + 1)
+    assert ne == nx * (ny + 1) * (nz + 1) + (nx + 1) * ny * (nz + 1) + (nx + 1) * (ny + 1) * nz
