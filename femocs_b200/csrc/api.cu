@@ -769,7 +769,7 @@ int fb_get_system(fb_ctx* c, int* rowptr, int* col, double* val, double* val_sav
     if (val || rhs) {
         // the solver keeps K and the raw right-hand side and applies the Dirichlet conditions as a mask; the ELIMINATED
         // matrix and the lifted right-hand side of the reference (MatrixTools::apply_boundary_values) are produced here,
-        // on demand, for the tests that compare them with the oracle
+        // on demand, for the parity tests that read them back
         FB_REQUIRE(c, c->assembled, "fb_get_system: val / rhs need an assembled system");
         fb::DevBuf<double> tv, tr, tl, td; fb::DevBuf<int> tp;
         FB_CUDA(c, tv.alloc(c->nnz)); FB_CUDA(c, tr.alloc(c->n_dofs)); FB_CUDA(c, tl.alloc(c->n_dofs)); FB_CUDA(c, td.alloc(c->n_dofs));
