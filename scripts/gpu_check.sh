@@ -6,7 +6,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.txt 2>&1
 nproc >> $OUT/${TAG}_smi.txt; lscpu | grep "Model name" >> $OUT/${TAG}_smi.txt
-timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
+timeout 900 python -m pytest tests -m gpu -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
 tail -5 $OUT/${TAG}_pytest.log
 timeout 900 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?"
 tail -3 $OUT/${TAG}_bench.err; cat $OUT/${TAG}_bench.json

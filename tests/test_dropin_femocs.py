@@ -116,7 +116,7 @@ if rv.value == 0:
     E = np.zeros(3 * n); L.femocs_export_data(fem, C.byref(rv), E.ctypes.data_as(dp), n, b"elfield"); out["export_rv"] = rv.value
     En = np.zeros(n); L.femocs_export_data(fem, C.byref(rv), En.ctypes.data_as(dp), n, b"elfield_norm")
     ph = np.zeros(n); L.femocs_export_data(fem, C.byref(rv), ph.ctypes.data_as(dp), n, b"potential")
-    pts = f(atoms[::5]); k = len(pts)
+    pts = f(atoms[::10]); k = len(pts)
     x, y, z = f(pts[:, 0]), f(pts[:, 1]), f(pts[:, 2])
     res = {}
     for name in ("femocs_interpolate_elfield", "femocs_interpolate_surface_elfield"):
@@ -177,13 +177,17 @@ def test_reference_femocs_runs_on_the_gpu_through_its_own_c_abi(golden):
     assert rel(z["En"][ids], np.sqrt((sol[:, :3] ** 2).sum(1))) < 1e-8
     other = np.ones(len(E), bool); other[ids] = False
     assert np.all(z["E"][other] == 0)
-    # femocs_interpolate_elfield / _phi on every 5th atom (dim 3) and femocs_interpolate_surface_elfield (dim 2)
+    # femocs_interpolate_elfield / _phi on every 10th atom (dim 3) and femocs_interpolate_surface_elfield (dim 2).
+    # The flags the reference hands out are NOT those of the query points: ProjectRunaway::interpolate reads
+    # fields.get_marker(i), the cell of the i-th SURFACE atom of the last prepare_export (ProjectRunaway.cpp:655-656),
+    # so the query is kept shorter than the surface-atom list and the expectation is that list's located cells.
     c3, s3 = o.locate_interpolate(3, 1, z["pts"])
     assert z["vol_rv"] == 0
-    assert np.array_equal(z["vol_flag"], (c3 >= 0).astype(np.int32))            # located cells: exact
+    k = len(z["pts"]); assert k <= len(cells)
+    assert np.array_equal(z["vol_flag"], (cells[:k] >= 0).astype(np.int32))     # located cells: exact
     assert rel(z["vol_E"], s3[:, :3]) < 1e-8
     assert rel(z["phi"], s3[:, 4]) < 1e-8 and np.array_equal(z["phi_flag"], z["vol_flag"])
     c2, s2 = o.locate_interpolate(2, 1, z["pts"])
-    assert np.array_equal(z["surf_flag"], (c2 >= 0).astype(np.int32))
+    assert np.array_equal(z["surf_flag"], z["vol_flag"])
     assert rel(z["surf_E"], s2[:, :3]) < 1e-8
     assert rel(z["surf_norm"], np.sqrt((s2[:, :3] ** 2).sum(1))) < 1e-8
