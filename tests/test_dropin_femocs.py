@@ -62,7 +62,11 @@ ip = C.POINTER(C.c_int)
 
 def _run_child(code):
     """the reference keeps process-wide globals and chdir()s: run every session in its own interpreter"""
-    env = dict(os.environ, PYTHONPATH=ROOT)
+    # Femocs::interpolate_elfield hands export_results an UNINITIALISED new double[3n] (Femocs.cpp:219) and the
+    # lower-case label makes SolutionReader::export_vec ADD to it (SolutionReader.cpp:306,330-335): the reference's
+    # result is heap garbage + E unless malloc happens to return zero pages.  MALLOC_PERTURB_=255 makes glibc fill
+    # every allocation with ~255 = 0x00, which pins that undefined behaviour to the intended value.
+    env = dict(os.environ, PYTHONPATH=ROOT, MALLOC_PERTURB_="255")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return r.stdout
