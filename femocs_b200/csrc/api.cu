@@ -158,6 +158,12 @@ fb_ctx* fb_plan_create(int rank, int world) {
     c->host_only = true; c->rank = rank; c->world = world;
     return c;
 }
+// host-only: mesh kind of the next fb_plan_import (0 = vacuum hexahedra, 1 = bulk hexahedra of the current / heat solvers)
+int fb_plan_set_kind(fb_ctx* c, int kind) {
+    FB_REQUIRE(c, c->host_only && (kind == 0 || kind == 1), "fb_plan_set_kind: needs a plan context and kind in {0, 1}");
+    c->mesh_kind = kind;
+    return FB_OK;
+}
 int fb_plan_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex, double* bbox6) {
     FB_REQUIRE(c, c->host_only, "fb_plan_phase1: not a plan context");
     const int rc = fb_host_partition_phase1(c, xyz, n_nodes, hex8, hex_marker, n_hex);
@@ -256,7 +262,27 @@ int fb_plan_jds_get(const fb_ctx* c, unsigned short* perm, unsigned short* len, 
 void* fb_get_stream(fb_ctx* c) { return (void*) c->stream; }
 
 // ------------------------------------------------------------------------------------------
+static int import_mesh_impl(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
+
 int fb_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {
+    c->mesh_kind = 0;
+    return import_mesh_impl(c, xyz, n_nodes, hex8, hex_marker, n_hex);
+}
+
+int fb_import_bulk_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {
+    FB_REQUIRE(c, c->world == 1, "fb_import_bulk_mesh: the current / heat solvers run on un-partitioned meshes (native sizes)");
+    c->mesh_kind = 1;
+    const int rc = import_mesh_impl(c, xyz, n_nodes, hex8, hex_marker, n_hex);
+    if (rc) return rc;
+    // second system (the heat equation shares the sparsity of the current equation) and the per-face Neumann data
+    FB_CUDA(c, c->d_val_other.alloc(c->nnz)); FB_CUDA(c, c->d_x_other.alloc(c->n_cols));
+    FB_CUDA(c, c->d_face_bc.alloc(std::max(1, c->n_top_faces)));
+    c->ch_active = 0; c->ch_setup_ok = false;
+    c->ch_matrix_ok[0] = c->ch_matrix_ok[1] = c->ch_assembled[0] = c->ch_assembled[1] = false;
+    return FB_OK;
+}
+
+static int import_mesh_impl(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {
     FB_REQUIRE(c, xyz && hex8 && hex_marker && n_nodes > 0 && n_hex > 0, "fb_import_mesh: empty mesh");
     cudaSetDevice(c->device);
     c->setup_ok = c->assembled = c->matrix_ok = c->interp_ok = false;
@@ -296,7 +322,7 @@ int fb_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, c
     static const int FV[6][4] = {{0, 2, 4, 6}, {1, 3, 5, 7}, {0, 1, 4, 5}, {2, 3, 6, 7}, {0, 1, 2, 3}, {4, 5, 6, 7}};
     std::vector<int> top;
     for (const auto& bf : c->bfaces)
-        if (bf.id == 8) for (int k = 0; k < 4; ++k) top.push_back(c->cells_dof[8 * (size_t) bf.cell + FV[bf.face][k]]);
+        if (bf.id == (c->mesh_kind ? 2 : 8)) for (int k = 0; k < 4; ++k) top.push_back(c->cells_dof[8 * (size_t) bf.cell + FV[bf.face][k]]);
     FB_CUDA(c, c->d_vxyz.upload(vxyz, s));
     FB_CUDA(c, c->d_cells.upload(c->cells_dof, s));
     FB_CUDA(c, c->d_rowptr.upload(c->rowptr, s));
@@ -344,6 +370,7 @@ int fb_get_sizes(const fb_ctx* c, long* out) {
 
 int fb_poisson_setup(fb_ctx* c, double field, double potential, int anode_is_dirichlet) {
     FB_REQUIRE(c, c->mesh_ok, "fb_poisson_setup: no mesh imported");
+    FB_REQUIRE(c, c->mesh_kind == 0, "fb_poisson_setup: the context holds a bulk mesh (fb_import_bulk_mesh)");
     cudaSetDevice(c->device);
     c->applied_field = field; c->applied_potential = potential; c->anode_dirichlet = anode_is_dirichlet;
     c->setup_ok = true; c->assembled = false; c->matrix_ok = false;
@@ -781,6 +808,161 @@ int fb_get_system(fb_ctx* c, int* rowptr, int* col, double* val, double* val_sav
     }
     if (sol) FB_CUDA(c, cudaMemcpyAsync(sol, c->d_x.p, c->n_dofs * sizeof(double), cudaMemcpyDeviceToHost, s));
     return sync_check(c, "fb_get_system");
+}
+
+// ------------------------------------------------------------------------------------------
+// CurrentHeatSolver<3> on the bulk mesh (src/CurrentHeatSolver.cpp).  Two systems share one sparsity
+// pattern and the CG engine of fb_poisson_solve: `which` 0 = CurrentSolver (Laplace, sigma = 1), 1 = HeatSolver.
+// The engine reads d_val_save / d_x; the system that is not being worked on is parked in d_val_other / d_x_other.
+// ------------------------------------------------------------------------------------------
+static void ch_activate(fb_ctx* c, int which) {
+    if (c->ch_active == which) return;
+    std::swap(c->d_val_save.p, c->d_val_other.p); std::swap(c->d_val_save.n, c->d_val_other.n);
+    std::swap(c->d_x.p, c->d_x_other.p); std::swap(c->d_x.n, c->d_x_other.n);
+    c->ch_active = which;
+    drop_graph(c);                      // captured launches hold the old pointers
+    c->jds_val_dirty = true; c->cheb_lmax = 0;
+    c->assembled = false;               // the Dirichlet mask / dinv / rhs belong to the system assembled last
+}
+static double* ch_solution(fb_ctx* c, int which) { return which == c->ch_active ? c->d_x.p : c->d_x_other.p; }
+
+int fb_ch_set_physics(fb_ctx* c, const double* T, const double* rho, int n, double lorentz) {
+    FB_REQUIRE(c, T && rho && n >= 2, "fb_ch_set_physics: the resistivity table needs at least two rows");
+    for (int i = 1; i < n; ++i) FB_REQUIRE(c, T[i] > T[i - 1], "fb_ch_set_physics: temperatures must increase");
+    cudaSetDevice(c->device);
+    FB_CUDA(c, c->d_res_T.upload(T, n, c->stream)); FB_CUDA(c, c->d_res_rho.upload(rho, n, c->stream));
+    c->ch_n_table = n; c->ch_lorentz = lorentz;
+    return sync_check(c, "fb_ch_set_physics");
+}
+
+int fb_ch_setup(fb_ctx* c, double T_ambient) {
+    FB_REQUIRE(c, c->mesh_ok && c->mesh_kind == 1, "fb_ch_setup: no bulk mesh imported (fb_import_bulk_mesh)");
+    cudaSetDevice(c->device);
+    ch_activate(c, 0);
+    c->ch_T_ambient = T_ambient;
+    // DealSolver::setup_system: solution = dirichlet_bc_value (0 for the current, T_ambient for the heat equation)
+    FB_CUDA(c, cudaMemsetAsync(c->d_x.p, 0, c->n_cols * sizeof(double), c->stream));
+    FB_CUDA(c, c->d_sol.alloc(c->n_cols));
+    std::vector<double> t(c->n_cols, T_ambient);
+    FB_CUDA(c, cudaMemcpyAsync(c->d_x_other.p, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->ch_setup_ok = true; c->setup_ok = true; c->assembled = false;
+    c->ch_matrix_ok[0] = c->ch_matrix_ok[1] = c->ch_assembled[0] = c->ch_assembled[1] = false;
+    return FB_OK;
+}
+
+static int ch_face_data(fb_ctx* c, const double* face_bc, int n_faces, const char* who) {
+    if (n_faces != c->n_top_faces) return c->fail(FB_ERR_ARG, "%s: %d face values for %d copper_surface faces", who, n_faces, c->n_top_faces);
+    if (n_faces > 0) {
+        if (!face_bc) return c->fail(FB_ERR_ARG, "%s: face data missing", who);
+        FB_CUDA(c, cudaMemcpyAsync(c->d_face_bc.p, face_bc, n_faces * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    return FB_OK;
+}
+
+// boundary part shared by the two assemblies: Neumann faces, Dirichlet mask on copper_bottom, constrained dofs of the solution
+static int ch_finish_assembly(fb_ctx* c, int which, double dirichlet_value) {
+    cudaStream_t s = c->stream;
+    fb::launch_neumann(c);                                              // assemble_rhs(copper_surface) with per-face data
+    FB_CUDA(c, cudaMemsetAsync(c->d_bcflag.p, 0, c->n_cols * sizeof(int), s));
+    FB_CUDA(c, cudaMemsetAsync(c->d_bcval.p, 0, c->n_cols * sizeof(double), s));
+    fb::launch_set_bc(c, c->d_bc_dofs.p, (int) c->copper_dofs.size(), dirichlet_value);      // append_dirichlet(copper_bottom, value)
+    c->n_dirichlet = c->n_dirichlet_cu;
+    fb::launch_bc_prepare(c);
+    fb::launch_bc_solution(c);
+    c->jds_val_dirty = true; c->cheb_lmax = 0;
+    c->matrix_ok = true; c->assembled = true;
+    c->ch_assembled[which] = true; c->ch_assembled[1 - which] = false;
+    return sync_check(c, which ? "fb_heat_assemble" : "fb_current_assemble");
+}
+
+int fb_current_assemble(fb_ctx* c, const double* face_current_density, int n_faces) {
+    FB_REQUIRE(c, c->ch_setup_ok, "fb_current_assemble: call fb_ch_setup first");
+    cudaSetDevice(c->device);
+    ch_activate(c, 0);
+    int rc = ch_face_data(c, face_current_density, n_faces, "fb_current_assemble");
+    if (rc) return rc;
+    if (!c->ch_matrix_ok[0]) {
+        // sigma = 1 (CurrentHeatSolver.cpp:466): the matrix is the plain stiffness matrix of the mesh, assembled once
+        FB_CUDA(c, cudaMemsetAsync(c->d_val_save.p, 0, c->nnz * sizeof(double), c->stream));
+        fb::launch_assemble_stiffness(c);
+        c->ch_matrix_ok[0] = true;
+    }
+    FB_CUDA(c, cudaMemsetAsync(c->d_rhs.p, 0, c->n_dofs * sizeof(double), c->stream));
+    return ch_finish_assembly(c, 0, 0.0);
+}
+
+int fb_heat_assemble(fb_ctx* c, double delta_time, const double* face_nottingham, int n_faces) {
+    FB_REQUIRE(c, c->ch_setup_ok, "fb_heat_assemble: call fb_ch_setup first");
+    FB_REQUIRE(c, c->ch_n_table >= 2, "fb_heat_assemble: no resistivity table (fb_ch_set_physics)");
+    FB_REQUIRE(c, delta_time > 0, "fb_heat_assemble: invalid delta time");
+    cudaSetDevice(c->device);
+    ch_activate(c, 1);
+    int rc = ch_face_data(c, face_nottingham, n_faces, "fb_heat_assemble");
+    if (rc) return rc;
+    const double cu_rho_cp = 3.4496e-24;                                // CurrentHeatSolver.h:118 [J/(K*Ang^3)]
+    FB_CUDA(c, cudaMemsetAsync(c->d_val_save.p, 0, c->nnz * sizeof(double), c->stream));
+    FB_CUDA(c, cudaMemsetAsync(c->d_rhs.p, 0, c->n_dofs * sizeof(double), c->stream));
+    fb::launch_assemble_heat(c, cu_rho_cp * (1.0 / delta_time), c->d_x.p, c->d_x_other.p);
+    c->ch_matrix_ok[1] = true;
+    return ch_finish_assembly(c, 1, c->ch_T_ambient);
+}
+
+int fb_ch_solve(fb_ctx* c, int which, int max_iter, double abs_tol, int precond, int* n_iter, double* final_residual) {
+    FB_REQUIRE(c, which == 0 || which == 1, "fb_ch_solve: which must be 0 (current) or 1 (heat)");
+    FB_REQUIRE(c, c->mesh_kind == 1 && c->ch_assembled[which] && c->ch_active == which,
+               "fb_ch_solve: assemble that system first (the Dirichlet mask and right-hand side belong to the system assembled last)");
+    return fb_poisson_solve(c, max_iter, abs_tol, precond, n_iter, final_residual);
+}
+
+// x.p of the engine temporarily points at the requested system
+struct ChView {
+    fb_ctx* c; bool swapped;
+    ChView(fb_ctx* c_, int which) : c(c_), swapped(c_->mesh_kind == 1 && which != c_->ch_active) { if (swapped) std::swap(c->d_x.p, c->d_x_other.p); }
+    ~ChView() { if (swapped) std::swap(c->d_x.p, c->d_x_other.p); }
+};
+
+int fb_ch_export_solution(fb_ctx* c, int which, double* vertex_values) {
+    FB_REQUIRE(c, c->mesh_kind == 1 && (which == 0 || which == 1), "fb_ch_export_solution: needs a bulk mesh and which in {0, 1}");
+    ChView v(c, which);
+    return fb_export_solution(c, vertex_values);
+}
+int fb_ch_import_solution(fb_ctx* c, int which, const double* vertex_values) {
+    FB_REQUIRE(c, c->mesh_kind == 1 && (which == 0 || which == 1), "fb_ch_import_solution: needs a bulk mesh and which in {0, 1}");
+    ChView v(c, which);
+    return fb_import_solution(c, vertex_values);
+}
+int fb_ch_export_solution_grad(fb_ctx* c, int which, double* grad3) {
+    FB_REQUIRE(c, c->mesh_kind == 1 && (which == 0 || which == 1), "fb_ch_export_solution_grad: needs a bulk mesh and which in {0, 1}");
+    ChView v(c, which);
+    return fb_export_solution_grad(c, grad3);
+}
+int fb_ch_check_limits(fb_ctx* c, int which, double lo, double hi, int* bad, double* mn, double* mx) {
+    FB_REQUIRE(c, c->mesh_kind == 1 && (which == 0 || which == 1), "fb_ch_check_limits: needs a bulk mesh and which in {0, 1}");
+    ChView v(c, which);
+    return fb_check_limits(c, lo, hi, bad, mn, mx);
+}
+
+// DealSolver::export_surface_centroids (DealSolver.cpp:229-245): centres of the copper_surface faces in cell / face order,
+// the order of the per-face data of fb_current_assemble / fb_heat_assemble.  xyz3 == NULL: count only.
+int fb_export_surface_centroids(fb_ctx* c, double* xyz3, int* n_faces) {
+    FB_REQUIRE(c, c->mesh_ok, "fb_export_surface_centroids: no mesh");
+    static const int FV[6][4] = {{0, 2, 4, 6}, {1, 3, 5, 7}, {0, 1, 4, 5}, {2, 3, 6, 7}, {0, 1, 2, 3}, {4, 5, 6, 7}};
+    int n = 0;
+    for (const auto& bf : c->bfaces) {
+        if (bf.id != 2) continue;
+        if (xyz3) {
+            double s[3] = {0, 0, 0};
+            for (int k = 0; k < 4; ++k) {
+                const double* p = &c->xyz[3 * (size_t) c->vert2node[c->dof2vertex[c->cells_dof[8 * (size_t) bf.cell + FV[bf.face][k]]]]];
+                s[0] += p[0]; s[1] += p[1]; s[2] += p[2];
+            }
+            xyz3[3 * (size_t) n] = s[0] / 4.0; xyz3[3 * (size_t) n + 1] = s[1] / 4.0; xyz3[3 * (size_t) n + 2] = s[2] / 4.0;
+        }
+        ++n;
+    }
+    if (n_faces) *n_faces = n;
+    return FB_OK;
 }
 
 // ------------------------------------------------------------------------------------------

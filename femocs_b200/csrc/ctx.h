@@ -106,6 +106,7 @@ struct fb_ctx {
     double bb_mn[3] = {0, 0, 0}, bb_mx[3] = {0, 0, 0};
 
     // ---- host copies of the mesh (femocs numbering) ----
+    int mesh_kind = 0;                       // 0 = vacuum hexahedra (PoissonSolver), 1 = bulk hexahedra (CurrentHeatSolver)
     int n_nodes = 0, n_hex = 0;
     std::vector<double> xyz;
     std::vector<int> hex8, hex_marker;
@@ -138,6 +139,12 @@ struct fb_ctx {
     fb::DevBuf<int> d_rowptr, d_col, d_diagpos, d_rowblk, d_win_off, d_win_list;
     fb::DevBuf<unsigned short> d_col16, d_jds_perm, d_jds_len, d_jds_slot;
     fb::DevBuf<int> d_jds_jdp, d_jds_jd, d_jds_base; fb::DevBuf<double> d_val_jds, d_diag;
+    // CurrentHeatSolver (mesh_kind 1): the CG engine works on d_val_save / d_x; the system that is NOT active is parked in
+    // d_val_other / d_x_other (ch_active: 0 = current, 1 = heat)
+    fb::DevBuf<double> d_val_other, d_x_other, d_res_T, d_res_rho;
+    int ch_active = 0, ch_n_table = 0; bool ch_setup_ok = false, ch_matrix_ok[2] = {false, false}, ch_assembled[2] = {false, false};
+    double ch_T_ambient = 300.0, ch_lorentz = 2.44e-8;
+    fb::DevBuf<double> d_face_bc;            // per-face Neumann data (emission current density / Nottingham heat)
     fb::DevBuf<double> d_val_save;           // K before boundary conditions (the reference's system_matrix_save); never rewritten between assemblies
     fb::DevBuf<int> d_bc_dofs;               // Dirichlet candidates: copper dofs, then top dofs (uploaded once per mesh)
     int n_dirichlet_cu = 0, n_dirichlet_cu_top = 0;      // owned constrained rows: copper only / copper + top

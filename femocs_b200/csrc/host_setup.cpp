@@ -94,14 +94,15 @@ int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* 
     // ---- solver cells and order-preserving vertex compaction ----
     c->hex2cell.assign(n_hex, -1); c->cell2hex.clear();
     c->node2vert.assign(n_nodes, -1);
+    // mesh_kind 0: vacuum hexahedra (Hexahedra::export_vacuum, marker > 0); 1: bulk (export_bulk, marker < 0; TetgenCells.cpp:688-701)
     for (int h = 0; h < n_hex; ++h)
-        if (hex_marker[h] > 0) {
+        if (c->mesh_kind ? hex_marker[h] < 0 : hex_marker[h] > 0) {
             c->hex2cell[h] = (int) c->cell2hex.size();
             c->cell2hex.push_back(h);
             for (int k = 0; k < 8; ++k) c->node2vert[hex8[8 * h + k]] = 0;
         }
     const int n_cells = c->n_cells = (int) c->cell2hex.size();
-    if (n_cells == 0) return c->fail(FB_ERR_MESH, "no vacuum hexahedra (marker > 0) in the mesh");
+    if (n_cells == 0) return c->fail(FB_ERR_MESH, c->mesh_kind ? "no bulk hexahedra (marker < 0) in the mesh" : "no vacuum hexahedra (marker > 0) in the mesh");
     c->vert2node.clear();
     for (int i = 0; i < n_nodes; ++i)
         if (c->node2vert[i] == 0) { c->node2vert[i] = (int) c->vert2node.size(); c->vert2node.push_back(i); }
@@ -218,9 +219,19 @@ int fb_host_import_phase2(fb_ctx* c) {
     for (auto& bf : c->bfaces) {
         double p[3]; face_centre(bf.cell, bf.face, p);
         auto on = [&](double v, double b) { return std::fabs(v - b) <= eps; };
-        if (on(p[0], mn[0]) || on(p[0], mx[0]) || on(p[1], mn[1]) || on(p[1], mx[1])) bf.id = 4;   // vacuum_sides
-        else if (on(p[2], mx[2])) { bf.id = 8; c->n_top_faces++; }                               // vacuum_top
-        else bf.id = 2;                                                                           // copper_surface (bottom & other)
+        if (c->mesh_kind == 0) {
+            // PoissonSolver::mark_mesh (PoissonSolver.cpp:52-55): top = vacuum_top, bottom = other = copper_surface
+            if (on(p[0], mn[0]) || on(p[0], mx[0]) || on(p[1], mn[1]) || on(p[1], mx[1])) bf.id = 4;   // vacuum_sides
+            else if (on(p[2], mx[2])) { bf.id = 8; c->n_top_faces++; }                               // vacuum_top
+            else bf.id = 2;                                                                           // copper_surface (bottom & other)
+        } else {
+            // CurrentHeatSolver::mark_mesh (CurrentHeatSolver.cpp:526-530): top = other = copper_surface (Neumann faces with
+            // per-face emission data), bottom = copper_bottom (Dirichlet), sides = copper_sides
+            if (on(p[0], mn[0]) || on(p[0], mx[0]) || on(p[1], mn[1]) || on(p[1], mx[1])) bf.id = 4;
+            else if (on(p[2], mx[2])) { bf.id = 2; c->n_top_faces++; }
+            else if (on(p[2], mn[2])) bf.id = 7;                                                      // copper_bottom
+            else { bf.id = 2; c->n_top_faces++; }
+        }
     }
 
     laps.lap("face ids");
@@ -311,7 +322,8 @@ int fb_host_import_phase2(fb_ctx* c) {
     for (const auto& bf : c->bfaces)
         for (int k = 0; k < 4; ++k) {
             const int d = c->cells_dof[8 * (size_t) bf.cell + FACE_VERTS[bf.face][k]];
-            if (bf.id == 2) on_cu[d] = 1;
+            // "copper" = the Dirichlet set of the mesh kind: copper_surface for the vacuum mesh, copper_bottom for the bulk
+            if (bf.id == (c->mesh_kind ? 7 : 2)) on_cu[d] = 1;
             if (bf.id == 8) on_top[d] = 1;
         }
     c->copper_dofs.clear(); c->top_dofs.clear();

@@ -12,6 +12,7 @@ void stream_block_shape(int kernel, int& chunk, int& maxrows);
 void launch_assemble_stiffness(fb_ctx* c);
 void launch_cell_volumes(fb_ctx* c, double* d_cell_vol);
 void launch_neumann(fb_ctx* c);
+void launch_assemble_heat(fb_ctx* c, double gamma, const double* d_T_prev, const double* d_phi);
 void launch_set_bc(fb_ctx* c, const int* d_dofs, int n, double value);
 void launch_bc_prepare(fb_ctx* c);
 void launch_bc_solution(fb_ctx* c);

@@ -208,32 +208,11 @@ __global__ void __launch_bounds__(ASM_BLOCK) k_cell_volumes(int n_cells, const i
     cell_vol[c] = vol;
 }
 
-__global__ void __launch_bounds__(ASM_BLOCK) k_assemble_stiffness(int n_cells, int n_rows, const int* __restrict__ cells,
-                                                                 const double* __restrict__ vxyz,
-                                                                 const int* __restrict__ rowptr, const int* __restrict__ col,
-                                                                 double* __restrict__ val) {
-    __shared__ double s_ke[ASM_BLOCK * ASM_STRIDE];
-    __shared__ int s_dof[ASM_BLOCK * 8];
+// phase B of the assembly kernels: lane i of an 8-lane group adds row i of one element matrix (upper triangle parked in
+// shared memory by phase A) to global row dof_i
+__device__ __forceinline__ void asm_scatter_rows(const double* s_ke, const int* s_dof, int n_rows, const int* __restrict__ rowptr,
+                                                 const int* __restrict__ col, double* __restrict__ val) {
     const int tid = threadIdx.x;
-    const int c = blockIdx.x * ASM_BLOCK + tid;
-    // ---- phase A: element matrix of hexahedron c ----
-    if (c < n_cells) {
-        double X[8], Y[8], Z[8], Ke[36], vol;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int d = __ldg(&cells[8 * (size_t) c + i]);
-            s_dof[8 * tid + i] = d;
-            X[i] = __ldg(&vxyz[3 * (size_t) d]); Y[i] = __ldg(&vxyz[3 * (size_t) d + 1]); Z[i] = __ldg(&vxyz[3 * (size_t) d + 2]);
-        }
-        hex_stiffness(X, Y, Z, Ke, vol);
-#pragma unroll
-        for (int k = 0; k < 36; ++k) s_ke[tid * ASM_STRIDE + k] = Ke[k];
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s_dof[8 * tid + i] = -1;
-    }
-    __syncthreads();
-    // ---- phase B: lane i of an 8-lane group adds row i of one element matrix to global row dof_i ----
     const int lane = tid & 7, sub = tid >> 3;
 #pragma unroll 1
     for (int pass = 0; pass < ASM_BLOCK / 16; ++pass) {
@@ -261,11 +240,149 @@ __global__ void __launch_bounds__(ASM_BLOCK) k_assemble_stiffness(int n_cells, i
     }
 }
 
+__global__ void __launch_bounds__(ASM_BLOCK) k_assemble_stiffness(int n_cells, int n_rows, const int* __restrict__ cells,
+                                                                 const double* __restrict__ vxyz,
+                                                                 const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                                 double* __restrict__ val) {
+    __shared__ double s_ke[ASM_BLOCK * ASM_STRIDE];
+    __shared__ int s_dof[ASM_BLOCK * 8];
+    const int tid = threadIdx.x;
+    const int c = blockIdx.x * ASM_BLOCK + tid;
+    // ---- phase A: element matrix of hexahedron c ----
+    if (c < n_cells) {
+        double X[8], Y[8], Z[8], Ke[36], vol;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int d = __ldg(&cells[8 * (size_t) c + i]);
+            s_dof[8 * tid + i] = d;
+            X[i] = __ldg(&vxyz[3 * (size_t) d]); Y[i] = __ldg(&vxyz[3 * (size_t) d + 1]); Z[i] = __ldg(&vxyz[3 * (size_t) d + 2]);
+        }
+        hex_stiffness(X, Y, Z, Ke, vol);
+#pragma unroll
+        for (int k = 0; k < 36; ++k) s_ke[tid * ASM_STRIDE + k] = Ke[k];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_dof[8 * tid + i] = -1;
+    }
+    __syncthreads();
+    asm_scatter_rows(s_ke, s_dof, n_rows, rowptr, col, val);
+}
+
+// ---------------------------------------------------------------------------------------
+// HeatSolver::assemble_local_cell (CurrentHeatSolver.cpp:346-393), implicit Euler:
+//   K_e(i,j) = sum_q JxW_q ( gamma N_i N_j + kappa(T_q) grad N_i . grad N_j ),  gamma = cu_rho_cp / dt
+//   f_e(i)   = sum_q JxW_q N_i ( gamma T_q + sigma(T_q) |grad phi_q|^2 )
+// T_q / grad phi_q = previous temperature / gradient of the current potential at the Gauss point
+// (FEValues::get_function_values / get_function_gradients); sigma, kappa from the resistivity table
+// (PhysicalQuantities.cpp:31-64,173-185: clamped linear interpolation, Wiedemann-Franz).
+// Same two phases as k_assemble_stiffness; the load vector goes out with 8 atomics per hexahedron.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double pq_resistivity(const double* __restrict__ tab_T, const double* __restrict__ tab_rho, int n, double T) {
+    T = fmin(fmax(T, __ldg(&tab_T[0])), __ldg(&tab_T[n - 1]));
+    if (T <= __ldg(&tab_T[0])) return 10.0 * __ldg(&tab_rho[0]);
+    if (T >= __ldg(&tab_T[n - 1])) return 10.0 * __ldg(&tab_rho[n - 1]);
+    int lo = 0, hi = n;                                   // std::lower_bound: first entry with tab_T >= T
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(&tab_T[mid]) < T) lo = mid + 1; else hi = mid; }
+    const double t1 = __ldg(&tab_T[lo]), t2 = __ldg(&tab_T[lo - 1]), r1 = __ldg(&tab_rho[lo]), r2 = __ldg(&tab_rho[lo - 1]);
+    return 10.0 * (r2 + (r1 - r2) * (T - t2) / (t1 - t2));
+}
+
+__global__ void __launch_bounds__(ASM_BLOCK) k_assemble_heat(int n_cells, int n_rows, const int* __restrict__ cells,
+                                                            const double* __restrict__ vxyz, const int* __restrict__ rowptr,
+                                                            const int* __restrict__ col, double* __restrict__ val, double* __restrict__ rhs,
+                                                            const double* __restrict__ T_prev, const double* __restrict__ phi, double gamma,
+                                                            const double* __restrict__ tab_T, const double* __restrict__ tab_rho, int n_tab,
+                                                            double lorentz) {
+    __shared__ double s_ke[ASM_BLOCK * ASM_STRIDE];
+    __shared__ int s_dof[ASM_BLOCK * 8];
+    const int tid = threadIdx.x;
+    const int c = blockIdx.x * ASM_BLOCK + tid;
+    if (c < n_cells) {
+        double X[8], Y[8], Z[8], Tn[8], Pn[8], Ke[36], Fe[8];
+        int dof[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int d = __ldg(&cells[8 * (size_t) c + i]);
+            dof[i] = d; s_dof[8 * tid + i] = d;
+            X[i] = __ldg(&vxyz[3 * (size_t) d]); Y[i] = __ldg(&vxyz[3 * (size_t) d + 1]); Z[i] = __ldg(&vxyz[3 * (size_t) d + 2]);
+            Tn[i] = T_prev[d]; Pn[i] = phi[d];
+            Fe[i] = 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 36; ++k) Ke[k] = 0;
+        const double ga = 0.5 * (1.0 - 0.57735026918962576451), gb = 0.5 * (1.0 + 0.57735026918962576451);
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) {
+            const double xi = (q & 1) ? gb : ga, eta = (q & 2) ? gb : ga, zeta = (q & 4) ? gb : ga;
+            double N[8], dN[8][3];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const double fx = (i & 1) ? xi : 1.0 - xi, fy = (i & 2) ? eta : 1.0 - eta, fz = (i & 4) ? zeta : 1.0 - zeta;
+                const double sx = (i & 1) ? 1.0 : -1.0, sy = (i & 2) ? 1.0 : -1.0, sz = (i & 4) ? 1.0 : -1.0;
+                N[i] = fx * fy * fz;
+                dN[i][0] = sx * fy * fz; dN[i][1] = fx * sy * fz; dN[i][2] = fx * fy * sz;
+            }
+            double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int e = 0; e < 3; ++e) { J[0][e] += X[i] * dN[i][e]; J[1][e] += Y[i] * dN[i][e]; J[2][e] += Z[i] * dN[i][e]; }
+            const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+            const double c01 = J[1][0] * J[2][2] - J[1][2] * J[2][0];
+            const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+            const double det = J[0][0] * c00 - J[0][1] * c01 + J[0][2] * c02;
+            const double id = 1.0 / det;
+            double inv[3][3];
+            inv[0][0] = c00 * id;
+            inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+            inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+            inv[1][0] = -c01 * id;
+            inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+            inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+            inv[2][0] = c02 * id;
+            inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+            inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+            const double JxW = det * 0.125;
+            double G[8][3], Tq = 0, gp[3] = {0, 0, 0};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) G[i][d] = dN[i][0] * inv[0][d] + dN[i][1] * inv[1][d] + dN[i][2] * inv[2][d];
+                Tq += Tn[i] * N[i];
+                gp[0] += G[i][0] * Pn[i]; gp[1] += G[i][1] * Pn[i]; gp[2] += G[i][2] * Pn[i];
+            }
+            const double sigma = 1.0 / pq_resistivity(tab_T, tab_rho, n_tab, Tq);
+            const double Tc = fmin(fmax(Tq, __ldg(&tab_T[0])), __ldg(&tab_T[n_tab - 1]));
+            const double kappa = lorentz * Tc * sigma;
+            const double src = gamma * Tq + sigma * (gp[0] * gp[0] + gp[1] * gp[1] + gp[2] * gp[2]);
+            int k = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                Fe[i] += JxW * N[i] * src;
+#pragma unroll
+                for (int j = i; j < 8; ++j, ++k)
+                    Ke[k] += JxW * (gamma * N[i] * N[j] + kappa * (G[i][0] * G[j][0] + G[i][1] * G[j][1] + G[i][2] * G[j][2]));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 36; ++k) s_ke[tid * ASM_STRIDE + k] = Ke[k];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (dof[i] < n_rows) atomicAdd(&rhs[dof[i]], Fe[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_dof[8 * tid + i] = -1;
+    }
+    __syncthreads();
+    asm_scatter_rows(s_ke, s_dof, n_rows, rowptr, col, val);
+}
+
 // Neumann faces (DealSolver.cpp:389-430): b_i += sum_q N_i(q) * bc * JxW_face(q), QGauss<2>(2)
 __global__ void k_neumann_faces(int n_faces, int n_rows, const int* __restrict__ face_dofs, const double* __restrict__ vxyz,
-                                double bc_value, double* __restrict__ rhs) {
+                                double bc_uniform, const double* __restrict__ face_bc, double* __restrict__ rhs) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_faces) return;
+    // face_bc: EmissionSolver::get_face_bc (CurrentHeatSolver.h:53-56), one value per face in cell/face iteration order
+    const double bc_value = face_bc ? face_bc[f] : bc_uniform;
     int d[4]; double P[4][3];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -1343,7 +1460,14 @@ void launch_cell_volumes(fb_ctx* c, double* d_cell_vol) {
 void launch_neumann(fb_ctx* c) {
     if (c->n_top_faces == 0) return;
     k_neumann_faces<<<(c->n_top_faces + 127) / 128, 128, 0, c->stream>>>(c->n_top_faces, c->n_dofs, c->d_topfaces.p, c->d_vxyz.p,
-                                                                       c->applied_field, c->d_rhs.p);
+                                                                       c->applied_field, c->mesh_kind ? c->d_face_bc.p : nullptr, c->d_rhs.p);
+    c->launches++;
+}
+
+void launch_assemble_heat(fb_ctx* c, double gamma, const double* d_T_prev, const double* d_phi) {
+    k_assemble_heat<<<(c->n_cells + ASM_BLOCK - 1) / ASM_BLOCK, ASM_BLOCK, 0, c->stream>>>(
+        c->n_cells, c->n_dofs, c->d_cells.p, c->d_vxyz.p, c->d_rowptr.p, c->d_col.p, c->d_val_save.p, c->d_rhs.p, d_T_prev, d_phi, gamma,
+        c->d_res_T.p, c->d_res_rho.p, c->ch_n_table, c->ch_lorentz);
     c->launches++;
 }
 

@@ -71,6 +71,18 @@ SIGNATURES = {
     "fb_plan_jds": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
     "fb_plan_jds_get": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "fb_get_stream": (vp, [vp]),
+    "fb_plan_set_kind": (C.c_int, [vp, C.c_int]),
+    "fb_import_bulk_mesh": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int]),
+    "fb_ch_set_physics": (C.c_int, [vp, vp, vp, C.c_int, C.c_double]),
+    "fb_ch_setup": (C.c_int, [vp, C.c_double]),
+    "fb_export_surface_centroids": (C.c_int, [vp, vp, c_int_p]),
+    "fb_current_assemble": (C.c_int, [vp, vp, C.c_int]),
+    "fb_heat_assemble": (C.c_int, [vp, C.c_double, vp, C.c_int]),
+    "fb_ch_solve": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_int, c_int_p, c_double_p]),
+    "fb_ch_export_solution": (C.c_int, [vp, C.c_int, vp]),
+    "fb_ch_import_solution": (C.c_int, [vp, C.c_int, vp]),
+    "fb_ch_export_solution_grad": (C.c_int, [vp, C.c_int, vp]),
+    "fb_ch_check_limits": (C.c_int, [vp, C.c_int, C.c_double, C.c_double, c_int_p, c_double_p, c_double_p]),
 }
 
 _lib = None

@@ -510,9 +510,11 @@ class PartitionPlan:
         self._check(self.L.fb_plan_phase1(self.h, _p(nodes), len(nodes), _p(hexs), _p(hex_markers), len(hexs), _p(bbox)))
         return bbox                      # local (min xyz, max xyz) of the boundary-face centres
 
-    def import_whole(self, nodes, hexs, hex_markers):
-        """the un-partitioned host import of fb_import_mesh (world 1): complete numbering and sparsity"""
+    def import_whole(self, nodes, hexs, hex_markers, bulk=False):
+        """the un-partitioned host import of fb_import_mesh (world 1): complete numbering and sparsity;
+        bulk=True: the host import of fb_import_bulk_mesh (hexahedra with marker < 0, CurrentHeatSolver::mark_mesh)"""
         nodes = _f(nodes); hexs = _i(hexs); hex_markers = _i(hex_markers)
+        self._check(self.L.fb_plan_set_kind(self.h, int(bulk)))
         self._check(self.L.fb_plan_import(self.h, _p(nodes), len(nodes), _p(hexs), _p(hex_markers), len(hexs)))
         return self._collect()
 
@@ -536,6 +538,14 @@ class PartitionPlan:
         self.__dict__.update(a)
         return self
 
+    def surface_centroids(self):
+        """DealSolver::export_surface_centroids of the imported mesh (copper_surface faces, cell / face order)"""
+        n = C.c_int(0)
+        self._check(self.L.fb_export_surface_centroids(self.h, None, C.byref(n)))
+        out = np.zeros((n.value, 3))
+        self._check(self.L.fb_export_surface_centroids(self.h, _p(out), C.byref(n)))
+        return out
+
     def jds(self, R=512, max_window=8192, sym=False):
         """block-JDS tables of the HBM SpMV for this plan's sparsity (fb_host_jds_build), as numpy arrays"""
         sz = np.zeros(6, np.int64)
@@ -549,3 +559,128 @@ class PartitionPlan:
                                            _p(t["col16"]), _p(t["win_off"]), _p(t["win_list"])))
         t["win_list"] = t["win_list"][:nwin]
         return t
+
+
+@dataclass
+class HeatingConfig:
+    """Subset of Config::Heating used by the current / heat solvers (defaults: src/Config.cpp:73-84)."""
+    lorentz: float = 2.44e-8
+    t_ambient: float = 300.0
+    n_cg: int = 2000
+    cg_tolerance: float = 1e-9
+    ssor_param: float = 1.2         # accepted for config compatibility; the GPU path uses Jacobi
+    T_min: float = 0.0
+    T_max: float = 1e5
+    precond: int = PRECOND_JACOBI
+
+
+class _EmissionSolver:
+    """femocs::EmissionSolver<3> view (CurrentSolver / HeatSolver) of one of the two systems of a CurrentHeatSolver."""
+
+    def __init__(self, parent, which):
+        self.parent, self.which = parent, which
+        self.stat_sol_min = 0.0
+        self.stat_sol_max = 0.0
+        self.last_residual = 0.0
+        self.bc_values = None
+
+    # EmissionSolver::set_bcs (include/CurrentHeatSolver.h:49-51): per-face data in export_surface_centroids order
+    def set_bcs(self, bc_values):
+        self.bc_values = _f(bc_values)
+
+    # CurrentSolver::assemble() (src/CurrentHeatSolver.cpp:420-449) / HeatSolver::assemble(delta_time) (:105-152)
+    def assemble(self, delta_time=None):
+        ctx = self.parent.ctx
+        bc = self.bc_values if self.bc_values is not None else np.zeros(self.parent.n_surface_faces)
+        if self.which == 0:
+            ctx.check(ctx.L.fb_current_assemble(ctx.h, _p(bc), len(bc)))
+        else:
+            ctx.check(ctx.L.fb_heat_assemble(ctx.h, float(delta_time), _p(bc), len(bc)))
+
+    # EmissionSolver::solve (include/CurrentHeatSolver.h:41): +#CG / -#CG
+    def solve(self, n_cg=None, cg_tolerance=None):
+        ctx, conf = self.parent.ctx, self.parent.conf
+        it = C.c_int(0); res = C.c_double(0)
+        ctx.check(ctx.L.fb_ch_solve(ctx.h, self.which, int(conf.n_cg if n_cg is None else n_cg),
+                                    float(conf.cg_tolerance if cg_tolerance is None else cg_tolerance), int(conf.precond),
+                                    C.byref(it), C.byref(res)))
+        self.last_residual = res.value
+        return it.value
+
+    def export_solution(self):
+        ctx = self.parent.ctx
+        out = np.zeros(self.parent.n_vertices)
+        ctx.check(ctx.L.fb_ch_export_solution(ctx.h, self.which, _p(out)))
+        return out
+
+    def import_solution(self, vertex_values):
+        ctx = self.parent.ctx
+        v = _f(vertex_values)
+        assert len(v) == self.parent.n_vertices
+        ctx.check(ctx.L.fb_ch_import_solution(ctx.h, self.which, _p(v)))
+
+    def export_solution_grad(self):
+        ctx = self.parent.ctx
+        out = np.zeros((self.parent.n_vertices, 3))
+        ctx.check(ctx.L.fb_ch_export_solution_grad(ctx.h, self.which, _p(out)))
+        return out
+
+    # DealSolver::check_limits (src/DealSolver.cpp:157-167): True when OUT of limits, like the reference
+    def check_limits(self, lo, hi):
+        ctx = self.parent.ctx
+        bad = C.c_int(0); mn = C.c_double(0); mx = C.c_double(0)
+        ctx.check(ctx.L.fb_ch_check_limits(ctx.h, self.which, float(lo), float(hi), C.byref(bad), C.byref(mn), C.byref(mx)))
+        self.stat_sol_min, self.stat_sol_max = mn.value, mx.value
+        return bool(bad.value)
+
+
+class CurrentHeatSolver:
+    """femocs::CurrentHeatSolver<3> (include/CurrentHeatSolver.h:143-184) behind libfemocs_b200: members `current` and
+    `heat` as in the reference (ProjectRunaway.cpp:542-553: ch_solver.current.assemble(); ch_solver.current.solve();
+    ch_solver.heat.assemble(dt); ch_solver.heat.solve(); ch_solver.heat.check_limits(T_min, T_max))."""
+
+    def __init__(self, ctx, conf=None):
+        self.ctx = ctx
+        self.conf = conf or HeatingConfig()
+        self.current = _EmissionSolver(self, 0)
+        self.heat = _EmissionSolver(self, 1)
+
+    # PhysicalQuantities::resistivity_data rows (T, rho) and Config::Heating::lorentz
+    def set_dependencies(self, table_T, table_rho, lorentz=None):
+        T = _f(table_T); rho = _f(table_rho)
+        self.ctx.check(self.ctx.L.fb_ch_set_physics(self.ctx.h, _p(T), _p(rho), len(T),
+                                                    float(self.conf.lorentz if lorentz is None else lorentz)))
+
+    # CurrentHeatSolver::import_mesh(nodes.export_dealii(), hexs.export_bulk()) (ProjectRunaway.cpp:222)
+    def import_mesh(self, nodes, hexs, hex_markers):
+        nodes = _f(nodes); hexs = _i(hexs); hex_markers = _i(hex_markers)
+        rc = self.ctx.L.fb_import_bulk_mesh(self.ctx.h, _p(nodes), len(nodes), _p(hexs), _p(hex_markers), len(hexs))
+        if rc == 3:
+            return False
+        self.ctx.check(rc)
+        sz = np.zeros(7, np.int64)
+        self.ctx.check(self.ctx.L.fb_get_sizes(self.ctx.h, _p(sz)))
+        (self.n_dofs, self.n_cells, self.nnz, self.n_vertices, self.n_bfaces, self.n_surface_faces, _) = [int(v) for v in sz]
+        return True
+
+    def size(self):
+        return self.n_dofs
+
+    # CurrentHeatSolver::setup(temperature) (src/CurrentHeatSolver.cpp:509-513)
+    def setup(self, temperature):
+        self.ctx.check(self.ctx.L.fb_ch_setup(self.ctx.h, float(temperature)))
+
+    # DealSolver::export_surface_centroids (src/DealSolver.cpp:229-245)
+    def export_surface_centroids(self):
+        n = C.c_int(0)
+        self.ctx.check(self.ctx.L.fb_export_surface_centroids(self.ctx.h, None, C.byref(n)))
+        out = np.zeros((n.value, 3))
+        self.ctx.check(self.ctx.L.fb_export_surface_centroids(self.ctx.h, _p(out), C.byref(n)))
+        return out
+
+    # test hook: the system assembled last, as the reference holds it after apply_boundary_values (fb_get_system)
+    get_system = PoissonSolver.get_system
+
+    # CurrentHeatSolver::export_temp_rho (src/CurrentHeatSolver.cpp:515-523)
+    def export_temp_rho(self):
+        return self.heat.export_solution(), self.current.export_solution_grad()

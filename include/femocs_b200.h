@@ -103,6 +103,9 @@ int fb_plan_interp_tables(fb_ctx* plan, const double* xyz, int n_nodes, const in
 /* host-only: block-JDS tables (R rows per block; sym != 0: lower triangle only) of the plan's sparsity.
  * sizes6 = {blocks, stored slots incl. padding, window entries, longest row, largest window, diagonal offsets} */
 int fb_plan_jds(fb_ctx* plan, int R, int max_window, int sym, long* sizes6);
+/* host-only: mesh kind of the next fb_plan_import: 0 = vacuum hexahedra (fb_import_mesh), 1 = bulk (fb_import_bulk_mesh);
+ * fb_export_surface_centroids works on plan contexts too */
+int fb_plan_set_kind(fb_ctx* plan, int kind);
 int fb_plan_jds_get(const fb_ctx* plan, unsigned short* perm, unsigned short* len, unsigned short* slot, int* jdp, int* jd,
                     int* base, unsigned short* col16, int* win_off, int* win_list);
 
@@ -167,6 +170,46 @@ int fb_check_limits(fb_ctx* ctx, double lo, double hi, int* out_of_limits,
 
 /* double DealSolver::get_cell_vol(i) / int get_n_cells()        src/DealSolver.cpp:169-173 */
 int fb_get_cell_volumes(fb_ctx* ctx, double* vol_cells);
+
+/* ---------------------------------------------------------------------------------------
+ * CurrentHeatSolver<3> on the BULK hexahedra: the current-continuity and heat equations of
+ * ProjectRunaway::solve_heat (src/ProjectRunaway.cpp:535-571), through the same assembly + PCG engine.
+ * `which`: 0 = CurrentSolver (current potential), 1 = HeatSolver (temperature).  One context per mesh kind: a
+ * context that imported a bulk mesh serves fb_ch_* / fb_current_* / fb_heat_* only.
+ * ------------------------------------------------------------------------------------- */
+/* bool CurrentHeatSolver::import_mesh(nodes.export_dealii(), hexs.export_bulk())   src/ProjectRunaway.cpp:222,
+ *   Hexahedra::export_bulk (hex_marker < 0) src/TetgenCells.cpp:688-701, mark_mesh src/CurrentHeatSolver.cpp:526-530:
+ *   top + other -> copper_surface (Neumann faces with per-face data), bottom -> copper_bottom (Dirichlet). */
+int fb_import_bulk_mesh(fb_ctx* ctx, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
+/* PhysicalQuantities::resistivity_data (src/PhysicalQuantityData.cpp:47-, rows {T [K], rho}) and Config::Heating::lorentz:
+ *   sigma(T) = 1 / (10 rho(T)), kappa(T) = lorentz T sigma(T), T clamped to the table (src/PhysicalQuantities.cpp:31-64) */
+int fb_ch_set_physics(fb_ctx* ctx, const double* table_T, const double* table_rho, int n_rows, double lorentz);
+/* void CurrentHeatSolver::setup(double temperature)             src/CurrentHeatSolver.cpp:509-513
+ *   both systems zeroed, current potential = 0, temperature = T_ambient everywhere */
+int fb_ch_setup(fb_ctx* ctx, double T_ambient);
+/* void DealSolver::export_surface_centroids(Medium&)            src/DealSolver.cpp:229-245
+ *   centres of the copper_surface faces in cell / face order = the order of the per-face data below.
+ *   xyz3 may be NULL (count only). */
+int fb_export_surface_centroids(fb_ctx* ctx, double* xyz3, int* n_faces);
+/* void CurrentSolver::assemble()                                src/CurrentHeatSolver.cpp:420-484
+ *   stiffness matrix (sigma = 1), Neumann faces with the emission current densities
+ *   (EmissionSolver::get_face_bc, include/CurrentHeatSolver.h:53-56), phi = 0 on copper_bottom */
+int fb_current_assemble(fb_ctx* ctx, const double* face_current_density, int n_faces);
+/* void HeatSolver::assemble(double delta_time [s])              src/CurrentHeatSolver.cpp:105-152,346-393
+ *   implicit Euler: (cu_rho_cp / dt) M + K_kappa(T_prev); load = (cu_rho_cp / dt) T_prev + sigma(T_prev) |grad phi|^2 with
+ *   phi the current potential solved last; Neumann faces with the Nottingham heat; T = T_ambient on copper_bottom */
+int fb_heat_assemble(fb_ctx* ctx, double delta_time, const double* face_nottingham_heat, int n_faces);
+/* int EmissionSolver::solve()  include/CurrentHeatSolver.h:41 -> DealSolver::solve_cg(conf->n_cg, cg_tolerance, ssor_param);
+ *   the system assembled last; same conventions as fb_poisson_solve (warm start, absolute tolerance, +#CG / -#CG) */
+int fb_ch_solve(fb_ctx* ctx, int which, int max_iter, double abs_tol, int precond, int* n_iter, double* final_residual);
+/* heat.export_solution / current.export_solution / current.export_solution_grad (CurrentHeatSolver::export_temp_rho
+ * src/CurrentHeatSolver.cpp:515-523, Interpolator::extract_solution(CurrentHeatSolver&) src/Interpolator.cpp:210-219),
+ * DealSolver::import_solution (heat_transfer.interpolate_dofs hand-over, src/ProjectRunaway.cpp:282) and
+ * heat.check_limits (src/ProjectRunaway.cpp:553) */
+int fb_ch_export_solution(fb_ctx* ctx, int which, double* vertex_values);
+int fb_ch_import_solution(fb_ctx* ctx, int which, const double* vertex_values);
+int fb_ch_export_solution_grad(fb_ctx* ctx, int which, double* grad3_vertex);
+int fb_ch_check_limits(fb_ctx* ctx, int which, double lo, double hi, int* out_of_limits, double* sol_min, double* sol_max);
 
 /* operator<<(ostream&, const DealSolver&) / to_str()             include/DealSolver.h:107-117
  *   #faces and #edges of the solver mesh (tria->n_active_faces(), n_active_lines()); counted on the host on first use */

@@ -76,7 +76,7 @@ double det4(V3 v1, V3 v2, V3 v3, V3 v4) {
     return d4 - d3 + d2 - d1;
 }
 
-enum { BID_COPPER = 2, BID_SIDES = 4, BID_TOP = 8 };   // Globals.h:60-68
+enum { BID_COPPER = 2, BID_SIDES = 4, BID_TOP = 8, BID_BOTTOM = 7 };   // Globals.h:60-68 (copper_surface, sides, vacuum_top, copper_bottom)
 enum { NODE_TET = 1, NODE_EDGE = 2, NODE_FACE = 3, NODE_TETCENTROID = 4 };  // Globals.h:53-56
 constexpr int TYPE_VACUUM = 3;  // Globals.h TYPES.VACUUM (tet marker of vacuum tets)
 
@@ -103,6 +103,11 @@ struct Oracle {
     double applied_field = 0, applied_potential = 0;
     int anode_dirichlet = 0;
     double last_res = 0;
+    // ---------------- CurrentHeatSolver (bulk mesh: mesh_kind == 1) ----------------
+    int mesh_kind = 0;                           // 0 = vacuum hexes (PoissonSolver), 1 = bulk hexes (CurrentHeatSolver)
+    std::vector<double> ch_current, ch_heat;     // CurrentSolver::solution, HeatSolver::solution (dof order)
+    std::vector<double> res_T, res_rho;          // PhysicalQuantities::resistivity_data
+    double lorentz = 2.44e-8, ch_T_ambient = 300.0;
 
     // ---------------- interpolator (Interpolator / InterpolatorCells) ----------------
     std::vector<Sol> nodal;                      // InterpolatorNodes::solutions
@@ -194,12 +199,18 @@ void cell_geometry(const Oracle& o, int cell, int q, double& JxW, V3 grad[8]) {
 
 // TetgenCells.cpp:673-686 (export_vacuum), DealSolver.cpp:191-209 (import_mesh),
 // :460-518 (mark_boundary), PoissonSolver.cpp:52-55 (mark_mesh), DealSolver.cpp:368-387 (setup_system)
-int import_mesh(Oracle& o, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {
+// kind 1: TetgenCells.cpp:688-701 (export_bulk: marker < 0) and CurrentHeatSolver.cpp:526-530 mark_mesh
+// (top -> copper_surface, bottom -> copper_bottom, sides -> copper_sides, other -> copper_surface)
+int import_mesh(Oracle& o, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker_in, int n_hex, int kind = 0) {
+    o.mesh_kind = kind;
+    std::vector<int> sel(n_hex);                 // > 0: the hexahedron belongs to this solver's mesh
+    for (int h = 0; h < n_hex; ++h) sel[h] = kind ? (hex_marker_in[h] < 0) : (hex_marker_in[h] > 0);
+    const int* hex_marker = sel.data();
     o.n_nodes = n_nodes; o.n_hex = n_hex;
     o.xyz.resize(n_nodes);
     for (int i = 0; i < n_nodes; ++i) o.xyz[i] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
     o.hex8.assign(hex8, hex8 + 8 * (size_t) n_hex);
-    o.hex_marker.assign(hex_marker, hex_marker + n_hex);
+    o.hex_marker.assign(hex_marker_in, hex_marker_in + n_hex);
 
     // GridTools::delete_unused_vertices: order-preserving compaction (InterpolatorCells.cpp:50-65)
     o.node2vert.assign(n_nodes, -1);
@@ -287,8 +298,8 @@ int import_mesh(Oracle& o, const double* xyz, int n_nodes, const int* hex8, cons
     for (auto& bf : o.bfaces) {
         const V3 p = face_center(bf.cell, bf.face);
         if (on_b(p.x, xmin) || on_b(p.x, xmax) || on_b(p.y, ymin) || on_b(p.y, ymax)) bf.id = BID_SIDES;
-        else if (on_b(p.z, zmax)) bf.id = BID_TOP;
-        else if (on_b(p.z, zmin)) bf.id = BID_COPPER;   // "bottom" = copper_surface, PoissonSolver.cpp:52-55
+        else if (on_b(p.z, zmax)) bf.id = kind ? BID_COPPER : BID_TOP;
+        else if (on_b(p.z, zmin)) bf.id = kind ? BID_BOTTOM : BID_COPPER;   // "bottom" = copper_surface, PoissonSolver.cpp:52-55
         else bf.id = BID_COPPER;                       // "other"  = copper_surface
     }
 
@@ -372,11 +383,13 @@ void assemble_matrix(Oracle& o) {
 }
 
 // DealSolver.cpp:389-430 assemble_rhs(bid) with get_face_bc = applied_field (PoissonSolver.cpp:152-154)
-void assemble_rhs_faces(Oracle& o, int bid) {
+// face_bc != nullptr: EmissionSolver::get_face_bc = (*bc_values)[boundary_face_index++] (CurrentHeatSolver.h:53-56)
+void assemble_rhs_faces(Oracle& o, int bid, const double* face_bc = nullptr) {
     const double g[2] = {0.5 * (1.0 - 1.0 / std::sqrt(3.0)), 0.5 * (1.0 + 1.0 / std::sqrt(3.0))};
+    int boundary_face_index = 0;
     for (const auto& bf : o.bfaces) {
         if (bf.id != bid) continue;
-        const double bc_value = o.applied_field;
+        const double bc_value = face_bc ? face_bc[boundary_face_index++] : o.applied_field;
         V3 p[4];
         for (int v = 0; v < 4; ++v) p[v] = cell_vertex(o, bf.cell, FACE_VERTS[bf.face][v]);
         double cell_rhs[4] = {0, 0, 0, 0};
@@ -579,6 +592,98 @@ int solve_cg(Oracle& o, int max_iter, double tol, double ssor_param, int precond
             for (int i = 0; i < n; ++i) d[i] = beta * d[i] - g[i];
         }
     }
+}
+
+// ============================================================================
+//  CurrentHeatSolver on the bulk mesh.  Same deal.II semantics as above: parity unpinned.
+// ============================================================================
+
+// PhysicalQuantities.cpp:173-185 linear_interp over resistivity_data
+double pq_linear_interp(const Oracle& o, double x) {
+    const int n = (int) o.res_T.size();
+    if (x <= o.res_T[0]) return o.res_rho[0];
+    if (x >= o.res_T[n - 1]) return o.res_rho[n - 1];
+    const int i1 = (int) (std::lower_bound(o.res_T.begin(), o.res_T.end(), x) - o.res_T.begin());
+    const int i2 = i1 - 1;
+    return o.res_rho[i2] + (o.res_rho[i1] - o.res_rho[i2]) * (x - o.res_T[i2]) / (o.res_T[i1] - o.res_T[i2]);
+}
+// PhysicalQuantities.cpp:31-37 evaluate_resistivity, :47-50 sigma
+double pq_sigma(const Oracle& o, double T) {
+    if (T < o.res_T.front()) T = o.res_T.front();
+    if (T > o.res_T.back()) T = o.res_T.back();
+    return 1.0 / (10. * pq_linear_interp(o, T));
+}
+// PhysicalQuantities.cpp:57-64 kappa (Wiedemann-Franz)
+double pq_kappa(const Oracle& o, double T) {
+    if (T < o.res_T.front()) T = o.res_T.front();
+    if (T > o.res_T.back()) T = o.res_T.back();
+    return o.lorentz * T * pq_sigma(o, T);
+}
+
+// CurrentHeatSolver.cpp:509-513 setup(temperature): heat.dirichlet_bc_value = T; both setup_system()
+// (DealSolver.cpp:368-387: solution = dirichlet_bc_value, boundary_values cleared)
+void ch_setup(Oracle& o, double T_ambient) {
+    o.ch_T_ambient = T_ambient;
+    o.ch_current.assign(o.n_dofs, 0.0);
+    o.ch_heat.assign(o.n_dofs, T_ambient);
+    o.boundary_values.clear();
+}
+
+// CurrentHeatSolver.cpp:420-449 CurrentSolver::assemble + :451-484 assemble_local_cell (sigma = 1)
+void current_assemble(Oracle& o, const double* face_bc) {
+    std::fill(o.val.begin(), o.val.end(), 0.0);
+    std::fill(o.rhs.begin(), o.rhs.end(), 0.0);
+    assemble_matrix(o);
+    assemble_rhs_faces(o, BID_COPPER, face_bc);
+    o.boundary_values.clear();
+    append_dirichlet(o, BID_BOTTOM, 0.0);                  // current.dirichlet_bc_value = 0 (DealSolver.cpp:38)
+    o.sol = o.ch_current;
+    apply_dirichlet(o);
+    o.ch_current = o.sol;
+}
+
+// CurrentHeatSolver.cpp:105-152 HeatSolver::assemble(delta_time) + :346-393 assemble_local_cell (implicit Euler)
+void heat_assemble(Oracle& o, double delta_time, const double* face_bc) {
+    const double cu_rho_cp = 3.4496e-24;                   // CurrentHeatSolver.h:118
+    const double gamma = cu_rho_cp * (1.0 / delta_time);
+    std::fill(o.val.begin(), o.val.end(), 0.0);
+    std::fill(o.rhs.begin(), o.rhs.end(), 0.0);
+    const int n_cells = (int) o.cells.size();
+    for (int c = 0; c < n_cells; ++c) {
+        int dofs[8];
+        for (int i = 0; i < 8; ++i) dofs[i] = o.vertex2dof[o.cells[c][i]];
+        double Ke[8][8] = {}, Fe[8] = {};
+        double JxW[8]; V3 g[8][8]; double prev_T[8]; V3 pot_grad[8];
+        for (int q = 0; q < 8; ++q) {
+            cell_geometry(o, c, q, JxW[q], g[q]);
+            prev_T[q] = 0; pot_grad[q] = V3();
+            for (int i = 0; i < 8; ++i) {                  // get_function_values / get_function_gradients
+                prev_T[q] += o.ch_heat[dofs[i]] * REFCUBE.N[q][i];
+                pot_grad[q] = pot_grad[q] + g[q][i] * o.ch_current[dofs[i]];
+            }
+        }
+        for (int q = 0; q < 8; ++q) {
+            const double kappa = pq_kappa(o, prev_T[q]);
+            for (int i = 0; i < 8; ++i)
+                for (int j = 0; j < 8; ++j)
+                    Ke[i][j] += JxW[q] * (gamma * REFCUBE.N[q][i] * REFCUBE.N[q][j] + kappa * dot(g[q][i], g[q][j]));
+        }
+        for (int q = 0; q < 8; ++q) {
+            const double pot_grad_squared = dot(pot_grad[q], pot_grad[q]);
+            const double sigma = pq_sigma(o, prev_T[q]);
+            for (int i = 0; i < 8; ++i) Fe[i] += JxW[q] * REFCUBE.N[q][i] * (gamma * prev_T[q] + sigma * pot_grad_squared);
+        }
+        for (int i = 0; i < 8; ++i) {                      // DealSolver.cpp:64-72 copy_global_cell
+            o.rhs[dofs[i]] += Fe[i];
+            for (int j = 0; j < 8; ++j) o.val[csr_pos(o, dofs[i], dofs[j])] += Ke[i][j];
+        }
+    }
+    assemble_rhs_faces(o, BID_COPPER, face_bc);
+    o.boundary_values.clear();
+    append_dirichlet(o, BID_BOTTOM, o.ch_T_ambient);
+    o.sol = o.ch_heat;
+    apply_dirichlet(o);
+    o.ch_heat = o.sol;
 }
 
 // ============================================================================
@@ -1030,6 +1135,52 @@ int fo_solve(void* h, int max_iter, double tol, double ssor, int precond, double
     if (res) *res = o.last_res;
     return it;
 }
+// ---- CurrentHeatSolver (bulk mesh) ----
+int fo_import_mesh_kind(void* h, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex, int kind) {
+    return import_mesh(*(Oracle*) h, xyz, n_nodes, hex8, hex_marker, n_hex, kind);
+}
+void fo_ch_set_physics(void* h, const double* T, const double* rho, int n, double lorentz) {
+    Oracle& o = *(Oracle*) h; o.res_T.assign(T, T + n); o.res_rho.assign(rho, rho + n); o.lorentz = lorentz;
+}
+double fo_ch_sigma(void* h, double T) { return pq_sigma(*(Oracle*) h, T); }
+double fo_ch_kappa(void* h, double T) { return pq_kappa(*(Oracle*) h, T); }
+void fo_ch_setup(void* h, double T_ambient) { ch_setup(*(Oracle*) h, T_ambient); }
+void fo_current_assemble(void* h, const double* face_bc) { current_assemble(*(Oracle*) h, face_bc); }
+void fo_heat_assemble(void* h, double delta_time, const double* face_bc) { heat_assemble(*(Oracle*) h, delta_time, face_bc); }
+// EmissionSolver::solve (CurrentHeatSolver.h:41): solve_cg(conf->n_cg, conf->cg_tolerance, conf->ssor_param) on the system assembled last
+int fo_ch_solve(void* h, int which, int max_iter, double tol, double ssor, int precond, double* res) {
+    Oracle& o = *(Oracle*) h;
+    o.sol = which ? o.ch_heat : o.ch_current;
+    const int it = solve_cg(o, max_iter, tol, ssor, precond);
+    (which ? o.ch_heat : o.ch_current) = o.sol;
+    if (res) *res = o.last_res;
+    return it;
+}
+// which: 0 = current potential, 1 = temperature; dof order
+void fo_ch_get_solution(void* h, int which, double* out) {
+    Oracle& o = *(Oracle*) h; const auto& v = which ? o.ch_heat : o.ch_current; std::copy(v.begin(), v.end(), out);
+}
+void fo_ch_set_solution(void* h, int which, const double* in) {
+    Oracle& o = *(Oracle*) h; auto& v = which ? o.ch_heat : o.ch_current; v.assign(in, in + o.n_dofs);
+}
+// makes `which` the solution that fo_export_solution / fo_export_solution_grad / fo_check_limits read
+void fo_ch_select(void* h, int which) { Oracle& o = *(Oracle*) h; o.sol = which ? o.ch_heat : o.ch_current; }
+// DealSolver.cpp:229-245 export_surface_centroids: centres of the copper_surface faces, cell/face iteration order
+int fo_surface_centroids(void* h, double* xyz3) {
+    Oracle& o = *(Oracle*) h; int n = 0;
+    for (const auto& bf : o.bfaces) {
+        if (bf.id != BID_COPPER) continue;
+        if (xyz3) {
+            V3 s;
+            for (int v = 0; v < 4; ++v) s = s + cell_vertex(o, bf.cell, FACE_VERTS[bf.face][v]);
+            s = s / 4.0;
+            xyz3[3 * n] = s.x; xyz3[3 * n + 1] = s.y; xyz3[3 * n + 2] = s.z;
+        }
+        ++n;
+    }
+    return n;
+}
+
 // out: n_dofs, n_cells, nnz, n_vertices, n_boundary_faces
 void fo_sizes(void* h, long* out) {
     Oracle& o = *(Oracle*) h;

@@ -65,6 +65,18 @@ def lib():
         L.fo_particle_weights.argtypes = [C.c_void_p, C.c_long, _dp, _ip, _dp]
         L.fo_linhex_locate.argtypes = [C.c_void_p, C.c_long, _dp, _ip]
         L.fo_nodal_gradient.argtypes = [C.c_void_p, C.c_long, _ip, _ip, _dp]
+        L.fo_import_mesh_kind.argtypes = [C.c_void_p, _dp, C.c_int, _ip, _ip, C.c_int, C.c_int]
+        L.fo_ch_set_physics.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double]
+        L.fo_ch_sigma.argtypes = [C.c_void_p, C.c_double]; L.fo_ch_sigma.restype = C.c_double
+        L.fo_ch_kappa.argtypes = [C.c_void_p, C.c_double]; L.fo_ch_kappa.restype = C.c_double
+        L.fo_ch_setup.argtypes = [C.c_void_p, C.c_double]
+        L.fo_current_assemble.argtypes = [C.c_void_p, _dp]
+        L.fo_heat_assemble.argtypes = [C.c_void_p, C.c_double, _dp]
+        L.fo_ch_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double)]
+        L.fo_ch_get_solution.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.fo_ch_set_solution.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.fo_ch_select.argtypes = [C.c_void_p, C.c_int]
+        L.fo_surface_centroids.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -101,6 +113,59 @@ class Oracle:
         sz = np.zeros(5, np.int64)
         self.L.fo_sizes(self.h, sz)
         self.n_dofs, self.n_cells, self.nnz, self.n_vertices, self.n_bfaces = [int(v) for v in sz]
+
+    # ---- CurrentHeatSolver on the bulk hexahedra (CurrentHeatSolver.cpp) -----------
+    def import_bulk_mesh(self, nodes, hexs, hex_markers):
+        nodes = _f(nodes); hexs = _i(hexs); hex_markers = _i(hex_markers)
+        self.n_nodes = len(nodes)
+        rc = self.L.fo_import_mesh_kind(self.h, nodes.reshape(-1), len(nodes), hexs.reshape(-1), hex_markers, len(hexs), 1)
+        if rc:
+            raise RuntimeError("oracle import_mesh (bulk) failed rc=%d" % rc)
+        sz = np.zeros(5, np.int64)
+        self.L.fo_sizes(self.h, sz)
+        self.n_dofs, self.n_cells, self.nnz, self.n_vertices, self.n_bfaces = [int(v) for v in sz]
+
+    def ch_set_physics(self, T, rho, lorentz=2.44e-8):
+        T = _f(T); rho = _f(rho)
+        self.L.fo_ch_set_physics(self.h, T, rho, len(T), lorentz)
+
+    def ch_setup(self, T_ambient):
+        self.L.fo_ch_setup(self.h, T_ambient)
+
+    def surface_centroids(self):
+        n = self.L.fo_surface_centroids(self.h, None)
+        out = np.zeros((n, 3))
+        self.L.fo_surface_centroids(self.h, out.ctypes.data)
+        return out
+
+    def current_assemble(self, face_bc):
+        self.L.fo_current_assemble(self.h, _f(face_bc))
+
+    def heat_assemble(self, delta_time, face_bc):
+        self.L.fo_heat_assemble(self.h, delta_time, _f(face_bc))
+
+    def ch_solve(self, which, max_iter=2000, tol=1e-9, ssor=1.2, precond=0):
+        res = C.c_double(0)
+        it = self.L.fo_ch_solve(self.h, which, max_iter, tol, ssor, precond, C.byref(res))
+        self.last_res = res.value
+        return it
+
+    def ch_solution(self, which):
+        out = np.zeros(self.n_dofs)
+        self.L.fo_ch_get_solution(self.h, which, out)
+        return out
+
+    def ch_set_solution(self, which, v):
+        self.L.fo_ch_set_solution(self.h, which, _f(v))
+
+    def ch_select(self, which):
+        self.L.fo_ch_select(self.h, which)
+
+    def sigma(self, T):
+        return self.L.fo_ch_sigma(self.h, T)
+
+    def kappa(self, T):
+        return self.L.fo_ch_kappa(self.h, T)
 
     def setup(self, field, potential=0.0, anode_dirichlet=False):
         self.L.fo_setup(self.h, field, potential, int(anode_dirichlet))

@@ -39,3 +39,30 @@ def test_mixed_orientation_is_refused():
         _plan(nodes, bad, mk)
     with pytest.raises(RuntimeError):
         Oracle().import_mesh(nodes, bad, mk)
+
+
+@pytest.mark.parametrize("name", ["hemicone", "mdsmall"])
+def test_bulk_mesh_import_matches_oracle(name, golden):
+    """fb_import_bulk_mesh's host half (Hexahedra::export_bulk selection, CurrentHeatSolver::mark_mesh boundary roles,
+    numbering, sparsity, face order of export_surface_centroids) against the oracle restatement"""
+    m = golden("mesh", name)
+    o = Oracle(); o.import_bulk_mesh(m["nodes"], m["hexs"], m["hex_markers"])
+    a = PartitionPlan(0, 1).import_whole(m["nodes"], m["hexs"], m["hex_markers"], bulk=True)
+    assert (a.n_rows, a.n_cells, a.nnz) == (o.n_dofs, o.n_cells, o.nnz)
+    assert a.n_cells == int((m["hex_markers"] < 0).sum())
+    rp, col, _, _ = o.csr()
+    assert np.array_equal(a.rowptr, rp) and np.array_equal(a.col, col)
+    v2d = o.vectors()[2]
+    assert np.array_equal(v2d[o.cells()], a.cells_dof)
+    # Dirichlet set = dofs of the copper_bottom faces (BoundaryID 7); no "top" role on the bulk mesh
+    cell, face, bid = o.bfaces()
+    FV = np.array([[0, 2, 4, 6], [1, 3, 5, 7], [0, 1, 4, 5], [2, 3, 6, 7], [0, 1, 2, 3], [4, 5, 6, 7]])
+    bottom = np.zeros(o.n_dofs, np.int32)
+    sel = bid == 7
+    bottom[a.cells_dof[cell[sel]][np.arange(sel.sum())[:, None], FV[face[sel]]].ravel()] = 1
+    assert sel.sum() > 0 and np.array_equal(a.copper, bottom) and a.top.sum() == 0
+    cen = a.surface_centroids()
+    assert np.array_equal(cen, o.surface_centroids()) and len(cen) == int((bid == 2).sum()) == len(m["quads"])
+    # the vacuum import of the same arrays is untouched by the bulk option
+    b = PartitionPlan(0, 1).import_whole(m["nodes"], m["hexs"], m["hex_markers"])
+    assert b.n_cells == int((m["hex_markers"] > 0).sum())
