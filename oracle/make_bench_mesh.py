@@ -1,4 +1,4 @@
-"""TEST/BENCH INFRASTRUCTURE -- regenerates tests/golden/bench_x90.npz from the reference's own mesher.
+"""TEST/BENCH INFRASTRUCTURE -- regenerates tests/golden/bench_x90.npz and mesh_tip110.npz from the reference's own mesher.
 
 Run in the build container (needs /root/reference and oracle/_ref/libfemocs_ref.so):
 
@@ -33,6 +33,15 @@ def main():
     out = os.path.join(ROOT, "tests", "golden", "bench_x90.npz")
     np.savez_compressed(out, nodes=m["nodes"][used], hexs=remap[hexs].astype(np.int32))
     print(out, "hexes", len(hexs), "vertices", len(used), "%.1f MB" % (os.path.getsize(out) / 1e6))
+    # config 5 ("ProjectHeat coupled Poisson + current/heat on tip110.ckx"): the complete mesh of the Main.cpp:216-220
+    # preset (vacuum AND bulk hexahedra, tetrahedra, surface triangles / quadrangles, surface atoms); the full atom
+    # list is not needed by the bench leg and is left out
+    m = RefLib().generate("tip110")
+    m.pop("atoms", None)
+    out = os.path.join(ROOT, "tests", "golden", "mesh_tip110.npz")
+    np.savez_compressed(out, **m)
+    print(out, "vacuum hexes", int((m["hex_markers"] > 0).sum()), "bulk hexes", int((m["hex_markers"] < 0).sum()),
+          "%.1f MB" % (os.path.getsize(out) / 1e6))
 
 
 if __name__ == "__main__":
