@@ -333,6 +333,8 @@ def run_b200(args):
     ctx.set_option("cg_profile", 32)
     if args.dof_order is not None:
         ctx.set_option("dof_order", args.dof_order)
+    if args.cg_p2p is not None:
+        ctx.set_option("cg_p2p", args.cg_p2p)
     solver = fb.PoissonSolver(ctx, fb.FieldConfig(E0=E0, cg_tolerance=CG_TOL, n_cg=N_CG, mode="transient"))
     t0 = time.perf_counter()
     assert solver.import_mesh(nodes, hexs, mk), "import_mesh failed"
@@ -432,8 +434,12 @@ def run_b200(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args),
         "sizes": {"n_dofs": n, "nnz": int(nnz_all), "n_cells": part["n_cells_global"],
-                  "parallelism": ("element-partitioned over %d GPUs (RCB), NCCL p2p halo + all-reduce; rank 0: %d rows, %d ghosts, %d halo values sent"
-                                  % (world, part["n_rows"], part["n_ghost"], part["n_send"])) if world > 1 else "1 GPU",
+                  "parallelism": ("element-partitioned over %d GPUs (RCB), %s; rank 0: %d rows, %d ghosts, %d halo values sent"
+                                  % (world, {2: "peer-mapped iteration: halo values and dot-product sums stored into the peers' memory over NVLink by the kernels, "
+                                                "4 kernels per iteration in a CUDA graph, no NCCL inside the loop",
+                                             1: "NCCL inside the iteration (grouped send/recv halo + 2 all-reduces, host-issued)"}.get(ctx.comm_mode, "?"),
+                                     part["n_rows"], part["n_ghost"], part["n_send"])) if world > 1 else "1 GPU",
+                  "comm_mode": ctx.comm_mode,
                   "cg_iterations_per_step": its, "converged": bool(all(i > 0 for i in its)), "seconds_per_step": ms / args.steps * 1e-3,
                   "preconditioner": "Jacobi", "import_mesh_s": import_s},
         "verified": verified,
@@ -1013,6 +1019,7 @@ def main():
     ap.add_argument("--levels", type=int, default=2, help="uniform refinements of the X base mesh (2 = 2.3e7 DoF)")
     ap.add_argument("--particles", type=int, default=1000000)
     ap.add_argument("--dof-order", type=int, default=None)
+    ap.add_argument("--cg-p2p", type=int, default=None, help="0: NCCL inside the partitioned CG iteration instead of the peer-mapped mode")
     ap.add_argument("--skip-native", action="store_true")
     ap.add_argument("--only", default=None, choices=["native", "pic", "heat"],
                     help="development aid: run ONE sub-benchmark alone and print its object (not the contract line)")

@@ -58,6 +58,70 @@ static int allreduce(fb_ctx* c, double* buf, int n, ncclRedOp_t op) {
     return FB_OK;
 }
 
+// ---- peer-mapped iteration: CUDA IPC mappings of every peer's search-direction vector and slot
+// record, exchanged once per partitioned import with ncclAllGather.  Collective: every rank leaves with the same verdict
+// (p2p_ready on all ranks or on none), otherwise the ranks would run different iteration protocols.
+static void p2p_release(fb_ctx* c) {
+    for (void* m : c->p2p_mapped) cudaIpcCloseMemHandle(m);
+    c->p2p_mapped.clear();
+    c->p2p_ready = false;
+}
+
+static int p2p_setup(fb_ctx* c) {
+    using fb::P2P_MAX;
+    c->p2p_ready = false;
+    if (c->world <= 1 || c->world > P2P_MAX) return FB_OK;
+    struct Rec { cudaIpcMemHandle_t vec, slots; int n_dofs, ok; int recv_off[P2P_MAX + 1]; };
+    cudaStream_t s = c->stream;
+    const int W = c->world, me = c->rank;
+    Rec mine; memset(&mine, 0, sizeof mine);
+    mine.ok = c->cg_p2p ? 1 : 0;
+    if (mine.ok && (c->d_p2p_slots.alloc(1) != cudaSuccess || c->d_p2p.alloc(1) != cudaSuccess || c->d_p2p_counter.alloc(1) != cudaSuccess)) mine.ok = 0;
+    if (mine.ok) { c->d_p2p_slots.zero(s); c->d_p2p_counter.zero(s); }
+    if (mine.ok && cudaIpcGetMemHandle(&mine.vec, c->d_d.p) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
+    if (mine.ok && cudaIpcGetMemHandle(&mine.slots, c->d_p2p_slots.p) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
+    mine.n_dofs = c->n_dofs;
+    for (int p = 0; p <= W; ++p) mine.recv_off[p] = c->recv_off[p];
+    fb::DevBuf<unsigned char> d_all;
+    FB_CUDA(c, d_all.alloc(sizeof(Rec) * (size_t) W));
+    FB_CUDA(c, cudaMemcpyAsync(d_all.p + sizeof(Rec) * (size_t) me, &mine, sizeof(Rec), cudaMemcpyHostToDevice, s));
+    FB_NCCL(c, fb::Nccl::get().AllGather(d_all.p + sizeof(Rec) * (size_t) me, d_all.p, sizeof(Rec), ncclChar, (ncclComm_t) c->nccl_comm, s));
+    std::vector<Rec> all(W);
+    FB_CUDA(c, cudaMemcpyAsync(all.data(), d_all.p, sizeof(Rec) * (size_t) W, cudaMemcpyDeviceToHost, s));
+    FB_CUDA(c, cudaStreamSynchronize(s));
+    bool ok = true;
+    for (int p = 0; p < W; ++p) ok = ok && all[p].ok;
+    fb::P2pDesc D; memset(&D, 0, sizeof D);
+    D.rank = me; D.world = W;
+    if (ok) {
+        for (int p = 0; p < W && ok; ++p) {
+            if (p == me) { D.slots[p] = c->d_p2p_slots.p; D.peer_vec[p] = c->d_d.p; continue; }
+            void* pv = nullptr; void* ps = nullptr;
+            if (cudaIpcOpenMemHandle(&pv, all[p].vec, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+            c->p2p_mapped.push_back(pv);
+            if (cudaIpcOpenMemHandle(&ps, all[p].slots, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+            c->p2p_mapped.push_back(ps);
+            D.peer_vec[p] = (double*) pv; D.slots[p] = (fb::P2pSlots*) ps;
+            D.dst_base[p] = all[p].n_dofs + all[p].recv_off[me];
+        }
+    }
+    // second round: a rank that could not map a peer vetoes the mode for everybody
+    double* hb = (double*) c->pin_out.p;
+    hb[0] = ok ? 1.0 : 0.0;
+    FB_CUDA(c, cudaMemcpyAsync(c->d_red.p, hb, sizeof(double), cudaMemcpyHostToDevice, s));
+    int rc = allreduce(c, c->d_red.p, 1, ncclMin);
+    if (rc) return rc;
+    FB_CUDA(c, cudaMemcpyAsync(hb, c->d_red.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    FB_CUDA(c, cudaStreamSynchronize(s));
+    if (hb[0] != 1.0) { p2p_release(c); return FB_OK; }
+    for (int p = 0; p <= W; ++p) D.send_off[p] = c->send_off[p];
+    for (int p = 0; p < W; ++p) D.n_recv[p] = c->recv_off[p + 1] - c->recv_off[p];
+    FB_CUDA(c, cudaMemcpyAsync(c->d_p2p.p, &D, sizeof D, cudaMemcpyHostToDevice, s));
+    FB_CUDA(c, cudaStreamSynchronize(s));
+    c->p2p_ready = true;
+    return FB_OK;
+}
+
 extern "C" {
 
 const char* fb_create_error(void) { return g_create_error.c_str(); }
@@ -94,6 +158,7 @@ void fb_destroy(fb_ctx* c) {
     if (!c) return;
     if (c->host_only) { delete c; return; }
     cudaSetDevice(c->device);
+    p2p_release(c);
     if (c->nccl_comm) { cudaStreamSynchronize(c->stream); fb::Nccl::get().CommDestroy((ncclComm_t) c->nccl_comm); c->nccl_comm = nullptr; }
     drop_graph(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -118,6 +183,7 @@ int fb_set_option(fb_ctx* c, const char* key, double value) {
     else if (k == "spmv_kernel") { c->spmv_kernel = (int) value; drop_graph(c); }
     else if (k == "cg_persistent") c->cg_persistent = (int) value;
     else if (k == "cg_debug") c->cg_debug = (int) value;
+    else if (k == "cg_p2p") c->cg_p2p = (int) value;          // read by the next partitioned fb_import_mesh
     else if (k == "cg_persistent_ctas") { c->pers_ctas = (int) value; c->pers_grid = 0; }
     else if (k == "cg_profile") c->cg_profile = std::max(0, std::min(4096, (int) value));
     else return c->fail(FB_ERR_ARG, "unknown option %s", key);
@@ -293,6 +359,7 @@ static int import_mesh_impl(fb_ctx* c, const double* xyz, int n_nodes, const int
     if (c->world > 1) {
         // partitioned import: local sub-mesh, extremes of the boundary-face centres reduced over the ranks
         FB_REQUIRE(c, c->nccl_comm, "fb_import_mesh: fb_comm_init has not been called");
+        p2p_release(c);     // peers' mappings of the previous mesh go first (the collective below orders this before any re-allocation)
         // a rank-local failure (e.g. "rank owns no vertices") must not leave the other ranks waiting in the collective:
         // the error flag travels with the extremes and every rank leaves with the same verdict
         const int rc_local = fb_host_partition_phase1(c, xyz, n_nodes, hex8, hex_marker, n_hex);
@@ -358,6 +425,7 @@ static int import_mesh_impl(fb_ctx* c, const double* xyz, int n_nodes, const int
         for (int lc = 0; lc < c->n_cells; ++lc) g2l[c->part_cell_g[lc]] = lc;
         FB_CUDA(c, c->d_gcell2local.upload(g2l, s));
         FB_CUDA(c, cudaStreamSynchronize(s));
+        if ((rc = p2p_setup(c))) return rc;
     }
     return sync_check(c, "fb_import_mesh");
 }
@@ -454,7 +522,7 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
     long spmv = 1;
     c->prof_samples = 0; c->prof_spmv_ms = c->prof_vec_ms = 0;
     const bool persistent = c->world == 1 && c->cg_profile == 0 && !cheb && fb::persistent_eligible(c);
-    if (c->world > 1) h->red = c->d_red.p;
+    if (c->world > 1) { h->red = c->d_red.p; if (c->p2p_ready) h->p2p = c->d_p2p.p; }
     FB_CUDA(c, cudaEventRecord(c->ev0, s));
     FB_CUDA(c, cudaMemcpyAsync(c->d_cg.p, h, sizeof(fb::CgScalars), cudaMemcpyHostToDevice, s));
     c->last_kernel = -2;
@@ -533,8 +601,8 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
             }
         }
         c->last_kernel = lanes;
-        if (c->world > 1) {
-            // ---- partitioned CG: halo exchange of the SpMV input over NVLink (NCCL point-to-point) and one
+        if (c->world > 1 && !c->p2p_ready) {
+            // ---- partitioned CG, NCCL mode (fallback when the peers' memory cannot be mapped): halo exchange of the SpMV input over NVLink (NCCL point-to-point) and one
             //      all-reduce per dot-product pair; same operation order as on one GPU ----
             int rc;
             if ((rc = halo_exchange(c, c->d_x.p))) return rc;
@@ -595,7 +663,14 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
                 graph_key = lanes + 1000 * c->cheb_k;
                 FB_CUDA(c, cudaMemcpyAsync(c->d_cg.p, h, sizeof(fb::CgScalars), cudaMemcpyHostToDevice, s));   // cheb_prepare may have used the stream
             }
-            fb::launch_cg_init(c, lanes);
+            // partitioned, peer-mapped mode: the initial residual needs the ghosts of x (NCCL, once per solve); inside the
+            // iteration the halo of d and the two all-reduces travel over the peer mappings, so the loop below -- graph
+            // capture included -- is the single-GPU one with k_pack_p2p in front of every SpMV
+            if (c->world > 1) {
+                const int rc = halo_exchange(c, c->d_x.p); if (rc) return rc;
+                fb::launch_cg_init_spmv(c, lanes); fb::launch_cg_scalars(c, 0); fb::launch_cg_init_direction(c);
+            } else
+                fb::launch_cg_init(c, lanes);
             // CUDA graph of cg_graph_iters iterations; kernels become no-ops once cgs->done is set
             if (!c->cg_graph || c->cg_graph_n != c->cg_graph_iters || c->cg_graph_precond != graph_key) {
                 drop_graph(c);
@@ -620,6 +695,13 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
                 n_prof = std::min(c->cg_profile, std::max(0, max_iter));
                 for (int i = 0; i < n_prof; ++i) {
                     FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i], s));
+                    if (c->world > 1) {
+                        fb::launch_pack_p2p(c, c->d_d.p); fb::launch_cg_spmv(c, lanes); fb::launch_cg_scalars(c, 1);
+                        FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i + 1], s));
+                        fb::launch_cg_update_only(c); fb::launch_cg_scalars(c, 2); fb::launch_cg_direction_only(c);
+                        FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i + 2], s));
+                        continue;
+                    }
                     fb::launch_cg_spmv(c, lanes);
                     FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i + 1], s));
                     fb::launch_cg_vectors(c);
@@ -642,7 +724,7 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
             }
             while (!h->done) {
                 FB_CUDA(c, cudaGraphLaunch(c->cg_graph, s));
-                c->launches += (cheb ? 1L + 2L * c->cheb_k : 3L) * c->cg_graph_n;
+                c->launches += (cheb ? 1L + 2L * c->cheb_k : (c->world > 1 ? 6L : 3L)) * c->cg_graph_n;
                 spmv += (long) (cheb ? c->cheb_k : 1) * c->cg_graph_n;
                 FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
                 FB_CUDA(c, cudaStreamSynchronize(s));
@@ -653,6 +735,7 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
     FB_CUDA(c, cudaEventSynchronize(c->ev1));
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     c->last_solve_ms = ms; c->last_iters = h->it; c->last_spmv = spmv;
+    if (h->done == 3) return c->fail(FB_ERR_CUDA, "fb_poisson_solve: a peer GPU did not answer within the spin limit (iteration %d)", h->it);
     if (n_iter) *n_iter = (h->done == 1) ? h->it : -h->it;
     if (final_residual) *final_residual = std::sqrt(h->res2);
     return sync_check(c, "fb_poisson_solve");
@@ -700,6 +783,9 @@ int fb_get_partition(const fb_ctx* c, long* out10) {
     out10[6] = (long) c->send_idx.size(); out10[7] = c->n_cols - c->n_dofs; out10[8] = c->n_vert_global; out10[9] = c->n_cells_global;
     return FB_OK;
 }
+
+// 0 = one GPU, 1 = partitioned with NCCL inside the iteration, 2 = partitioned, peer-mapped iteration (CUDA IPC over NVLink)
+int fb_comm_mode(const fb_ctx* c) { return c->world <= 1 ? 0 : (c->p2p_ready ? 2 : 1); }
 
 int fb_export_charge_dens(fb_ctx* c, double* rho_vertex) {
     // PoissonSolver.cpp:198-207: charge_density is only filled when a file is being written

@@ -59,6 +59,25 @@ struct TetRec { double det0; double d[4][4]; };                 // 136 B: Linear
 struct TriRec { double vert0[3], edge1[3], edge2[3], pvec[3], norm[3], maxd; };   // 128 B
 struct HexRec { double f[8][3]; };                              // 192 B: LinearHexahedra f0..f7
 
+// ---- partitioned CG without NCCL inside the iteration: peer-mapped (CUDA IPC) buffers over NVLink ------------------
+// Every rank owns one P2pSlots record in IPC-shared memory; PEERS write into it, the owner polls it.
+constexpr int P2P_MAX = 16;
+struct P2pSlots {
+    double red[2][P2P_MAX][2];          // [reduction of the iteration: 0 = after the SpMV, 1 = after the update][source rank][2 sums]
+    long long red_seq[2][P2P_MAX];      // sequence number of the sums above (release / acquire at system scope)
+    long long halo_flag[P2P_MAX];       // [source rank]: number of halo exchanges whose values have landed in the ghost segment
+};
+struct P2pDesc {                        // device-resident descriptor read by the kernels
+    int rank, world;
+    P2pSlots* slots[P2P_MAX];           // [rank] = own record, the others are peer mappings
+    double* peer_vec[P2P_MAX];          // peers' search-direction vector (owned rows, then the ghost segment)
+    int dst_base[P2P_MAX];              // first entry of THIS rank's segment in peer p's vector: n_dofs_p + recv_off_p[rank]
+    int send_off[P2P_MAX + 1];          // this rank's send list, per peer
+    int n_recv[P2P_MAX];                // ghost values expected from peer p
+    long long red_count[2];             // reductions completed (per kind); identical on all ranks
+    long long halo_count;               // halo exchanges completed
+};
+
 struct CgScalars {          // device-resident CG state (one struct, updated by the kernels)
     double gh;              // g.h of the previous iteration
     double res2;            // ||g||^2 after the last update
@@ -69,6 +88,8 @@ struct CgScalars {          // device-resident CG state (one struct, updated by 
     int pad;
     double* red;            // multi-GPU: kernels deposit their LOCAL sums here (all-reduced over the ranks by NCCL,
                             // then k_cg_scalars_* finishes the step); nullptr on one GPU
+    P2pDesc* p2p;           // multi-GPU, peer-mapped mode: the last block all-reduces over NVLink itself (no NCCL, no extra kernel);
+                            // done = 3 reports a peer that never answered
 };
 
 }  // namespace fb
@@ -100,6 +121,10 @@ struct fb_ctx {
     std::vector<int> part_cell_g;            // local cell -> global solver cell id
     std::vector<int> send_off, send_idx, recv_off;   // halo plan: per peer, owned dofs to send / ghost segment to receive
     fb::DevBuf<int> d_send_idx, d_l2g, d_gcell2local;
+    // peer-mapped iteration (option cg_p2p, default on): IPC mappings of the peers' direction vectors and slot records
+    int cg_p2p = 1; bool p2p_ready = false;
+    fb::DevBuf<fb::P2pSlots> d_p2p_slots; fb::DevBuf<fb::P2pDesc> d_p2p; fb::DevBuf<unsigned> d_p2p_counter;
+    std::vector<void*> p2p_mapped;           // pointers obtained from cudaIpcOpenMemHandle (closed on re-import / destroy)
     fb::DevBuf<double> d_sendbuf, d_red;
     // import intermediates (phase 1 -> phase 2)
     std::vector<int> h_cv, h_v2c_off, h_v2c; std::vector<unsigned char> h_isb;

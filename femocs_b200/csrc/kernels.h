@@ -26,6 +26,7 @@ bool persistent_eligible(fb_ctx* c);
 cudaError_t cheb_prepare(fb_ctx* c, int lanes);
 // multi-GPU
 void launch_pack(fb_ctx* c, const double* v);
+void launch_pack_p2p(fb_ctx* c, const double* v);
 void launch_flags_to_double(fb_ctx* c, double* out);
 void launch_double_to_ghost_flags(fb_ctx* c, const double* in);
 void launch_cg_scalars(fb_ctx* c, int which);

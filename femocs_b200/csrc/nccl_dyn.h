@@ -12,6 +12,7 @@ struct Nccl {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -30,7 +31,7 @@ struct Nccl {
         if (!h) { n.why = "libnccl.so.2 not found"; return n; }
 #define FB_SYM(field, name) *(void**) (&n.field) = dlsym(h, name); if (!n.field) { n.why = "missing symbol " name; return n; }
         FB_SYM(GetUniqueId, "ncclGetUniqueId") FB_SYM(CommInitRank, "ncclCommInitRank") FB_SYM(CommDestroy, "ncclCommDestroy")
-        FB_SYM(AllReduce, "ncclAllReduce") FB_SYM(Send, "ncclSend") FB_SYM(Recv, "ncclRecv")
+        FB_SYM(AllReduce, "ncclAllReduce") FB_SYM(AllGather, "ncclAllGather") FB_SYM(Send, "ncclSend") FB_SYM(Recv, "ncclRecv")
         FB_SYM(GroupStart, "ncclGroupStart") FB_SYM(GroupEnd, "ncclGroupEnd") FB_SYM(GetErrorString, "ncclGetErrorString")
 #undef FB_SYM
         n.ok = true;

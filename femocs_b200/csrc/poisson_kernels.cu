@@ -107,6 +107,48 @@ __device__ __forceinline__ void cg_scalars_update_cheb(CgScalars* cgs, const dou
     if (tot[1] <= cgs->tol2) cgs->done = 1;
     else if (it >= cgs->max_iter || tot[1] != tot[1]) cgs->done = 2;
 }
+// ---------------------------------------------------------------------------------------
+// Peer-mapped all-reduce of the two sums of a reduction kernel, executed by ONE thread (the one that holds the grid
+// totals): the sums go straight into every rank's slot record over NVLink (plain remote stores, then a release store
+// of the sequence number at system scope), then the thread polls its own record until all ranks have delivered and
+// adds the contributions in rank order -- every rank obtains bit-identical totals, hence identical alpha / beta /
+// convergence decisions, without an NCCL call or a kernel boundary.  A slot is rewritten only after its reader has
+// consumed it: the writer's next reduction of the same kind lies behind a reduction of the other kind, which needs
+// the reader's contribution.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+    long long v;
+    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+constexpr long long P2P_SPIN_LIMIT = 8000000000LL;      // ~4 s of SM clocks: a peer that died must not hang the GPU
+
+__device__ __noinline__ bool p2p_allreduce2(P2pDesc* D, int kind, double* tot) {
+    const long long seq = D->red_count[kind] + 1;
+    D->red_count[kind] = seq;
+    const int me = D->rank, W = D->world;
+    for (int p = 0; p < W; ++p) {
+        volatile double* dst = D->slots[p]->red[kind][me];
+        dst[0] = tot[0]; dst[1] = tot[1];
+    }
+    __threadfence_system();
+    for (int p = 0; p < W; ++p) st_release_sys(&D->slots[p]->red_seq[kind][me], seq);
+    P2pSlots* mine = D->slots[me];
+    double a = 0, b = 0;
+    const long long t0 = clock64();
+    for (int p = 0; p < W; ++p) {
+        while (ld_acquire_sys(&mine->red_seq[kind][p]) < seq)
+            if (clock64() - t0 > P2P_SPIN_LIMIT) return false;
+        const volatile double* src = mine->red[kind][p];
+        a += src[0]; b += src[1];
+    }
+    tot[0] = a; tot[1] = b;
+    return true;
+}
+
 template <bool INIT>
 __device__ __forceinline__ void cg_finish_spmv(CgScalars* cgs, const double* tot, double* alpha_out) {
     if (cgs->red) { cgs->red[0] = tot[0]; cgs->red[1] = tot[1]; }
@@ -116,13 +158,18 @@ __device__ __forceinline__ void cg_finish_update(CgScalars* cgs, const double* t
     if (cgs->red) { cgs->red[0] = tot[0]; cgs->red[1] = tot[1]; }
     else cg_scalars_update(cgs, tot, beta_out);
 }
+// The scalar kernels (one thread) of the partitioned CG: in peer-mapped mode they ARE the all-reduce.  It lives here
+// and not in the epilogue of the reduction kernels on purpose: a call in k_spmv_jds costs that kernel its register
+// schedule (78 registers + stack instead of 80 and none, SpMV 0.74 -> 0.85 ms on half of X).
 template <bool INIT>
 __global__ void k_cg_scalars_spmv(CgScalars* cgs, double* alpha_out) {
     if (!INIT && cgs->done) return;
+    if (cgs->p2p && !p2p_allreduce2(cgs->p2p, 0, cgs->red)) { cgs->done = 3; return; }
     cg_scalars_spmv<INIT>(cgs, cgs->red, alpha_out);
 }
 __global__ void k_cg_scalars_update(CgScalars* cgs, double* beta_out) {
     if (cgs->done) return;
+    if (cgs->p2p && !p2p_allreduce2(cgs->p2p, 1, cgs->red)) { cgs->done = 3; return; }
     cg_scalars_update(cgs, cgs->red, beta_out);
 }
 
@@ -1741,6 +1788,15 @@ void launch_cg_vectors(fb_ctx* c) {               // x, g update + dots + conver
 }
 
 void launch_cg_iteration(fb_ctx* c, int lanes) {
+    if (c->world > 1) {         // peer-mapped mode (the NCCL mode issues its iteration from api.cu): 6 kernels, no host involvement
+        launch_pack_p2p(c, c->d_d.p);
+        launch_cg_spmv(c, lanes);
+        launch_cg_scalars(c, 1);
+        launch_cg_update_only(c);
+        launch_cg_scalars(c, 2);
+        launch_cg_direction_only(c);
+        return;
+    }
     launch_cg_spmv(c, lanes);
     launch_cg_vectors(c);
 }
@@ -1809,6 +1865,41 @@ cudaError_t launch_cg_persistent(fb_ctx* c) {
 __global__ void k_pack(int n, const int* __restrict__ idx, const double* __restrict__ v, double* __restrict__ out) {
     for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) out[i] = v[idx[i]];
 }
+// Halo exchange of the search direction WITHOUT NCCL: every owned value a peer needs is stored directly into that peer's
+// ghost segment over NVLink; the last block to finish publishes "exchange #seq has landed" in the peers' slot records
+// (release at system scope, after every block has fenced its stores) and then waits for the same announcement from the
+// ranks it receives from, so that the kernel boundary orders the SpMV behind the complete ghost segment.  The peers'
+// previous SpMV has finished reading the old ghost values: this kernel runs behind an all-reduce that needed their sums.
+__global__ void __launch_bounds__(256) k_pack_p2p(int n, const int* __restrict__ idx, const double* __restrict__ v, P2pDesc* D,
+                                                  unsigned* counter, CgScalars* cgs) {
+    if (cgs->done) return;
+    __shared__ bool is_last;
+    const int W = D->world;
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+        int p = 0;
+        while (p + 1 < W && i >= D->send_off[p + 1]) ++p;
+        D->peer_vec[p][D->dst_base[p] + (int) (i - D->send_off[p])] = v[idx[i]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last || threadIdx.x != 0) return;
+    *counter = 0;
+    __threadfence_system();
+    const long long seq = D->halo_count + 1;
+    D->halo_count = seq;
+    const int me = D->rank;
+    for (int p = 0; p < W; ++p)
+        if (p != me && D->send_off[p + 1] > D->send_off[p]) st_release_sys(&D->slots[p]->halo_flag[me], seq);
+    const long long t0 = clock64();
+    for (int p = 0; p < W; ++p) {
+        if (p == me || D->n_recv[p] == 0) continue;
+        while (ld_acquire_sys(&D->slots[me]->halo_flag[p]) < seq)
+            if (clock64() - t0 > P2P_SPIN_LIMIT) { cgs->done = 3; return; }
+    }
+}
+
 __global__ void k_flags_to_double(int n, const int* __restrict__ flag, double* __restrict__ out) {
     for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) out[i] = flag[i] ? 1.0 : 0.0;
 }
@@ -1819,6 +1910,13 @@ void launch_pack(fb_ctx* c, const double* v) {
     const int n = (int) c->send_idx.size();
     if (n == 0) return;
     k_pack<<<grid_for(c, n, 256), 256, 0, c->stream>>>(n, c->d_send_idx.p, v, c->d_sendbuf.p);
+    c->launches++;
+}
+void launch_pack_p2p(fb_ctx* c, const double* v) {
+    const int n = (int) c->send_idx.size();
+    // (a rank without halo still takes part: the kernel is what advances halo_count on every rank alike)
+    const int g = std::max(1, std::min(grid_for(c, std::max(1, n), 256), c->n_sm * 2));
+    k_pack_p2p<<<g, 256, 0, c->stream>>>(n, c->d_send_idx.p, v, c->d_p2p.p, c->d_p2p_counter.p, c->d_cg.p);
     c->launches++;
 }
 void launch_flags_to_double(fb_ctx* c, double* out) {

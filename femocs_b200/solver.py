@@ -110,6 +110,11 @@ class Context:
         return dict(zip(keys, (int(v) for v in out)))
 
     @property
+    def comm_mode(self):
+        """0 = one GPU, 1 = NCCL inside the CG iteration, 2 = peer-mapped iteration (fb_comm_mode)"""
+        return int(self.L.fb_comm_mode(self.h))
+
+    @property
     def stream(self):
         """cudaStream_t of the context (integer address)."""
         return int(self.L.fb_get_stream(self.h))

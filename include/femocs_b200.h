@@ -80,6 +80,11 @@ int fb_comm_init(fb_ctx* ctx, int rank, int world, const char* id128);
 /* out[0..9] = rank, world, owned rows, local columns (rows + ghosts), local nnz, local cells,
  * halo values sent per exchange, ghosts received, global solver vertices, global solver cells */
 int fb_get_partition(const fb_ctx* ctx, long* out10);
+/* how the partitioned CG communicates: 0 = one GPU; 1 = NCCL inside the iteration (grouped ncclSend/ncclRecv halo + two
+ * ncclAllReduce per iteration, host-issued); 2 = peer-mapped (default when CUDA IPC works between the ranks, option
+ * "cg_p2p" = 0 disables): halo values and the two pairs of sums are stored straight into the peers' memory over NVLink by
+ * the kernels themselves, so that an iteration is 4 kernels, captured in a CUDA graph like on one GPU */
+int fb_comm_mode(const fb_ctx* ctx);
 /* host-only view of the same partition logic (no CUDA): used by the world_size-2 CPU tests.
  * phase1 returns the extremes of the local boundary-face centres (min xyz, max xyz); the caller reduces
  * them over the ranks (min / max) and passes the result to phase2.  Destroy with fb_destroy. */

@@ -16,7 +16,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, p2p):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -31,9 +31,11 @@ def _worker(rank, world, port, q):
         torch.cuda.set_device(rank)
         ctx = fb.Context(rank)
         ctx.init_comm_torch(dist)
+        ctx.set_option("cg_p2p", p2p)
         s = fb.PoissonSolver(ctx, fb.FieldConfig(cg_tolerance=1e-11, mode="transient"))
         assert s.import_mesh(m["nodes"], m["hexs"], m["hex_markers"])
         part = ctx.partition()
+        part["comm_mode"] = ctx.comm_mode
         ok = g["pic_ok"]
         cf = -180.9512268 * 0.01
         out = {"part": part}
@@ -56,8 +58,9 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("p2p", [1, 0], ids=["peer_mapped", "nccl"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_partitioned_solve_matches_oracle(world, golden):
+def test_partitioned_solve_matches_oracle(world, p2p, golden):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
@@ -65,7 +68,7 @@ def test_partitioned_solve_matches_oracle(world, golden):
     from oracle.oracle import Oracle
     mpc = mp.get_context("spawn")
     q = mpc.Queue(); port = _free_port()
-    procs = [mpc.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [mpc.Process(target=_worker, args=(r, world, port, q, p2p)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
@@ -85,6 +88,8 @@ def test_partitioned_solve_matches_oracle(world, golden):
     outs = [r[2] for r in res]
     assert sum(x["part"]["n_rows"] for x in outs) == o.n_vertices
     for x in outs:
+        # 2 = the iteration runs over peer mappings (CUDA IPC + NVLink stores, CUDA-graph captured), 1 = NCCL inside the iteration
+        assert x["part"]["comm_mode"] == (2 if p2p else 1), x["part"]
         assert x["it_laplace"] > 0 and x["it_poisson"] > 0 and x["it_warm"] == 0
         assert x["it_laplace"] == outs[0]["it_laplace"]                      # every rank takes the same decisions
         assert rel(x["phi_laplace"], ref_l) < 1e-8                            # complete potential on every rank
