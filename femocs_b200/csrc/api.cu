@@ -183,6 +183,7 @@ int fb_set_option(fb_ctx* c, const char* key, double value) {
     else if (k == "spmv_kernel") { c->spmv_kernel = (int) value; drop_graph(c); }
     else if (k == "cg_persistent") c->cg_persistent = (int) value;
     else if (k == "cg_debug") c->cg_debug = (int) value;
+    else if (k == "mesh_reuse") c->mesh_reuse = (int) value;  // 0: fb_import_mesh never takes the unchanged-topology path
     else if (k == "cg_p2p") c->cg_p2p = (int) value;          // read by the next partitioned fb_import_mesh
     else if (k == "cg_persistent_ctas") { c->pers_ctas = (int) value; c->pers_grid = 0; }
     else if (k == "cg_profile") c->cg_profile = std::max(0, std::min(4096, (int) value));
@@ -241,6 +242,8 @@ int fb_plan_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, c
 // numbering, sparsity) on a plan context; fb_plan_sizes / fb_plan_get / fb_plan_jds then describe the complete system
 int fb_plan_import(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {
     FB_REQUIRE(c, c->host_only, "fb_plan_import: not a plan context");
+    c->last_import_reused = fb_host_try_reuse(c, xyz, n_nodes, hex8, hex_marker, n_hex, c->mesh_kind);
+    if (c->last_import_reused) return FB_OK;
     const int rc = fb_host_import_mesh(c, xyz, n_nodes, hex8, hex_marker, n_hex);
     if (rc) return rc;
     c->n_vert_global = c->n_vert; c->n_cells_global = c->n_cells; c->n_dofs_global = c->n_dofs;
@@ -351,6 +354,26 @@ int fb_import_bulk_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* he
 static int import_mesh_impl(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {
     FB_REQUIRE(c, xyz && hex8 && hex_marker && n_nodes > 0 && n_hex > 0, "fb_import_mesh: empty mesh");
     cudaSetDevice(c->device);
+    c->last_import_reused = false;
+    if (c->world == 1 && fb_host_try_reuse(c, xyz, n_nodes, hex8, hex_marker, n_hex, c->mesh_kind)) {
+        // same connectivity, new coordinates: numbering, sparsity, block-JDS tables, persistent-CG slices, the
+        // captured CG graph and every integer device array stay; the matrices and the interpolator tables depend on the
+        // geometry and are rebuilt by the next assemble(true) / fb_interp_initialize
+        c->setup_ok = c->assembled = c->matrix_ok = c->interp_ok = false;
+        c->jds_val_dirty = true; c->cheb_lmax = 0;
+        const int n = c->n_cols;
+        double* vx = (double*) c->pin_in.p;
+        if (c->pin_in.bytes < 3 * (size_t) n * sizeof(double)) { FB_CUDA(c, c->pin_in.reserve(3 * (size_t) n * sizeof(double))); vx = (double*) c->pin_in.p; }
+#pragma omp parallel for schedule(static)
+        for (int d = 0; d < n; ++d) {
+            const double* p = &c->xyz[3 * (size_t) c->vert2node[c->dof2vertex[d]]];
+            vx[3 * (size_t) d] = p[0]; vx[3 * (size_t) d + 1] = p[1]; vx[3 * (size_t) d + 2] = p[2];
+        }
+        FB_CUDA(c, cudaMemcpyAsync(c->d_vxyz.p, vx, 3 * (size_t) n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        FB_CUDA(c, cudaMemsetAsync(c->d_x.p, 0, n * sizeof(double), c->stream));
+        c->last_import_reused = true;
+        return sync_check(c, "fb_import_mesh");
+    }
     c->setup_ok = c->assembled = c->matrix_ok = c->interp_ok = false;
     c->n_mesh_faces = c->n_mesh_edges = -1; c->d_vert_lastcell.release();
     drop_graph(c);
@@ -783,6 +806,9 @@ int fb_get_partition(const fb_ctx* c, long* out10) {
     out10[6] = (long) c->send_idx.size(); out10[7] = c->n_cols - c->n_dofs; out10[8] = c->n_vert_global; out10[9] = c->n_cells_global;
     return FB_OK;
 }
+
+// 1 when the last fb_import_mesh / fb_import_bulk_mesh found the connectivity unchanged and only refreshed the geometry
+int fb_last_import_reused(const fb_ctx* c) { return c->last_import_reused ? 1 : 0; }
 
 // 0 = one GPU, 1 = partitioned with NCCL inside the iteration, 2 = partitioned, peer-mapped iteration (CUDA IPC over NVLink)
 int fb_comm_mode(const fb_ctx* c) { return c->world <= 1 ? 0 : (c->p2p_ready ? 2 : 1); }

@@ -131,6 +131,7 @@ struct fb_ctx {
     double bb_mn[3] = {0, 0, 0}, bb_mx[3] = {0, 0, 0};
 
     // ---- host copies of the mesh (femocs numbering) ----
+    int mesh_reuse = 1; bool mesh_flipped = false, last_import_reused = false; int imported_kind = 0;   // fb_host_try_reuse
     int mesh_kind = 0;                       // 0 = vacuum hexahedra (PoissonSolver), 1 = bulk hexahedra (CurrentHeatSolver)
     int n_nodes = 0, n_hex = 0;
     std::vector<double> xyz;
@@ -240,6 +241,7 @@ bool fb_host_row_blocks(fb_ctx* c, int chunk, int maxrows);
 bool fb_host_col_windows(fb_ctx* c, int max_window);
 bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym);
 int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
+bool fb_host_try_reuse(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex, int mesh_kind);
 int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
 int fb_host_import_phase2(fb_ctx* c);
 // partition.cpp: cuts the mesh for c->rank of c->world and runs phase 1 on the local sub-mesh

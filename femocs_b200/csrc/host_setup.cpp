@@ -128,6 +128,8 @@ int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* 
         }
         if (hex_volume(v) < 0) ++n_neg;
     }
+    c->mesh_flipped = (n_neg == n_cells);
+    c->imported_kind = c->mesh_kind;
     if (n_neg == n_cells) {
         // deal.II 9.2 swaps vertices i <-> i + 4 of the OLD-STYLE (UCD) numbering the cells arrive in; through
         // UCD_TO_LEX these are the lexicographic pairs (0,2) (1,3) (4,6) (5,7)
@@ -332,6 +334,54 @@ int fb_host_import_phase2(fb_ctx* c) {
     std::vector<unsigned char>().swap(c->h_isb);
     c->mesh_ok = true;
     return FB_OK;
+}
+
+// Mesh hand-off with UNCHANGED topology (the reference decides between "skip" and "re-mesh" on the rmsd of
+// the atoms, ProjectRunaway.cpp:55-67 / GeneralProject.cpp:19-55 -- a host code that moves nodes without re-meshing hands
+// over the same connectivity with new coordinates): when node count, hexahedra and markers are identical to the mesh
+// already held, everything integer -- vertex compaction, cell orientation, boundary faces, DoF numbering, sparsity,
+// Dirichlet sets, and with them the block-JDS tables, persistent-CG slices and device copies -- stays valid.  Only the
+// geometry is refreshed and re-validated: no cell may have changed orientation and every boundary face must keep its id
+// (mark_boundary works on face centres, DealSolver.cpp:460-518).  Returns false (nothing modified but c->xyz untouched)
+// when the full import has to run.
+bool fb_host_try_reuse(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex, int mesh_kind) {
+    if (!c->mesh_ok || c->mesh_reuse == 0 || c->part_n_owned >= 0 || c->mesh_flipped) return false;
+    if (mesh_kind != c->imported_kind || n_nodes != c->n_nodes || n_hex != c->n_hex) return false;
+    if (memcmp(hex_marker, c->hex_marker.data(), sizeof(int) * (size_t) n_hex) != 0) return false;
+    if (memcmp(hex8, c->hex8.data(), sizeof(int) * 8 * (size_t) n_hex) != 0) return false;
+    Laps laps("import (topology unchanged)");
+    const int n_cells = c->n_cells;
+    auto vertex = [&](int ce, int k) { return &xyz[3 * (size_t) c->vert2node[c->dof2vertex[c->cells_dof[8 * (size_t) ce + k]]]]; };
+    long n_neg = 0;
+#pragma omp parallel for schedule(static) reduction(+ : n_neg)
+    for (int ce = 0; ce < n_cells; ++ce) {
+        P3 v[8];
+        for (int k = 0; k < 8; ++k) { const double* p = vertex(ce, k); v[k] = {p[0], p[1], p[2]}; }
+        if (hex_volume(v) < 0) ++n_neg;
+    }
+    if (n_neg > 0) return false;
+    laps.lap("orientation");
+    double mx[3] = {-1e16, -1e16, -1e16}, mn[3] = {1e16, 1e16, 1e16};
+    std::vector<double> ctr(3 * c->bfaces.size());
+    for (size_t i = 0; i < c->bfaces.size(); ++i) {
+        double s[3] = {0, 0, 0};
+        for (int k = 0; k < 4; ++k) { const double* p = vertex(c->bfaces[i].cell, FACE_VERTS[c->bfaces[i].face][k]); s[0] += p[0]; s[1] += p[1]; s[2] += p[2]; }
+        for (int d = 0; d < 3; ++d) { ctr[3 * i + d] = s[d] / 4.0; mx[d] = std::max(mx[d], ctr[3 * i + d]); mn[d] = std::min(mn[d], ctr[3 * i + d]); }
+    }
+    const double eps = 1e-6;
+    auto on = [&](double v, double b) { return std::fabs(v - b) <= eps; };
+    for (size_t i = 0; i < c->bfaces.size(); ++i) {
+        const double* p = &ctr[3 * i];
+        int id;
+        const bool side = on(p[0], mn[0]) || on(p[0], mx[0]) || on(p[1], mn[1]) || on(p[1], mx[1]);
+        if (c->mesh_kind == 0) id = side ? 4 : (on(p[2], mx[2]) ? 8 : 2);
+        else id = side ? 4 : (on(p[2], mx[2]) ? 2 : (on(p[2], mn[2]) ? 7 : 2));
+        if (id != c->bfaces[i].id) return false;
+    }
+    laps.lap("face ids");
+    c->xyz.assign(xyz, xyz + 3 * (size_t) n_nodes);
+    for (int d = 0; d < 3; ++d) { c->bb_mn[d] = mn[d]; c->bb_mx[d] = mx[d]; }
+    return true;
 }
 
 int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {

@@ -72,6 +72,7 @@ SIGNATURES = {
     "fb_plan_jds_get": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "fb_get_stream": (vp, [vp]),
     "fb_comm_mode": (C.c_int, [vp]),
+    "fb_last_import_reused": (C.c_int, [vp]),
     "fb_plan_set_kind": (C.c_int, [vp, C.c_int]),
     "fb_import_bulk_mesh": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int]),
     "fb_ch_set_physics": (C.c_int, [vp, vp, vp, C.c_int, C.c_double]),

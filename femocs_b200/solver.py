@@ -110,6 +110,11 @@ class Context:
         return dict(zip(keys, (int(v) for v in out)))
 
     @property
+    def last_import_reused(self):
+        """True when the last import_mesh found the connectivity unchanged and only refreshed the geometry"""
+        return bool(self.L.fb_last_import_reused(self.h))
+
+    @property
     def comm_mode(self):
         """0 = one GPU, 1 = NCCL inside the CG iteration, 2 = peer-mapped iteration (fb_comm_mode)"""
         return int(self.L.fb_comm_mode(self.h))
@@ -521,6 +526,7 @@ class PartitionPlan:
         nodes = _f(nodes); hexs = _i(hexs); hex_markers = _i(hex_markers)
         self._check(self.L.fb_plan_set_kind(self.h, int(bulk)))
         self._check(self.L.fb_plan_import(self.h, _p(nodes), len(nodes), _p(hexs), _p(hex_markers), len(hexs)))
+        self.reused = bool(self.L.fb_last_import_reused(self.h))
         return self._collect()
 
     def phase2(self, bbox_global):

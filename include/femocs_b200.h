@@ -127,6 +127,13 @@ int fb_plan_jds_get(const fb_ctx* plan, unsigned short* perm, unsigned short* le
 int fb_import_mesh(fb_ctx* ctx, const double* xyz, int n_nodes,
                    const int* hex8, const int* hex_marker, int n_hex);
 
+/* Mesh hand-off with unchanged topology (re-mesh decision of src/ProjectRunaway.cpp:55-67,
+ * src/GeneralProject.cpp:19-55): when fb_import_mesh / fb_import_bulk_mesh receives the node count, hexahedra and markers
+ * of the mesh it already holds, only the geometry is refreshed (orientation and boundary ids re-validated); numbering,
+ * sparsity, SpMV tables and the captured CG graph are kept.  Returns 1 if the last import took that path.  Option
+ * "mesh_reuse" = 0 forces the full import.  Un-partitioned contexts only. */
+int fb_last_import_reused(const fb_ctx* ctx);
+
 /* sizes after import: out[0]=n_dofs, [1]=n_cells, [2]=nnz, [3]=n_vertices,
  * [4]=n_boundary_faces, [5]=n_top_faces, [6]=n_dirichlet_dofs (after assemble) */
 int fb_get_sizes(const fb_ctx* ctx, long* out7);

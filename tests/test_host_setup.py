@@ -66,3 +66,50 @@ def test_bulk_mesh_import_matches_oracle(name, golden):
     # the vacuum import of the same arrays is untouched by the bulk option
     b = PartitionPlan(0, 1).import_whole(m["nodes"], m["hexs"], m["hex_markers"])
     assert b.n_cells == int((m["hex_markers"] > 0).sum())
+
+
+def _interior_jitter(nodes, scale, seed=3):
+    """moves every node that does not lie on one of the six bounding planes (the faces there keep their boundary ids)"""
+    rng = np.random.default_rng(seed)
+    lo, hi = nodes.min(0), nodes.max(0)
+    inside = np.all((nodes > lo + 1e-9) & (nodes < hi - 1e-9), axis=1)
+    out = nodes.copy()
+    out[inside] += scale * rng.standard_normal((int(inside.sum()), 3))
+    return out
+
+
+def test_unchanged_topology_is_reused(golden):
+    """a second import with identical connectivity only refreshes the geometry -- and must leave the context
+    exactly as a fresh import of the moved mesh would (numbering, sparsity, Dirichlet sets, face order); anything that
+    changes the integer side (connectivity, a boundary face leaving its plane) takes the full path"""
+    m = golden("mesh", "mdsmall")
+    nodes, hexs, mk = m["nodes"], m["hexs"], m["hex_markers"]
+    p = PartitionPlan(0, 1)
+    p.import_whole(nodes, hexs, mk)
+    assert not p.reused
+    cen0 = p.surface_centroids()
+    moved = _interior_jitter(nodes, 0.02)
+    p.import_whole(moved, hexs, mk)
+    assert p.reused
+    f = PartitionPlan(0, 1).import_whole(moved, hexs, mk)
+    for key in ("rowptr", "col", "cells_dof", "copper", "top"):
+        assert np.array_equal(getattr(p, key), getattr(f, key)), key
+    assert np.array_equal(p.surface_centroids(), f.surface_centroids())          # the refreshed coordinates are in use
+    assert not np.array_equal(p.surface_centroids(), cen0)
+    # the bulk mesh of the same arrays is another mesh kind: full import
+    p.import_whole(moved, hexs, mk, bulk=True)
+    assert not p.reused
+    # permuted hexahedra: full import
+    q = PartitionPlan(0, 1); q.import_whole(nodes, hexs, mk)
+    h2 = hexs.copy(); h2[[0, 1]] = h2[[1, 0]]; k2 = mk.copy(); k2[[0, 1]] = k2[[1, 0]]
+    q.import_whole(nodes, h2, k2)
+    assert not q.reused
+    # a node of the top plane pushed outwards: its faces define a new zmax, the others lose the "top" id -> full import,
+    # same result as a fresh context
+    top = np.flatnonzero(nodes[:, 2] > nodes[:, 2].max() - 1e-9)
+    bumped = nodes.copy(); bumped[top[0], 2] += 0.5
+    q.import_whole(bumped, h2, k2)
+    assert not q.reused
+    g = PartitionPlan(0, 1).import_whole(bumped, h2, k2)
+    assert np.array_equal(q.top, g.top) and np.array_equal(q.copper, g.copper)
+    # option mesh_reuse = 0 is honoured by the full library only (plan contexts have no options): covered on the GPU
