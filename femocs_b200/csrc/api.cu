@@ -6,6 +6,8 @@
 #include <cstdlib>
 #include <string>
 
+#include <omp.h>
+
 #include "kernels.h"
 #include "nccl_dyn.h"
 
@@ -183,7 +185,8 @@ int fb_set_option(fb_ctx* c, const char* key, double value) {
     else if (k == "spmv_kernel") { c->spmv_kernel = (int) value; drop_graph(c); }
     else if (k == "cg_persistent") c->cg_persistent = (int) value;
     else if (k == "cg_debug") c->cg_debug = (int) value;
-    else if (k == "mesh_reuse") c->mesh_reuse = (int) value;  // 0: fb_import_mesh never takes the unchanged-topology path
+    else if (k == "mesh_reuse") c->mesh_reuse = (int) value;
+    else if (k == "cell_grid") c->cell_grid = (int) value;    // 0: brute-force tetrahedron scan (read by the next fb_interp_initialize)  // 0: fb_import_mesh never takes the unchanged-topology path
     else if (k == "cg_p2p") c->cg_p2p = (int) value;          // read by the next partitioned fb_import_mesh
     else if (k == "cg_persistent_ctas") { c->pers_ctas = (int) value; c->pers_grid = 0; }
     else if (k == "cg_profile") c->cg_profile = std::max(0, std::min(4096, (int) value));
@@ -1089,6 +1092,8 @@ int fb_interp_initialize(fb_ctx* c, const int* node_marker, const int* tet4, con
     cudaSetDevice(c->device);
     cudaStream_t s = c->stream;
     c->interp_ok = false;
+    const bool verbose = getenv("FB_VERBOSE") != nullptr;
+    const double t_begin = omp_get_wtime();
     fb_interp_tables T;
     fb_host_interp_tables(c, node_marker, tet4, tet_nbr4, tet_marker, n_tet, tri3, tri_norm3, n_tri, quad4, n_quad, T);
     c->n_tet = n_tet; c->n_tri = n_tri; c->n_quad = n_quad; c->n_voro = n_voro;
@@ -1117,6 +1122,14 @@ int fb_interp_initialize(fb_ctx* c, const int* node_marker, const int* tet4, con
     }
     int rc = sync_check(c, "fb_interp_initialize");
     if (rc) return rc;
+    const double t_upload = omp_get_wtime();
+    {   // uniform-grid filter of the tetrahedron scan: box of all mesh nodes on the host, lists on the device
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int i = 0; i < c->n_nodes; ++i)
+            for (int d = 0; d < 3; ++d) { const double x = c->xyz[3 * (size_t) i + d]; lo[d] = std::min(lo[d], x); hi[d] = std::max(hi[d], x); }
+        if ((rc = fb::launch_build_cell_grid(c, lo, hi))) return rc;
+    }
+    if (verbose) fprintf(stderr, "[fb] fb_interp_initialize (ms): host tables + uploads %.2f, cell grid %.2f\n", 1e3 * (t_upload - t_begin), 1e3 * (omp_get_wtime() - t_upload));
     c->interp_ok = true;
     return FB_OK;
 }

@@ -211,6 +211,9 @@ struct fb_ctx {
     fb::DevBuf<fb::TriRec> d_tri; fb::DevBuf<double> d_tri_cent; fb::DevBuf<int> d_tri_nbr_off, d_tri_nbr, d_tri2tet;
     fb::DevBuf<fb::HexRec> d_hex; fb::DevBuf<int> d_quad2hex;
     fb::DevBuf<int> d_qtet, d_qtri;          // 10 / 6 node ids
+    // uniform-grid filter of the tetrahedron scan (option cell_grid, default on)
+    int cell_grid = 1; bool grid_on = false; int grid_g[3] = {1, 1, 1}, grid_entries = 0; double grid_lo[3] = {0, 0, 0}, grid_h[3] = {1, 1, 1};
+    fb::DevBuf<int> d_grid_off, d_grid_list, d_grid_coff, d_grid_clist, d_grid_cnt;
     // scratch for queries
     fb::DevBuf<double> d_pts; fb::DevBuf<int> d_cellsA, d_cellsB, d_scan, d_scan2, d_flag;
     fb::DevBuf<double> d_pic_pos, d_pic_vel; fb::DevBuf<int> d_pic_cell, d_pic_blk;   // compaction targets of the PIC push

@@ -45,11 +45,20 @@ __device__ __forceinline__ P3 ldp(const double* __restrict__ a, long i) { return
 __device__ __forceinline__ P3 p3(const double* a) { return {a[0], a[1], a[2]}; }
 __device__ __forceinline__ double comp(const P3& a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 
+// Uniform grid over the tetrahedra (built on the device by fb_interp_initialize): per bucket the searchable tetrahedra
+// whose slightly enlarged bounding box overlaps it (`off`/`list`) and the tetrahedra whose centroid lies in it
+// (`coff`/`clist`).  It only PRUNES the linear scan of locate_cell: see grid_scan.
+struct CellGridDev {
+    double lo[3], h[3], inv_h[3]; int g[3]; int n_buckets;
+    const int* off; const int* list; const int* coff; const int* clist;
+};
+
 struct Tables {                 // device view of the interpolator tables
     const double* nxyz; const double* nodal; const int* hex8;
     const TetRec* tet; const double* tet_cent; const int* tet_mark; const int* tet_nbr_off; const int* tet_nbr; const int* tet4; int n_tet;
     const TriRec* tri; const double* tri_cent; const int* tri_nbr_off; const int* tri_nbr; const int* tri2tet; int n_tri;
     const HexRec* hex; const int* quad2hex; const int* qtet; const int* qtri;
+    CellGridDev grid;                                      // uniform-grid filter over the tetrahedra (n_buckets == 0: none)
 };
 
 // ---- tetrahedra ----
@@ -259,6 +268,141 @@ __global__ void __launch_bounds__(256) k_scan_cells(Tables T, long n, const doub
             if (d2o < d2 || (d2o == d2 && io < mi)) { d2 = d2o; mi = io; }
         }
         if (lane == 0) out[i0 + q] = found[q] ? result[q] : -mi;
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// The guess-free answer of locate_cell for tetrahedra through the uniform grid -- bit-identical to the linear scan:
+//   * hit: a tetrahedron that contains p (barycentric test with its 1e-15 tolerance) has p inside its bounding box
+//     enlarged by the build margin, hence sits in the list of p's bucket; the FIRST hit in index order of the scan is
+//     the minimum index over the hits in that list (lists are unordered: every candidate is tested);
+//   * miss: the scan returns the lexicographic minimum of (distance^2 to the centroid, index) over ALL tetrahedra.
+//     Centroids are binned one bucket each; shells of buckets around p's (clamped) bucket are visited until the best
+//     distance is strictly below the distance to everything unvisited (the faces of the visited box that are not grid
+//     boundaries, minus a safety margin far above round-off); ties keep the smaller index, as the ascending loop does.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int grid_bucket(const CellGridDev& G, double x, int d) {
+    const int b = (int) floor((x - G.lo[d]) * G.inv_h[d]);
+    return min(max(b, 0), G.g[d] - 1);
+}
+
+// one WARP per point: all 32 lanes pass the same p and obtain the same answer
+__device__ int grid_scan(const Tables& T, P3 p) {
+    const CellGridDev& G = T.grid;
+    const int lane = threadIdx.x & 31;
+    const double pc[3] = {p.x, p.y, p.z};
+    int b[3]; bool inside = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        b[d] = grid_bucket(G, pc[d], d);
+        inside = inside && pc[d] >= G.lo[d] && pc[d] <= G.lo[d] + G.h[d] * G.g[d];
+    }
+    if (inside) {
+        const int bk = (b[2] * G.g[1] + b[1]) * G.g[0] + b[0];
+        int hit = 0x7fffffff;
+        for (int k = G.off[bk] + lane; k < G.off[bk + 1]; k += 32) {
+            const int c = G.list[k];
+            if (c < hit && tet_in(T.tet[c], p)) hit = c;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hit = min(hit, __shfl_xor_sync(0xffffffffu, hit, o));
+        if (hit != 0x7fffffff) return hit;
+    }
+    double best = 1e100; int bi = 0;
+    const double safety = 1e-9 * fmin(G.h[0], fmin(G.h[1], G.h[2]));
+    for (int r = 0;; ++r) {
+        const int z0 = max(0, b[2] - r), z1 = min(G.g[2] - 1, b[2] + r);
+        const int y0 = max(0, b[1] - r), y1 = min(G.g[1] - 1, b[1] + r);
+        const int x0 = max(0, b[0] - r), x1 = min(G.g[0] - 1, b[0] + r);
+        const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, total = nx * ny * (z1 - z0 + 1);
+        for (int q = lane; q < total; q += 32) {                   // the lanes share the box of shell r; its interior was visited before
+            const int x = x0 + q % nx, y = y0 + (q / nx) % ny, z = z0 + q / (nx * ny);
+            if (max(abs(x - b[0]), max(abs(y - b[1]), abs(z - b[2]))) != r) continue;
+            const int bk = (z * G.g[1] + y) * G.g[0] + x;
+            for (int k = G.coff[bk]; k < G.coff[bk + 1]; ++k) {
+                const int c = G.clist[k];
+                const double d2 = dist2(p, T.tet_cent + 3 * (long) c);
+                if (d2 < best || (d2 == best && c < bi)) { best = d2; bi = c; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double d2o = __shfl_xor_sync(0xffffffffu, best, o);
+            const int io = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (d2o < best || (d2o == best && io < bi)) { best = d2o; bi = io; }
+        }
+        double dmin = 1e300;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (b[d] - r > 0) dmin = fmin(dmin, pc[d] - (G.lo[d] + G.h[d] * (b[d] - r)));
+            if (b[d] + r < G.g[d] - 1) dmin = fmin(dmin, (G.lo[d] + G.h[d] * (b[d] + r + 1)) - pc[d]);
+        }
+        if (dmin == 1e300) break;                         // the whole grid has been visited
+        dmin -= safety;
+        if (dmin > 0 && best < dmin * dmin) break;
+    }
+    return -bi;
+}
+
+__global__ void __launch_bounds__(128) k_scan_grid(Tables T, long n, const double* __restrict__ pts, int* __restrict__ out) {
+    const long i = ((long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;         // warp-uniform
+    if (i >= n) return;
+    const int c = grid_scan(T, ldp(pts, i));
+    if ((threadIdx.x & 31) == 0) out[i] = c;
+}
+
+// ---- grid build: count, (host-free) scan, fill ----
+__device__ __forceinline__ void tet_bucket_range(const Tables& T, const CellGridDev& G, int t, double margin, int lo[3], int hi[3], int cb[3]) {
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double* v = T.nxyz + 3 * (long) T.tet4[4 * (long) t + k];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { mn[d] = fmin(mn[d], v[d]); mx[d] = fmax(mx[d], v[d]); }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        lo[d] = grid_bucket(G, mn[d] - margin, d); hi[d] = grid_bucket(G, mx[d] + margin, d);
+        cb[d] = grid_bucket(G, T.tet_cent[3 * (long) t + d], d);
+    }
+}
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_grid_build(Tables T, CellGridDev G, double margin, int* __restrict__ cnt, int* __restrict__ ccnt,
+                                                    int* __restrict__ list, int* __restrict__ clist, int cap) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T.n_tet) return;
+    int lo[3], hi[3], cb[3];
+    tet_bucket_range(T, G, t, margin, lo, hi, cb);
+    const int cbk = (cb[2] * G.g[1] + cb[1]) * G.g[0] + cb[0];
+    const int pos = atomicAdd(&ccnt[cbk], 1);
+    if (FILL) clist[pos] = t;
+    if (T.tet_mark[t] != 0) return;                       // not searchable: never a hit of the linear scan
+    for (int z = lo[2]; z <= hi[2]; ++z)
+        for (int y = lo[1]; y <= hi[1]; ++y)
+            for (int x = lo[0]; x <= hi[0]; ++x) {
+                const int bk = (z * G.g[1] + y) * G.g[0] + x;
+                const int q = atomicAdd(&cnt[bk], 1);
+                if (FILL && q < cap) list[q] = t;
+            }
+}
+// exclusive scan of two count arrays by one block (n up to a few 1e5); cursors start at the offsets
+__global__ void __launch_bounds__(1024) k_grid_scan(int n, int* __restrict__ cnt, int* __restrict__ off, int* __restrict__ ccnt, int* __restrict__ coff,
+                                                    int* __restrict__ totals) {
+    __shared__ int s_sum[1024];
+    for (int which = 0; which < 2; ++which) {
+        int* c = which ? ccnt : cnt; int* o = which ? coff : off;
+        const int per = (n + blockDim.x - 1) / blockDim.x;
+        const int a = threadIdx.x * per, e = min(n, a + per);
+        int s = 0;
+        for (int i = a; i < e; ++i) s += c[i];
+        s_sum[threadIdx.x] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) { int run = 0; for (int i = 0; i < (int) blockDim.x; ++i) { const int v = s_sum[i]; s_sum[i] = run; run += v; } o[n] = run; totals[which] = run; }
+        __syncthreads();
+        int run = s_sum[threadIdx.x];
+        for (int i = a; i < e; ++i) { const int v = c[i]; o[i] = run; c[i] = run; run += v; }     // c becomes the fill cursor
+        __syncthreads();
     }
 }
 
@@ -493,6 +637,20 @@ __global__ void __launch_bounds__(256) k_finish_scanned(Tables T, int rank, cons
                                                         const int* __restrict__ needy_count, const int* __restrict__ needy_idx,
                                                         double* __restrict__ sol5) {
     const int count = *needy_count;
+    if (T.grid.n_buckets > 0) {         // grid filter: the scan of one point is a handful of candidates -> one WARP per deferred point
+        for (long e = ((long) blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < count; e += ((long) gridDim.x * blockDim.x) >> 5) {
+            const long i = needy_idx[e];
+            const P3 p = ldp(pts, i);
+            const int tet = grid_scan(T, p);
+            if ((threadIdx.x & 31) == 0) {
+                double out[5];
+                surface_finish(T, rank, p, tet, false, out);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) sol5[5 * i + k] = out[k];
+            }
+        }
+        return;
+    }
     for (int e = blockIdx.x; e < count; e += gridDim.x) {
         const long i = needy_idx[e];
         const P3 p = ldp(pts, i);
@@ -679,6 +837,18 @@ __global__ void __launch_bounds__(256) k_particle_scanned(Tables T, const double
                                                           const int* __restrict__ needy_count, const int* __restrict__ needy_idx,
                                                           int* __restrict__ cell_inout) {
     const int count = *needy_count;
+    if (T.grid.n_buckets > 0) {         // grid filter: one warp per deferred particle
+        for (long e = ((long) blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < count; e += ((long) gridDim.x * blockDim.x) >> 5) {
+            const long i = needy_idx[e];
+            const P3 p = ldp(pts, i);
+            const int tet = grid_scan(T, p);
+            if ((threadIdx.x & 31) == 0) {
+                const int fc = hex_from_tet(T, p, tet);
+                cell_inout[i] = fc < 0 ? -1 : hex2cell[fc];
+            }
+        }
+        return;
+    }
     for (int e = blockIdx.x; e < count; e += gridDim.x) {
         const long i = needy_idx[e];
         const P3 p = ldp(pts, i);
@@ -870,7 +1040,56 @@ static Tables make_tables(const fb_ctx* c) {
     T.tri = c->d_tri.p; T.tri_cent = c->d_tri_cent.p; T.tri_nbr_off = c->d_tri_nbr_off.p; T.tri_nbr = c->d_tri_nbr.p;
     T.tri2tet = c->d_tri2tet.p; T.n_tri = c->n_tri;
     T.hex = c->d_hex.p; T.quad2hex = c->d_quad2hex.p; T.qtet = c->d_qtet.p; T.qtri = c->d_qtri.p;
+    CellGridDev& G = T.grid;
+    G.n_buckets = c->grid_on ? c->grid_g[0] * c->grid_g[1] * c->grid_g[2] : 0;
+    for (int d = 0; d < 3; ++d) { G.lo[d] = c->grid_lo[d]; G.h[d] = c->grid_h[d]; G.inv_h[d] = 1.0 / c->grid_h[d]; G.g[d] = c->grid_g[d]; }
+    G.off = c->d_grid_off.p; G.list = c->d_grid_list.p; G.coff = c->d_grid_coff.p; G.clist = c->d_grid_clist.p;
     return T;
+}
+
+// Uniform grid over the tetrahedra, built on the device (two passes over the bucket ranges: count, fill); the host only
+// fixes the box (all mesh nodes) and the bucket edge (about 4 buckets per tetrahedron, at most 2^21 buckets).
+int launch_build_cell_grid(fb_ctx* c, const double* bb_lo, const double* bb_hi) {
+    c->grid_on = false;
+    if (c->n_tet < 64 || c->cell_grid == 0) return FB_OK;           // tiny meshes: the plain scan is as fast
+    double ext[3], vol = 1;
+    for (int d = 0; d < 3; ++d) { ext[d] = std::max(bb_hi[d] - bb_lo[d], 1e-9); vol *= ext[d]; }
+    double h = std::cbrt(vol / (4.0 * c->n_tet));
+    long nb = 1;
+    for (int it = 0; it < 8; ++it) {
+        nb = 1;
+        for (int d = 0; d < 3; ++d) { c->grid_g[d] = (int) std::min(512.0, std::max(1.0, std::ceil(ext[d] / h))); nb *= c->grid_g[d]; }
+        if (nb <= (1L << 21)) break;
+        h *= 1.3;
+    }
+    const double margin = 1e-6 * std::max(ext[0], std::max(ext[1], ext[2]));
+    for (int d = 0; d < 3; ++d) { c->grid_lo[d] = bb_lo[d] - 2 * margin; c->grid_h[d] = (ext[d] + 4 * margin) / c->grid_g[d]; }
+    cudaStream_t s = c->stream;
+    FB_CUDA(c, c->d_grid_cnt.alloc(2 * (size_t) nb + 4));
+    int* cnt = c->d_grid_cnt.p; int* ccnt = cnt + nb; int* totals = ccnt + nb;
+    FB_CUDA(c, c->d_grid_off.alloc(nb + 1)); FB_CUDA(c, c->d_grid_coff.alloc(nb + 1));
+    FB_CUDA(c, c->d_grid_clist.alloc(c->n_tet));
+    FB_CUDA(c, c->d_grid_list.alloc(std::max<size_t>(c->d_grid_list.n, 48 * (size_t) c->n_tet)));      // capacity; checked below
+    const int g = (c->n_tet + 127) / 128;
+    int h_tot[2] = {0, 0};
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        FB_CUDA(c, cudaMemsetAsync(cnt, 0, (2 * (size_t) nb + 4) * sizeof(int), s));
+        c->grid_on = true;
+        Tables T = make_tables(c);
+        c->grid_on = false;
+        const int cap = (int) std::min<size_t>(c->d_grid_list.n, 0x7fffffff);
+        k_grid_build<false><<<g, 128, 0, s>>>(T, T.grid, margin, cnt, ccnt, nullptr, nullptr, 0);
+        k_grid_scan<<<1, 1024, 0, s>>>((int) nb, cnt, c->d_grid_off.p, ccnt, c->d_grid_coff.p, totals);
+        k_grid_build<true><<<g, 128, 0, s>>>(T, T.grid, margin, cnt, ccnt, c->d_grid_list.p, c->d_grid_clist.p, cap);
+        c->launches += 3;
+        FB_CUDA(c, cudaMemcpyAsync(h_tot, totals, sizeof h_tot, cudaMemcpyDeviceToHost, s));
+        FB_CUDA(c, cudaStreamSynchronize(s));
+        if (h_tot[0] <= cap) break;
+        FB_CUDA(c, c->d_grid_list.alloc((size_t) h_tot[0]));        // graded mesh with huge far-field cells: exact size, once more
+    }
+    c->grid_on = true; c->grid_entries = h_tot[0];
+    if (getenv("FB_VERBOSE")) fprintf(stderr, "[fb] cell grid %d x %d x %d, %d list entries for %d tetrahedra\n", c->grid_g[0], c->grid_g[1], c->grid_g[2], h_tot[0], c->n_tet);
+    return FB_OK;
 }
 
 void launch_extract(fb_ctx* c, int smoothen) {
@@ -919,6 +1138,7 @@ int launch_locate_chain(fb_ctx* c, int dim, int rank, long n, const double* d_pt
     const int first_guess = (rank == 3) ? 0 : 1;
     const unsigned gs = (unsigned) ((n + 31) / 32);          // 32 points per block of 8 warps
     if (dim == 2) k_scan_cells<TriFam, 128><<<gs, 256, 0, c->stream>>>(T, n, d_pts, c->d_scan.p);
+    else if (T.grid.n_buckets > 0) k_scan_grid<<<(unsigned) ((n + 3) / 4), 128, 0, c->stream>>>(T, n, d_pts, c->d_scan.p);
     else k_scan_cells<TetFam, 128><<<gs, 256, 0, c->stream>>>(T, n, d_pts, c->d_scan.p);
     c->launches++;
     cudaMemsetAsync(c->d_flag.p, 0, 4 * sizeof(int), c->stream);

@@ -42,6 +42,7 @@ void launch_scatter(fb_ctx* c, int n, const int* idx, const double* src, double*
 
 // interp_kernels.cu
 void launch_extract(fb_ctx* c, int smoothen);
+int launch_build_cell_grid(fb_ctx* c, const double* bb_lo, const double* bb_hi);
 void launch_pack_points(fb_ctx* c, long n, const double* x, const double* y, const double* z, int stride, double* out);
 int launch_locate_chain(fb_ctx* c, int dim, int rank, long n, const double* d_pts, int** result, long chain_len = 0);
 void launch_finish_interp(fb_ctx* c, int dim, int rank, long n, const double* d_pts, const int* d_base, int final_cells,
