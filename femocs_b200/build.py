@@ -19,6 +19,7 @@ UNITS = [
     ("partition.cpp", []),
     ("poisson_kernels.cu", []),
     ("interp_kernels.cu", ["-fmad=false"]),
+    ("twolevel.cu", []),
     ("api.cu", []),
 ]
 

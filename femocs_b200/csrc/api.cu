@@ -186,6 +186,7 @@ int fb_set_option(fb_ctx* c, const char* key, double value) {
     else if (k == "cg_persistent") c->cg_persistent = (int) value;
     else if (k == "cg_debug") c->cg_debug = (int) value;
     else if (k == "mesh_reuse") c->mesh_reuse = (int) value;
+    else if (k == "tl_agg") { c->tl_agg_opt = (int) value; c->tl_ready = c->tl_agg_ready = false; drop_graph(c); }   // dofs per aggregate of FB_PRECOND_TWOLEVEL (0 = auto)
     else if (k == "cell_grid") c->cell_grid = (int) value;    // 0: brute-force tetrahedron scan (read by the next fb_interp_initialize)  // 0: fb_import_mesh never takes the unchanged-topology path
     else if (k == "cg_p2p") c->cg_p2p = (int) value;          // read by the next partitioned fb_import_mesh
     else if (k == "cg_persistent_ctas") { c->pers_ctas = (int) value; c->pers_grid = 0; }
@@ -363,7 +364,7 @@ static int import_mesh_impl(fb_ctx* c, const double* xyz, int n_nodes, const int
         // captured CG graph and every integer device array stay; the matrices and the interpolator tables depend on the
         // geometry and are rebuilt by the next assemble(true) / fb_interp_initialize
         c->setup_ok = c->assembled = c->matrix_ok = c->interp_ok = false;
-        c->jds_val_dirty = true; c->cheb_lmax = 0;
+        c->jds_val_dirty = true; c->cheb_lmax = 0; c->tl_ready = c->tl_agg_ready = false;
         const int n = c->n_cols;
         double* vx = (double*) c->pin_in.p;
         if (c->pin_in.bytes < 3 * (size_t) n * sizeof(double)) { FB_CUDA(c, c->pin_in.reserve(3 * (size_t) n * sizeof(double))); vx = (double*) c->pin_in.p; }
@@ -421,6 +422,7 @@ static int import_mesh_impl(fb_ctx* c, const double* xyz, int n_nodes, const int
     FB_CUDA(c, c->d_rowptr.upload(c->rowptr, s));
     FB_CUDA(c, c->d_col.upload(c->col, s));
     c->n_rowblk = 0; c->rowblk_chunk = 0; c->win_cap = 0; c->jds_ready = false; c->jds_val_dirty = true;
+    c->tl_ready = c->tl_agg_ready = false;
     c->pers_grid = 0;
     FB_CUDA(c, c->d_topfaces.upload(top, s));
     FB_CUDA(c, c->d_vertex2dof.upload(c->vertex2dof, s));
@@ -499,6 +501,7 @@ static int assemble_impl(fb_ctx* c, int first_time, const double* d_pxyz, const 
         fb::launch_bc_prepare(c);           // dinv (0 on constrained rows), diagpos
         c->jds_val_dirty = true;
         c->cheb_lmax = 0;                   // Gershgorin bound of the new matrix is computed by the next Chebyshev solve
+        c->tl_ready = false;                // ... and the coarse matrix of the two-level preconditioner by the next such solve
         c->matrix_ok = true;
     }
     // right-hand side: Neumann faces (or nothing), space charge; constrained dofs take their value in the solution
@@ -534,9 +537,11 @@ int fb_poisson_assemble(fb_ctx* c, int first_time, const double* pxyz, const int
 
 int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* n_iter, double* final_residual) {
     FB_REQUIRE(c, c->assembled, "fb_poisson_solve: system not assembled");
-    FB_REQUIRE(c, precond == FB_PRECOND_JACOBI || precond == FB_PRECOND_CHEBYSHEV,
-               "fb_poisson_solve: preconditioner must be FB_PRECOND_JACOBI or FB_PRECOND_CHEBYSHEV (SSOR is sequential and not provided)");
-    FB_REQUIRE(c, precond == FB_PRECOND_JACOBI || c->world == 1, "fb_poisson_solve: FB_PRECOND_CHEBYSHEV runs on un-partitioned meshes only");
+    FB_REQUIRE(c, precond == FB_PRECOND_JACOBI || precond == FB_PRECOND_CHEBYSHEV || precond == FB_PRECOND_TWOLEVEL,
+               "fb_poisson_solve: preconditioner must be FB_PRECOND_JACOBI, FB_PRECOND_CHEBYSHEV or FB_PRECOND_TWOLEVEL (SSOR is sequential and not provided)");
+    FB_REQUIRE(c, precond == FB_PRECOND_JACOBI || c->world == 1, "fb_poisson_solve: FB_PRECOND_CHEBYSHEV / FB_PRECOND_TWOLEVEL run on un-partitioned meshes only");
+    const bool tl = precond == FB_PRECOND_TWOLEVEL;
+    c->tl_active = false;
     const bool cheb = precond == FB_PRECOND_CHEBYSHEV && c->cheb_degree >= 2;        // degree 1 is Jacobi up to a scale factor
     c->cheb_active = false;
     cudaSetDevice(c->device);
@@ -547,7 +552,7 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
     *h = init;
     long spmv = 1;
     c->prof_samples = 0; c->prof_spmv_ms = c->prof_vec_ms = 0;
-    const bool persistent = c->world == 1 && c->cg_profile == 0 && !cheb && fb::persistent_eligible(c);
+    const bool persistent = c->world == 1 && c->cg_profile == 0 && !cheb && !tl && fb::persistent_eligible(c);
     if (c->world > 1) { h->red = c->d_red.p; if (c->p2p_ready) h->p2p = c->d_p2p.p; }
     FB_CUDA(c, cudaEventRecord(c->ev0, s));
     FB_CUDA(c, cudaMemcpyAsync(c->d_cg.p, h, sizeof(fb::CgScalars), cudaMemcpyHostToDevice, s));
@@ -571,7 +576,7 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
         }
     } else {
         int lanes = fb::choose_lanes(c);
-        if (cheb && lanes >= 310) lanes = 304;      // the Chebyshev steps multiply by the FULL matrix: the symmetric (lower-triangle) layout cannot serve them
+        if ((cheb || tl) && lanes >= 310) lanes = 304;      // the Chebyshev steps multiply by the FULL matrix: the symmetric (lower-triangle) layout cannot serve them
         while (lanes >= 300) {                     // block-JDS SpMV: tables once per mesh, values once per assemble
             const bool sym = lanes >= 310;         // 310/311: symmetric layout (lower triangle only)
             const int R = sym ? (lanes == 311 ? 256 : 512) : ((lanes == 301) ? 128 : ((lanes >= 302 && lanes <= 305) ? 512 : 256));
@@ -683,6 +688,13 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
             }
         } else {
             int graph_key = lanes;
+            if (tl) {
+                const int rc = fb::tl_prepare(c);
+                if (rc) return rc;
+                c->tl_active = true;
+                graph_key = lanes + 100000;
+                FB_CUDA(c, cudaMemcpyAsync(c->d_cg.p, h, sizeof(fb::CgScalars), cudaMemcpyHostToDevice, s));   // tl_prepare used the stream
+            }
             if (cheb) {
                 FB_CUDA(c, fb::cheb_prepare(c, lanes));
                 c->cheb_active = true;
@@ -750,7 +762,7 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
             }
             while (!h->done) {
                 FB_CUDA(c, cudaGraphLaunch(c->cg_graph, s));
-                c->launches += (cheb ? 1L + 2L * c->cheb_k : (c->world > 1 ? 6L : 3L)) * c->cg_graph_n;
+                c->launches += (cheb ? 1L + 2L * c->cheb_k : (tl ? 5L : (c->world > 1 ? 6L : 3L))) * c->cg_graph_n;
                 spmv += (long) (cheb ? c->cheb_k : 1) * c->cg_graph_n;
                 FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
                 FB_CUDA(c, cudaStreamSynchronize(s));
@@ -936,7 +948,7 @@ static void ch_activate(fb_ctx* c, int which) {
     std::swap(c->d_x.p, c->d_x_other.p); std::swap(c->d_x.n, c->d_x_other.n);
     c->ch_active = which;
     drop_graph(c);                      // captured launches hold the old pointers
-    c->jds_val_dirty = true; c->cheb_lmax = 0;
+    c->jds_val_dirty = true; c->cheb_lmax = 0; c->tl_ready = false;
     c->assembled = false;               // the Dirichlet mask / dinv / rhs belong to the system assembled last
 }
 static double* ch_solution(fb_ctx* c, int which) { return which == c->ch_active ? c->d_x.p : c->d_x_other.p; }
@@ -985,7 +997,7 @@ static int ch_finish_assembly(fb_ctx* c, int which, double dirichlet_value) {
     c->n_dirichlet = c->n_dirichlet_cu;
     fb::launch_bc_prepare(c);
     fb::launch_bc_solution(c);
-    c->jds_val_dirty = true; c->cheb_lmax = 0;
+    c->jds_val_dirty = true; c->cheb_lmax = 0; c->tl_ready = false;
     c->matrix_ok = true; c->assembled = true;
     c->ch_assembled[which] = true; c->ch_assembled[1 - which] = false;
     return sync_check(c, which ? "fb_heat_assemble" : "fb_current_assemble");

@@ -40,6 +40,11 @@ void launch_solution_grad(fb_ctx* c, double* d_grad3);
 void launch_gather(fb_ctx* c, int n, const int* idx, const double* src, double* dst);
 void launch_scatter(fb_ctx* c, int n, const int* idx, const double* src, double* dst);
 
+// twolevel.cu
+int tl_prepare(fb_ctx* c);
+void launch_tl_init_tail(fb_ctx* c);
+void launch_tl_vectors(fb_ctx* c);
+
 // interp_kernels.cu
 void launch_extract(fb_ctx* c, int smoothen);
 int launch_build_cell_grid(fb_ctx* c, const double* bb_lo, const double* bb_hi);

@@ -1752,6 +1752,12 @@ void launch_cg_init(fb_ctx* c, int lanes) {
         c->launches++;
         return;
     }
+    if (c->tl_active) {          // two-level preconditioner: the INIT SpMV leaves g, gh = g.Dinv g, |g|; twolevel.cu adds the coarse part
+        c->h_needs_zero = false;
+        spmv_dispatch<true>(c, lanes, c->d_x.p, c->d_g.p, nullptr);
+        launch_tl_init_tail(c);
+        return;
+    }
     c->h_needs_zero = lanes >= 310;
     if (c->h_needs_zero) cudaMemsetAsync(c->d_h.p, 0, (size_t) c->n_dofs * sizeof(double), c->stream);
     spmv_dispatch<true>(c, lanes, c->d_x.p, c->d_g.p, nullptr);
@@ -1768,6 +1774,7 @@ void launch_cg_vectors(fb_ctx* c) {               // x, g update + dots + conver
     unsigned* counter = (unsigned*) (c->d_partial.p + c->d_partial.n - 8);
     const int g = grid_for(c, c->n_dofs, 256);
     const int gu = std::min(g, c->n_sm * 6);          // k_update: 6 resident blocks per SM, one wave
+    if (c->tl_active) { launch_tl_vectors(c); return; }
     if (c->cheb_active) {       // Chebyshev-preconditioned iteration: update (+ first step), k-1 x (SpMV + step), direction
         k_update<false, true><<<gu, 256, 0, c->stream>>>(c->n_dofs, c->d_d.p, c->d_h.p, c->d_dinv.p, c->d_x.p, c->d_g.p, c->d_partial.p, counter,
                                                          c->d_cg.p, alpha_ptr(c), beta_ptr(c), c->d_cheb_p.p, c->d_z.p, c->cheb_inv_theta);

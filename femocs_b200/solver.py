@@ -25,6 +25,7 @@ from . import lib as _lib
 
 PRECOND_JACOBI = 1
 PRECOND_CHEBYSHEV = 2
+PRECOND_TWOLEVEL = 3
 
 
 class FemocsB200Error(RuntimeError):
