@@ -161,6 +161,7 @@ void fb_destroy(fb_ctx* c) {
     if (c->host_only) { delete c; return; }
     cudaSetDevice(c->device);
     p2p_release(c);
+    fb::tl_release(c);
     if (c->nccl_comm) { cudaStreamSynchronize(c->stream); fb::Nccl::get().CommDestroy((ncclComm_t) c->nccl_comm); c->nccl_comm = nullptr; }
     drop_graph(c);
     if (c->ev0) cudaEventDestroy(c->ev0);

@@ -195,7 +195,7 @@ struct fb_ctx {
     int cheb_k = 0, cheb_lanes = 0, cheb_power_iters = 15; bool cheb_active = false; double cheb_gershgorin = 0;
     fb::DevBuf<double> d_cheb_p, d_cheb_r;
     // two-level preconditioner (twolevel.cu): Morton aggregates (per mesh), dense inverse of the Galerkin matrix (per matrix)
-    bool tl_active = false, tl_ready = false, tl_agg_ready = false; int tl_agg_opt = 0, tl_agg = 0, tl_nc = 0;
+    bool tl_active = false, tl_ready = false, tl_agg_ready = false; int tl_agg_opt = 0, tl_agg = 0, tl_nc = 0; void* tl_solver = nullptr;
     fb::DevBuf<int> d_tl_perm, d_tl_agg; fb::DevBuf<double> d_tl_inv, d_tl_rc, d_tl_ec;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> prof_ev;        // 3 events per profiled iteration

@@ -42,6 +42,7 @@ void launch_scatter(fb_ctx* c, int n, const int* idx, const double* src, double*
 
 // twolevel.cu
 int tl_prepare(fb_ctx* c);
+void tl_release(fb_ctx* c);
 void launch_tl_init_tail(fb_ctx* c);
 void launch_tl_vectors(fb_ctx* c);
 

@@ -268,7 +268,7 @@ int tl_prepare(fb_ctx* c) {
     cudaStream_t s = c->stream;
     const int n = c->n_dofs;
     if (!c->tl_agg_ready) {
-        int agg = c->tl_agg_opt > 0 ? c->tl_agg_opt : std::max(256, (int) ((n + 8191L) / 8192));
+        int agg = c->tl_agg_opt > 0 ? c->tl_agg_opt : std::max(256, (int) ((n + 4095L) / 4096));
         agg = (agg + 63) & ~63;
         c->tl_agg = agg; c->tl_nc = (int) ((n + (long) agg - 1) / agg);
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -298,8 +298,12 @@ int tl_prepare(fb_ctx* c) {
     k_tl_coarse_matrix<<<grid_for(c, n, 256), 256, 0, s>>>(n, nc, c->d_rowptr.p, c->d_col.p, c->d_val_save.p, c->d_dinv.p, c->d_tl_agg.p, c->d_tl_inv.p);
     k_tl_fix_diag<<<(nc + 255) / 256, 256, 0, s>>>(nc, c->d_tl_inv.p);
     c->launches += 2;
-    cusolverDnHandle_t h = nullptr;
-    if (S.Create(&h) != CUSOLVER_STATUS_SUCCESS) return c->fail(FB_ERR_CUDA, "cusolverDnCreate failed");
+    if (!c->tl_solver) {                                   // created once per context (cusolverDnCreate takes ~0.1 s)
+        cusolverDnHandle_t hn = nullptr;
+        if (S.Create(&hn) != CUSOLVER_STATUS_SUCCESS) return c->fail(FB_ERR_CUDA, "cusolverDnCreate failed");
+        c->tl_solver = hn;
+    }
+    cusolverDnHandle_t h = (cusolverDnHandle_t) c->tl_solver;
     S.SetStream(h, s);
     int lw1 = 0, lw2 = 0, info = 0;
     DevBuf<double> work; DevBuf<int> d_info;
@@ -310,13 +314,17 @@ int tl_prepare(fb_ctx* c) {
     if (ok) { cudaMemcpyAsync(&info, d_info.p, sizeof(int), cudaMemcpyDeviceToHost, s); cudaStreamSynchronize(s); ok = (info == 0); }
     if (ok) ok = S.Potri(h, CUBLAS_FILL_MODE_LOWER, nc, c->d_tl_inv.p, nc, work.p, lw2, d_info.p) == CUSOLVER_STATUS_SUCCESS;
     if (ok) { cudaMemcpyAsync(&info, d_info.p, sizeof(int), cudaMemcpyDeviceToHost, s); cudaStreamSynchronize(s); ok = (info == 0); }
-    S.Destroy(h);
     if (!ok) return c->fail(FB_ERR_CUDA, "FB_PRECOND_TWOLEVEL: Cholesky inverse of the %d x %d coarse matrix failed (info %d)", nc, nc, info);
     k_tl_symmetrize<<<(unsigned) (((long) nc * nc + 255) / 256), 256, 0, s>>>(nc, c->d_tl_inv.p);
     c->launches++;
     FB_CUDA(c, cudaStreamSynchronize(s));
     c->tl_ready = true;
     return FB_OK;
+}
+
+void tl_release(fb_ctx* c) {
+    if (c->tl_solver && Solver::get().ok) Solver::get().Destroy((cusolverDnHandle_t) c->tl_solver);
+    c->tl_solver = nullptr;
 }
 
 // tail of the initial step (after the INIT SpMV has left g, gh = g.Dinv g, |g|): coarse part of z, first direction

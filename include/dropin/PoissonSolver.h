@@ -53,9 +53,10 @@ public:
     {
         stat.sol_min = 0; stat.sol_max = 0;
         static_assert(dim == 3, "libfemocs_b200 solves on the 3D hexahedral mesh");
-        // FEMOCS_B200_DEVICE picks the CUDA ordinal, FEMOCS_B200_PRECOND=chebyshev the polynomial preconditioner
+        // FEMOCS_B200_DEVICE picks the CUDA ordinal, FEMOCS_B200_PRECOND=chebyshev | twolevel another preconditioner
         const char* p = getenv("FEMOCS_B200_PRECOND");
         if (p && string(p) == "chebyshev") precond = FB_PRECOND_CHEBYSHEV;
+        if (p && string(p) == "twolevel") precond = FB_PRECOND_TWOLEVEL;
     }
 
     PoissonSolver(const PoissonSolver&) = delete;
