@@ -188,6 +188,7 @@ int fb_set_option(fb_ctx* c, const char* key, double value) {
     else if (k == "cg_debug") c->cg_debug = (int) value;
     else if (k == "mesh_reuse") c->mesh_reuse = (int) value;
     else if (k == "tl_agg") { c->tl_agg_opt = (int) value; c->tl_ready = c->tl_agg_ready = false; drop_graph(c); }   // dofs per aggregate of FB_PRECOND_TWOLEVEL (0 = auto)
+    else if (k == "asm_map") { c->asm_map_opt = (int) value; c->asm_map_ready = false; }   // 0: assemble by walking the rows (no 256 B / hexahedron map)
     else if (k == "cell_grid") c->cell_grid = (int) value;    // 0: brute-force tetrahedron scan (read by the next fb_interp_initialize)  // 0: fb_import_mesh never takes the unchanged-topology path
     else if (k == "cg_p2p") c->cg_p2p = (int) value;          // read by the next partitioned fb_import_mesh
     else if (k == "cg_persistent_ctas") { c->pers_ctas = (int) value; c->pers_grid = 0; }
@@ -423,7 +424,7 @@ static int import_mesh_impl(fb_ctx* c, const double* xyz, int n_nodes, const int
     FB_CUDA(c, c->d_rowptr.upload(c->rowptr, s));
     FB_CUDA(c, c->d_col.upload(c->col, s));
     c->n_rowblk = 0; c->rowblk_chunk = 0; c->win_cap = 0; c->jds_ready = false; c->jds_val_dirty = true;
-    c->tl_ready = c->tl_agg_ready = false;
+    c->tl_ready = c->tl_agg_ready = false; c->asm_map_ready = false;
     c->pers_grid = 0;
     FB_CUDA(c, c->d_topfaces.upload(top, s));
     FB_CUDA(c, c->d_vertex2dof.upload(c->vertex2dof, s));

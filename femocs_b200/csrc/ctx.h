@@ -162,6 +162,7 @@ struct fb_ctx {
     // ---- device: solver ----
     fb::DevBuf<double> d_vxyz;               // coordinates per DoF (3*n_dofs)
     fb::DevBuf<int> d_cells;                 // 8*n_cells dof ids (lexicographic)
+    fb::DevBuf<int> d_asm_map; bool asm_map_ready = false; int asm_map_opt = 1;   // scatter map of the assembly (64 positions per hexahedron)
     fb::DevBuf<int> d_rowptr, d_col, d_diagpos, d_rowblk, d_win_off, d_win_list;
     fb::DevBuf<unsigned short> d_col16, d_jds_perm, d_jds_len, d_jds_slot;
     fb::DevBuf<int> d_jds_jdp, d_jds_jd, d_jds_base; fb::DevBuf<double> d_val_jds, d_diag;
