@@ -49,6 +49,17 @@ def _worker(rank, world, port, q, p2p):
         s.assemble(False)                                   # PIC step: warm start from the converged potential
         out["it_warm"] = s.solve(cg_tolerance=1e-7)
         out["launches"] = ctx.kernel_launches
+        # atoms are independent once the potential is known -- every rank keeps a REPLICA of the mesh
+        # tables (MBs) in a second, un-partitioned context, takes the complete potential of the partitioned solve and
+        # interpolates ITS shard of the atoms (contiguous blocks: the guess chain restarts per shard); no collective
+        rep = fb.Context(rank)
+        rs = fb.PoissonSolver(rep); assert rs.import_mesh(m["nodes"], m["hexs"], m["hex_markers"])
+        rs.import_solution(out["phi_poisson"])
+        it = fb.Interpolator(rep); it.initialize(m); it.extract_solution(rs, True)
+        atoms = m["atoms"]; lo = len(atoms) * rank // world; hi = len(atoms) * (rank + 1) // world
+        f = fb.FieldReader(it); f.set_preferences(False, 3, 1); f.interpolate(atoms[lo:hi])
+        out["shard"] = (lo, hi, f.markers.copy(), f.interpolation.copy())
+        rep.close()
         ctx.close()
         q.put((rank, "ok", out))
     except Exception as e:           # noqa: BLE001
@@ -87,6 +98,13 @@ def test_partitioned_solve_matches_oracle(world, p2p, golden):
     rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
     outs = [r[2] for r in res]
     assert sum(x["part"]["n_rows"] for x in outs) == o.n_vertices
+    # sharded atom interpolation on the replicas: every shard equals the oracle's answer for that block of atoms
+    o.extract_solution(True)
+    for x in outs:
+        lo, hi, cells, sol = x["shard"]
+        oc, osol = o.locate_interpolate(3, 1, m["atoms"][lo:hi])
+        assert np.array_equal(cells, oc)
+        assert np.abs(sol - osol).max() <= 1e-8 * np.abs(osol).max()
     for x in outs:
         # 2 = the iteration runs over peer mappings (CUDA IPC + NVLink stores, CUDA-graph captured), 1 = NCCL inside the iteration
         assert x["part"]["comm_mode"] == (2 if p2p else 1), x["part"]
