@@ -113,3 +113,18 @@ def test_unchanged_topology_is_reused(golden):
     g = PartitionPlan(0, 1).import_whole(bumped, h2, k2)
     assert np.array_equal(q.top, g.top) and np.array_equal(q.copper, g.copper)
     # option mesh_reuse = 0 is honoured by the full library only (plan contexts have no options): covered on the GPU
+
+
+def test_parallel_numbering_on_a_large_mesh_matches_oracle():
+    """meshes with more than 2e6 cell vertices take the parallel paths of the host import (atomic counting sort of the
+    vertex -> cells adjacency, first-touch numbering as a scan over first-occurrence flags): the result must be the serial
+    deal.II numbering the oracle restates"""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    nodes, hexs, mk = bench.load_x_mesh(0)                 # 350 424 hexahedra
+    p = PartitionPlan(0, 1).import_whole(nodes, hexs, mk)
+    o = Oracle(); o.import_mesh(nodes, hexs, mk)
+    rp, col, _, _ = o.csr()
+    assert np.array_equal(p.rowptr, rp) and np.array_equal(p.col, col)
+    assert np.array_equal(o.vectors()[2][o.cells()], p.cells_dof)
