@@ -189,6 +189,7 @@ int fb_set_option(fb_ctx* c, const char* key, double value) {
     else if (k == "mesh_reuse") c->mesh_reuse = (int) value;
     else if (k == "tl_agg") { c->tl_agg_opt = (int) value; c->tl_ready = c->tl_agg_ready = false; drop_graph(c); }   // dofs per aggregate of FB_PRECOND_TWOLEVEL (0 = auto)
     else if (k == "asm_map") { c->asm_map_opt = (int) value; c->asm_map_ready = false; }   // 0: assemble by walking the rows (no 256 B / hexahedron map)
+    else if (k == "charge_density") c->want_charge_density = (int) value;   // the reference's write_time(): the next assemble keeps rhs / dof_volume
     else if (k == "cell_grid") c->cell_grid = (int) value;    // 0: brute-force tetrahedron scan (read by the next fb_interp_initialize)  // 0: fb_import_mesh never takes the unchanged-topology path
     else if (k == "cg_p2p") c->cg_p2p = (int) value;          // read by the next partitioned fb_import_mesh
     else if (k == "cg_persistent_ctas") { c->pers_ctas = (int) value; c->pers_grid = 0; }
@@ -512,6 +513,14 @@ static int assemble_impl(fb_ctx* c, int first_time, const double* d_pxyz, const 
     if (n_parts > 0) {
         fb::launch_space_charge(c, n_parts, d_pxyz, d_pcell, charge_factor);
     }
+    // PoissonSolver.cpp:196-207: when a file is about to be written (option "charge_density", the reference's write_time())
+    // charge_density = rhs / dof_volume is kept, BEFORE the Dirichlet conditions touch the right-hand side; zeros otherwise
+    c->rho_valid = false;
+    if (c->want_charge_density && c->world == 1) {
+        FB_CUDA(c, c->d_rho.alloc(n));
+        fb::launch_charge_density(c, c->d_h.p);          // d_h is scratch until the solve
+        c->rho_valid = true;
+    }
     fb::launch_bc_solution(c);          // (partitioned: the solve exchanges the halo of x before the initial residual)
     c->assembled = true;
     return FB_OK;
@@ -834,6 +843,7 @@ int fb_export_charge_dens(fb_ctx* c, double* rho_vertex) {
     // PoissonSolver.cpp:198-207: charge_density is only filled when a file is being written
     // (outside the hot path); otherwise it is reinit'ed to zeros, which is what export returns.
     FB_REQUIRE(c, c->mesh_ok && rho_vertex, "fb_export_charge_dens: no mesh");
+    if (c->rho_valid) { cudaSetDevice(c->device); return export_by_vertex(c, c->d_rho.p, rho_vertex); }
     std::fill(rho_vertex, rho_vertex + c->n_vert, 0.0);
     return FB_OK;
 }

@@ -176,6 +176,7 @@ struct fb_ctx {
     fb::DevBuf<int> d_bc_dofs;               // Dirichlet candidates: copper dofs, then top dofs (uploaded once per mesh)
     int n_dirichlet_cu = 0, n_dirichlet_cu_top = 0;      // owned constrained rows: copper only / copper + top
     fb::DevBuf<double> d_rhs, d_x, d_g, d_d, d_h, d_dinv, d_z, d_w;
+    fb::DevBuf<double> d_rho; int want_charge_density = 0; bool rho_valid = false;   // PoissonSolver::charge_density (filled when the host is about to write files)
     fb::DevBuf<int> d_topfaces;              // 4 dof ids per top (Neumann) face
     fb::DevBuf<int> d_bcflag; fb::DevBuf<double> d_bcval;
     fb::DevBuf<double> d_partial;            // block partials for dot products

@@ -184,7 +184,7 @@ int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* 
     std::vector<unsigned char>& is_b = c->h_isb;
     is_b.assign(6 * (size_t) n_cells, 0);
     const int n_owned_v = c->part_n_owned >= 0 ? c->part_n_owned : n_vert;
-#pragma omp parallel for schedule(dynamic, 4096)
+#pragma omp parallel for schedule(dynamic, 512)
     for (int ce = 0; ce < n_cells; ++ce)
         for (int f = 0; f < 6; ++f) {
             int fv[4];

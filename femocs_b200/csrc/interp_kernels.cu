@@ -755,12 +755,13 @@ __device__ P3 hex_nodal_gradient(const double* __restrict__ nxyz, const double* 
 
 // Interpolator::store_solution (:103-123): Solution(Vec3(0), charge_dens, potential) on vacuum nodes
 __global__ void k_store_solution(int n_nodes, const int* __restrict__ node2vert, const int* __restrict__ vertex2dof,
-                                 const double* __restrict__ x, double* __restrict__ nodal) {
+                                 const double* __restrict__ x, const double* __restrict__ rho, double* __restrict__ nodal) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     const int v = node2vert[i];
     double* s = nodal + 5 * (long) i;
-    s[0] = 0; s[1] = 0; s[2] = 0; s[3] = 0;
+    s[0] = 0; s[1] = 0; s[2] = 0;
+    s[3] = (v >= 0 && rho) ? rho[vertex2dof[v]] : 0.0;
     s[4] = v >= 0 ? x[vertex2dof[v]] : 0.0;
 }
 
@@ -1094,7 +1095,8 @@ int launch_build_cell_grid(fb_ctx* c, const double* bb_lo, const double* bb_hi) 
 
 void launch_extract(fb_ctx* c, int smoothen) {
     const int g = (c->n_nodes + 127) / 128;
-    k_store_solution<<<(c->n_nodes + 255) / 256, 256, 0, c->stream>>>(c->n_nodes, c->d_node2vert.p, c->d_vertex2dof.p, c->d_x.p, c->d_nodal.p);
+    k_store_solution<<<(c->n_nodes + 255) / 256, 256, 0, c->stream>>>(c->n_nodes, c->d_node2vert.p, c->d_vertex2dof.p, c->d_x.p, c->rho_valid ? c->d_rho.p : nullptr,
+                                                                                c->d_nodal.p);
     k_nodal_field<<<g, 128, 0, c->stream>>>(c->n_nodes, c->d_node2vert.p, c->d_n2c_off.p, c->d_n2c_list.p, c->d_nxyz.p, c->d_hex8.p,
                                             c->d_nodal.p);
     c->launches += 2;

@@ -11,6 +11,7 @@ int choose_lanes(const fb_ctx* c);
 void stream_block_shape(int kernel, int& chunk, int& maxrows);
 void launch_assemble_stiffness(fb_ctx* c);
 void launch_cell_volumes(fb_ctx* c, double* d_cell_vol);
+void launch_charge_density(fb_ctx* c, double* d_scratch);
 void launch_neumann(fb_ctx* c);
 void launch_assemble_heat(fb_ctx* c, double gamma, const double* d_T_prev, const double* d_phi);
 void launch_set_bc(fb_ctx* c, const int* d_dofs, int n, double value);

@@ -339,6 +339,26 @@ __global__ void __launch_bounds__(ASM_BLOCK) k_assemble_stiffness_mapped(int n_c
     asm_scatter_mapped(Ke, c, n_cells, map, val);
 }
 
+// DealSolver::calc_dof_volumes (DealSolver.cpp:344-366): every dof receives the whole volume (sum of JxW) of each cell
+// it belongs to; then charge_density = rhs / dof_volume (PoissonSolver.cpp:198-205)
+__global__ void __launch_bounds__(ASM_BLOCK) k_dof_volumes(int n_cells, int n_rows, const int* __restrict__ cells, const double* __restrict__ vxyz,
+                                                           double* __restrict__ dof_vol) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    double X[8], Y[8], Z[8], Ke[36], vol; int d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        d[i] = __ldg(&cells[8 * (size_t) c + i]);
+        X[i] = __ldg(&vxyz[3 * (size_t) d[i]]); Y[i] = __ldg(&vxyz[3 * (size_t) d[i] + 1]); Z[i] = __ldg(&vxyz[3 * (size_t) d[i] + 2]);
+    }
+    hex_stiffness(X, Y, Z, Ke, vol);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (d[i] < n_rows) atomicAdd(&dof_vol[d[i]], vol);
+}
+__global__ void k_charge_density(int n, const double* __restrict__ rhs, const double* __restrict__ dof_vol, double* __restrict__ rho) {
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) rho[i] = rhs[i] / dof_vol[i];
+}
+
 __global__ void __launch_bounds__(ASM_BLOCK) k_assemble_stiffness(int n_cells, int n_rows, const int* __restrict__ cells,
                                                                  const double* __restrict__ vxyz,
                                                                  const int* __restrict__ rowptr, const int* __restrict__ col,
@@ -1569,6 +1589,14 @@ void launch_assemble_stiffness(fb_ctx* c) {
         k_assemble_stiffness<<<(c->n_cells + ASM_BLOCK - 1) / ASM_BLOCK, ASM_BLOCK, 0, c->stream>>>(
             c->n_cells, c->n_dofs, c->d_cells.p, c->d_vxyz.p, c->d_rowptr.p, c->d_col.p, c->d_val_save.p);
     c->launches++;
+}
+
+// charge_density = rhs (Neumann faces + space charge, before the Dirichlet conditions) / dof_volume, into c->d_rho
+void launch_charge_density(fb_ctx* c, double* d_scratch) {
+    cudaMemsetAsync(d_scratch, 0, (size_t) c->n_dofs * sizeof(double), c->stream);
+    k_dof_volumes<<<(c->n_cells + ASM_BLOCK - 1) / ASM_BLOCK, ASM_BLOCK, 0, c->stream>>>(c->n_cells, c->n_dofs, c->d_cells.p, c->d_vxyz.p, d_scratch);
+    k_charge_density<<<grid_for(c, c->n_dofs, 256), 256, 0, c->stream>>>(c->n_dofs, c->d_rhs.p, d_scratch, c->d_rho.p);
+    c->launches += 2;
 }
 
 void launch_cell_volumes(fb_ctx* c, double* d_cell_vol) {

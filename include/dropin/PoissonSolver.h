@@ -114,6 +114,8 @@ public:
                 part_cell[i++] = sp.cell;
             }
         }
+        // src/PoissonSolver.cpp:196-207: the charge density (rhs / dof volume) is kept only when a file is about to be written
+        fb_set_option(ctx, "charge_density", this->write_time() ? 1.0 : 0.0);
         if (fb_poisson_assemble(ctx, first_time, n ? part_xyz.data() : NULL, n ? part_cell.data() : NULL, n, charge_factor))
             complain("assemble");
     }

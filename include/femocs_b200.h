@@ -169,7 +169,9 @@ int fb_poisson_solve(fb_ctx* ctx, int max_iter, double abs_tol, int precond,
  * void PoissonSolver::export_charge_dens(vector<double>&)       src/PoissonSolver.cpp:141-149
  * both in solver-vertex order, n_vertices values. */
 int fb_export_solution(fb_ctx* ctx, double* phi_vertex);
-int fb_export_charge_dens(fb_ctx* ctx, double* rho_vertex);
+int fb_export_charge_dens(fb_ctx* ctx, double* rho_vertex);   /* zeros unless option "charge_density" = 1 was set before the
+                                                                   last assemble (the reference's write_time(), src/PoissonSolver.cpp:196-207):
+                                                                   then rhs / dof_volume (DealSolver::calc_dof_volumes :344-366) */
 /* void DealSolver::export_solution_grad(vector<Tensor<1,3>>&)    src/DealSolver.cpp:280-301
  *   grad3[3 v .. 3 v + 2] = MINUS the gradient of the solution, taken -- exactly as the reference does -- at Gauss point
  *   number vertex2node[v] of cell vertex2cell[v] (the LAST cell, in cell order, that holds vertex v; :317-341), not at

@@ -103,6 +103,7 @@ struct Oracle {
     double applied_field = 0, applied_potential = 0;
     int anode_dirichlet = 0;
     double last_res = 0;
+    int write_time = 0; std::vector<double> charge_density;   // PoissonSolver.cpp:196-207
     // ---------------- CurrentHeatSolver (bulk mesh: mesh_kind == 1) ----------------
     int mesh_kind = 0;                           // 0 = vacuum hexes (PoissonSolver), 1 = bulk hexes (CurrentHeatSolver)
     std::vector<double> ch_current, ch_heat;     // CurrentSolver::solution, HeatSolver::solution (dof order)
@@ -511,6 +512,18 @@ void assemble(Oracle& o, int first_time, const double* pxyz, const int* pcell, l
     if (!o.anode_dirichlet) assemble_rhs_faces(o, BID_TOP);
     else append_dirichlet(o, BID_TOP, o.applied_potential);
     if (pxyz && n_parts > 0) assemble_space_charge(o, pxyz, pcell, n_parts, charge_factor);
+    // PoissonSolver.cpp:196-207: charge density for the files, before the Dirichlet conditions; DealSolver.cpp:344-366 calc_dof_volumes
+    o.charge_density.assign(o.n_dofs, 0.0);
+    if (o.write_time) {
+        std::vector<double> dof_volume(o.n_dofs, 0.0);
+        for (int c = 0; c < (int) o.cells.size(); ++c)
+            for (int q = 0; q < 8; ++q) {
+                double JxW; V3 g[8];
+                cell_geometry(o, c, q, JxW, g);
+                for (int i = 0; i < 8; ++i) dof_volume[o.vertex2dof[o.cells[c][i]]] += JxW;
+            }
+        for (int d = 0; d < o.n_dofs; ++d) o.charge_density[d] = o.rhs[d] / dof_volume[d];
+    }
     apply_dirichlet(o);
 }
 
@@ -1253,8 +1266,10 @@ void fo_mesh_counts(void* h, long* n_faces, long* n_edges) {
 }
 void fo_export_charge_dens(void* h, double* rho_vertex) {
     Oracle& o = *(Oracle*) h;
-    for (size_t v = 0; v < o.vertex2dof.size(); ++v) rho_vertex[v] = 0.0;
+    for (size_t v = 0; v < o.vertex2dof.size(); ++v)
+        rho_vertex[v] = o.charge_density.size() == (size_t) o.n_dofs ? o.charge_density[o.vertex2dof[v]] : 0.0;
 }
+void fo_set_write_time(void* h, int on) { ((Oracle*) h)->write_time = on; }
 // DealSolver.cpp:157-167 check_limits
 int fo_check_limits(void* h, double lo, double hi, double* mn, double* mx) {
     Oracle& o = *(Oracle*) h;
@@ -1333,7 +1348,10 @@ void fo_extract_solution(void* h, int smoothen) {
     Oracle& o = *(Oracle*) h;
     for (int i = 0; i < o.n_nodes; ++i) {
         Sol s;
-        if (o.node2vert[i] >= 0) { s.s1 = 0.0; s.s2 = o.sol[o.vertex2dof[o.node2vert[i]]]; }
+        if (o.node2vert[i] >= 0) {      // store_solution(charge_dens, potential): Interpolator.cpp:175-179
+            const int d = o.vertex2dof[o.node2vert[i]];
+            s.s1 = o.charge_density.size() == (size_t) o.n_dofs ? o.charge_density[d] : 0.0; s.s2 = o.sol[d];
+        }
         o.nodal[i] = s;
     }
     for (int node = 0; node < o.n_nodes; ++node) {

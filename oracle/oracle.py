@@ -48,6 +48,7 @@ def lib():
         L.fo_get_cells.argtypes = [C.c_void_p, _ip]
         L.fo_export_solution.argtypes = [C.c_void_p, _dp]
         L.fo_export_charge_dens.argtypes = [C.c_void_p, _dp]
+        L.fo_set_write_time.argtypes = [C.c_void_p, C.c_int]
         L.fo_export_solution_grad.argtypes = [C.c_void_p, _dp]
         L.fo_mesh_counts.argtypes = [C.c_void_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]
         L.fo_check_limits.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -222,6 +223,10 @@ class Oracle:
         a = C.c_long(0); b = C.c_long(0)
         self.L.fo_mesh_counts(self.h, C.byref(a), C.byref(b))
         return a.value, b.value
+
+    def set_write_time(self, on):
+        """FileWriter::write_time() of the solver: the next assemble keeps charge_density = rhs / dof_volume"""
+        self.L.fo_set_write_time(self.h, int(on))
 
     def export_charge_dens(self):
         rho = np.zeros(self.n_vertices)

@@ -197,3 +197,30 @@ def test_bench_pic_step_sequence_matches_oracle(fb, torch, golden):
     leg.step(reseed=True)
     assert leg.n == 4000
     leg.close()
+
+
+def test_charge_density_when_the_host_writes_files(golden):
+    """PoissonSolver.cpp:196-207: with write_time() true the solver keeps charge_density = rhs / dof_volume (taken before
+    the Dirichlet conditions) and Interpolator::extract_solution stores it as scalar1; zeros otherwise"""
+    import femocs_b200 as fb
+    from oracle.oracle import Oracle
+    m = golden("mesh", "mdsmall"); g = golden("interp", "mdsmall")
+    ok = g["pic_ok"]; cf = -180.9512268 * 0.01
+    c = fb.Context(0)
+    s = fb.PoissonSolver(c, fb.FieldConfig(cg_tolerance=1e-11, mode="transient"))
+    assert s.import_mesh(m["nodes"], m["hexs"], m["hex_markers"])
+    it = fb.Interpolator(c); it.initialize(m)
+    o = Oracle(); o.import_mesh(m["nodes"], m["hexs"], m["hex_markers"]); o.interp_initialize(m)
+    s.set_particles(g["points"][ok], g["pic_cells"][ok], cf)
+    s.setup(0.5, 0.0); s.assemble(True); assert s.solve() > 0
+    assert np.all(s.export_charge_dens() == 0)
+    c.set_option("charge_density", 1); o.set_write_time(True)
+    s.setup(0.5, 0.0); s.assemble(True); assert s.solve() > 0
+    o.setup(0.5, 0.0, False); o.assemble(True, g["points"][ok], g["pic_cells"][ok], cf); assert o.solve(10000, 1e-11, 1.2, 0) > 0
+    rho, rho_o = s.export_charge_dens(), o.export_charge_dens()
+    assert np.abs(rho_o).max() > 0 and np.abs(rho - rho_o).max() <= 1e-11 * np.abs(rho_o).max()
+    it.extract_solution(s, True)
+    nod, nod_o = it.get_solutions(), o.extract_solution(True)
+    assert np.abs(nod[:, 3] - nod_o[:, 3]).max() <= 1e-11 * np.abs(nod_o[:, 3]).max()
+    assert np.abs(nod - nod_o).max() <= 1e-8 * np.abs(nod_o).max()
+    c.close()
