@@ -550,7 +550,9 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
     FB_REQUIRE(c, c->assembled, "fb_poisson_solve: system not assembled");
     FB_REQUIRE(c, precond == FB_PRECOND_JACOBI || precond == FB_PRECOND_CHEBYSHEV || precond == FB_PRECOND_TWOLEVEL,
                "fb_poisson_solve: preconditioner must be FB_PRECOND_JACOBI, FB_PRECOND_CHEBYSHEV or FB_PRECOND_TWOLEVEL (SSOR is sequential and not provided)");
-    FB_REQUIRE(c, precond == FB_PRECOND_JACOBI || c->world == 1, "fb_poisson_solve: FB_PRECOND_CHEBYSHEV / FB_PRECOND_TWOLEVEL run on un-partitioned meshes only");
+    FB_REQUIRE(c, precond != FB_PRECOND_CHEBYSHEV || c->world == 1, "fb_poisson_solve: FB_PRECOND_CHEBYSHEV runs on un-partitioned meshes only");
+    FB_REQUIRE(c, precond != FB_PRECOND_TWOLEVEL || c->world == 1 || c->p2p_ready,
+               "fb_poisson_solve: FB_PRECOND_TWOLEVEL on a partitioned mesh needs the peer-mapped iteration (fb_comm_mode 2)");
     const bool tl = precond == FB_PRECOND_TWOLEVEL;
     c->tl_active = false;
     const bool cheb = precond == FB_PRECOND_CHEBYSHEV && c->cheb_degree >= 2;        // degree 1 is Jacobi up to a scale factor
@@ -717,7 +719,8 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
             // capture included -- is the single-GPU one with k_pack_p2p in front of every SpMV
             if (c->world > 1) {
                 const int rc = halo_exchange(c, c->d_x.p); if (rc) return rc;
-                fb::launch_cg_init_spmv(c, lanes); fb::launch_cg_scalars(c, 0); fb::launch_cg_init_direction(c);
+                fb::launch_cg_init_spmv(c, lanes); fb::launch_cg_scalars(c, 0);
+                if (tl) fb::launch_tl_init_tail(c); else fb::launch_cg_init_direction(c);
             } else
                 fb::launch_cg_init(c, lanes);
             // CUDA graph of cg_graph_iters iterations; kernels become no-ops once cgs->done is set
@@ -747,7 +750,8 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
                     if (c->world > 1) {
                         fb::launch_pack_p2p(c, c->d_d.p); fb::launch_cg_spmv(c, lanes); fb::launch_cg_scalars(c, 1);
                         FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i + 1], s));
-                        fb::launch_cg_update_only(c); fb::launch_cg_scalars(c, 2); fb::launch_cg_direction_only(c);
+                        if (tl) fb::launch_tl_vectors(c);
+                        else { fb::launch_cg_update_only(c); fb::launch_cg_scalars(c, 2); fb::launch_cg_direction_only(c); }
                         FB_CUDA(c, cudaEventRecord(c->prof_ev[3 * i + 2], s));
                         continue;
                     }
@@ -773,7 +777,7 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
             }
             while (!h->done) {
                 FB_CUDA(c, cudaGraphLaunch(c->cg_graph, s));
-                c->launches += (cheb ? 1L + 2L * c->cheb_k : (tl ? 5L : (c->world > 1 ? 6L : 3L))) * c->cg_graph_n;
+                c->launches += (cheb ? 1L + 2L * c->cheb_k : (tl ? (c->world > 1 ? 8L : 5L) : (c->world > 1 ? 6L : 3L))) * c->cg_graph_n;
                 spmv += (long) (cheb ? c->cheb_k : 1) * c->cg_graph_n;
                 FB_CUDA(c, cudaMemcpyAsync(h, c->d_cg.p, sizeof(fb::CgScalars), cudaMemcpyDeviceToHost, s));
                 FB_CUDA(c, cudaStreamSynchronize(s));

@@ -62,10 +62,13 @@ struct HexRec { double f[8][3]; };                              // 192 B: Linear
 // ---- partitioned CG without NCCL inside the iteration: peer-mapped (CUDA IPC) buffers over NVLink ------------------
 // Every rank owns one P2pSlots record in IPC-shared memory; PEERS write into it, the owner polls it.
 constexpr int P2P_MAX = 16;
+constexpr int TL_SLOT = 8200;           // coarse unknowns (+ 2 scalars) of the two-level preconditioner a rank can exchange
 struct P2pSlots {
     double red[2][P2P_MAX][2];          // [reduction of the iteration: 0 = after the SpMV, 1 = after the update][source rank][2 sums]
     long long red_seq[2][P2P_MAX];      // sequence number of the sums above (release / acquire at system scope)
     long long halo_flag[P2P_MAX];       // [source rank]: number of halo exchanges whose values have landed in the ghost segment
+    long long tl_seq[P2P_MAX];          // two-level preconditioner: sequence number of the partial restriction below
+    double tl[P2P_MAX][TL_SLOT];        // [source rank]: that rank's P^T g (n_c values) followed by its g.Dinv g and g.g
 };
 struct P2pDesc {                        // device-resident descriptor read by the kernels
     int rank, world;
@@ -76,6 +79,7 @@ struct P2pDesc {                        // device-resident descriptor read by th
     int n_recv[P2P_MAX];                // ghost values expected from peer p
     long long red_count[2];             // reductions completed (per kind); identical on all ranks
     long long halo_count;               // halo exchanges completed
+    long long tl_count;                 // restriction exchanges completed
 };
 
 struct CgScalars {          // device-resident CG state (one struct, updated by the kernels)
@@ -198,7 +202,8 @@ struct fb_ctx {
     fb::DevBuf<double> d_cheb_p, d_cheb_r;
     // two-level preconditioner (twolevel.cu): Morton aggregates (per mesh), dense inverse of the Galerkin matrix (per matrix)
     bool tl_active = false, tl_ready = false, tl_agg_ready = false; int tl_agg_opt = 0, tl_agg = 0, tl_nc = 0; void* tl_solver = nullptr;
-    fb::DevBuf<int> d_tl_perm, d_tl_agg; fb::DevBuf<double> d_tl_inv, d_tl_rc, d_tl_ec;
+    fb::DevBuf<int> d_tl_perm, d_tl_agg, d_tl_aoff; fb::DevBuf<double> d_tl_inv, d_tl_rc, d_tl_ec, d_tl_rc_part;
+    std::vector<double> part_gxyz;           // partitioned import: coordinates of ALL global solver vertices (global Morton aggregates)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> prof_ev;        // 3 events per profiled iteration
     double prof_spmv_ms = 0, prof_vec_ms = 0; int prof_samples = 0;

@@ -123,5 +123,6 @@ int fb_host_partition_phase1(fb_ctx* c, const double* xyz, int n_nodes, const in
         for (int k = 0; k < 8; ++k) hex_l[8 * (size_t) lc + k] = g2l[node2vert[h[k]]];
     }
     c->part_n_owned = n_own;
+    c->part_gxyz.swap(vx);              // global vertex coordinates: the two-level preconditioner aggregates along the GLOBAL Morton curve
     return fb_host_import_phase1(c, xyz_l.data(), n_loc, hex_l.data(), mark_l.data(), ncl);
 }

@@ -1899,6 +1899,7 @@ void launch_cg_iteration(fb_ctx* c, int lanes) {
         launch_pack_p2p(c, c->d_d.p);
         launch_cg_spmv(c, lanes);
         launch_cg_scalars(c, 1);
+        if (c->tl_active) { launch_tl_vectors(c); return; }     // update | restrict | exchange | coarse solve | direction (twolevel.cu)
         launch_cg_update_only(c);
         launch_cg_scalars(c, 2);
         launch_cg_direction_only(c);

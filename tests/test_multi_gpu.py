@@ -49,6 +49,12 @@ def _worker(rank, world, port, q, p2p):
         s.assemble(False)                                   # PIC step: warm start from the converged potential
         out["it_warm"] = s.solve(cg_tolerance=1e-7)
         out["launches"] = ctx.kernel_launches
+        if p2p:     # the two-level preconditioner on the partitioned mesh (global Morton aggregates, restriction summed over the peer mappings)
+            s.conf.precond = fb.PRECOND_TWOLEVEL
+            ctx.set_option("tl_agg", 64)
+            s.setup(0.5, 0.0); s.assemble(True)
+            out["it_tl"] = s.solve(); out["phi_tl"] = s.export_solution()
+            s.conf.precond = fb.PRECOND_JACOBI
         # atoms are independent once the potential is known -- every rank keeps a REPLICA of the mesh
         # tables (MBs) in a second, un-partitioned context, takes the complete potential of the partitioned solve and
         # interpolates ITS shard of the atoms (contiguous blocks: the guess chain restarts per shard); no collective
@@ -114,3 +120,6 @@ def test_partitioned_solve_matches_oracle(world, p2p, golden):
         assert rel(x["phi_poisson"], ref_p) < 1e-8
         assert not x["limits"][0] and x["limits"][1] == 0.0 and abs(x["limits"][2] - ref_l.max()) < 1e-8 * ref_l.max()
         assert x["part"]["n_send"] > 0 and x["launches"] > 0
+        if p2p:
+            assert 0 < x["it_tl"] < 0.8 * x["it_poisson"] and x["it_tl"] == outs[0]["it_tl"], (x["it_tl"], x["it_poisson"])
+            assert rel(x["phi_tl"], ref_p) < 1e-8
