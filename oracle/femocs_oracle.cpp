@@ -104,6 +104,9 @@ struct Oracle {
     int anode_dirichlet = 0;
     double last_res = 0;
     int write_time = 0; std::vector<double> charge_density;   // PoissonSolver.cpp:196-207
+    // FE_Q(2) variant (the reference built with DealSolver.h:130 shape_degree = 2, hence QGauss(3): north star config 2)
+    int fe_degree = 1;
+    std::vector<std::array<int, 27>> cdofs;      // dofs of a cell, local node (i, j, k) in {0, 1, 2}^3 at index i + 3 j + 9 k
     // ---------------- CurrentHeatSolver (bulk mesh: mesh_kind == 1) ----------------
     int mesh_kind = 0;                           // 0 = vacuum hexes (PoissonSolver), 1 = bulk hexes (CurrentHeatSolver)
     std::vector<double> ch_current, ch_heat;     // CurrentSolver::solution, HeatSolver::solution (dof order)
@@ -202,6 +205,7 @@ void cell_geometry(const Oracle& o, int cell, int q, double& JxW, V3 grad[8]) {
 // :460-518 (mark_boundary), PoissonSolver.cpp:52-55 (mark_mesh), DealSolver.cpp:368-387 (setup_system)
 // kind 1: TetgenCells.cpp:688-701 (export_bulk: marker < 0) and CurrentHeatSolver.cpp:526-530 mark_mesh
 // (top -> copper_surface, bottom -> copper_bottom, sides -> copper_sides, other -> copper_surface)
+void q2_distribute(Oracle& o);
 int import_mesh(Oracle& o, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker_in, int n_hex, int kind = 0) {
     o.mesh_kind = kind;
     std::vector<int> sel(n_hex);                 // > 0: the hexahedron belongs to this solver's mesh
@@ -345,6 +349,7 @@ int import_mesh(Oracle& o, const double* xyz, int n_nodes, const int* hex8, cons
     o.rhs.assign(o.n_dofs, 0.0);
     o.sol.assign(o.n_dofs, 0.0);
     o.boundary_values.clear();
+    if (o.fe_degree == 2) q2_distribute(o);
     return 0;
 }
 
@@ -352,6 +357,168 @@ inline int csr_pos(const Oracle& o, int r, int c) {
     auto b = o.col.begin() + o.rowptr[r], e = o.col.begin() + o.rowptr[r + 1];
     auto it = std::lower_bound(b, e, c);
     return (it != e && *it == c) ? (int) (it - o.col.begin()) : -1;
+}
+
+
+// ============================================================================
+//  FE_Q(2) variant: what the reference's solver does when DealSolver.h:130 reads shape_degree = 2 (quadrature_degree
+//  = shape_degree + 1 = 3 follows, :131).  Same call sites as above (setup_system, assemble_parallel, assemble_rhs,
+//  append_dirichlet, calc_vertex2dof); deal.II 9.2 FE_Q(2) (tensor-product Lagrange basis on the support points
+//  0, 1/2, 1), QGauss(3), MappingQ1 (trilinear geometry from the 8 vertices).  Parity unpinned like the rest of the
+//  solver half; validated in tests/test_oracle_q2.py (independent numpy derivation, linear exactness, order of
+//  convergence above FE_Q(1)).
+// ============================================================================
+const double Q2_GP[3] = {0.5 - 0.5 * std::sqrt(0.6), 0.5, 0.5 + 0.5 * std::sqrt(0.6)};   // QGauss<1>(3) on [0, 1]
+const double Q2_GW[3] = {5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0};
+inline void lagrange2(double x, double L[3], double dL[3]) {
+    L[0] = 2.0 * (x - 0.5) * (x - 1.0); L[1] = 4.0 * x * (1.0 - x); L[2] = 2.0 * x * (x - 0.5);
+    dL[0] = 4.0 * x - 3.0; dL[1] = 4.0 - 8.0 * x; dL[2] = 4.0 * x - 1.0;
+}
+// local nodes in the order deal.II numbers the dofs of a cell (dof_handler_policy.cc distribute_dofs_on_cell: vertices,
+// lines, quads, hex; GeometryInfo<3> line / face numbering), each as (i, j, k) with 0 / 2 = the end points, 1 = the middle
+const int Q2_ORDER[27][3] = {
+    {0, 0, 0}, {2, 0, 0}, {0, 2, 0}, {2, 2, 0}, {0, 0, 2}, {2, 0, 2}, {0, 2, 2}, {2, 2, 2},                    // vertices 0..7
+    {0, 1, 0}, {2, 1, 0}, {1, 0, 0}, {1, 2, 0}, {0, 1, 2}, {2, 1, 2}, {1, 0, 2}, {1, 2, 2},                    // lines 0..7
+    {0, 0, 1}, {2, 0, 1}, {0, 2, 1}, {2, 2, 1},                                                                // lines 8..11
+    {0, 1, 1}, {2, 1, 1}, {1, 0, 1}, {1, 2, 1}, {1, 1, 0}, {1, 1, 2},                                          // quads 0..5
+    {1, 1, 1}};                                                                                                // hex
+// the 9 local nodes of face f, (a, b) lexicographic in the two free directions (the order of FACE_VERTS at the corners)
+inline void q2_face_nodes(int f, int nodes[9]) {
+    const int fixed = f / 2, val = (f % 2) * 2;
+    const int d0 = fixed == 0 ? 1 : 0, d1 = fixed == 2 ? 1 : 2;
+    for (int b = 0; b < 3; ++b)
+        for (int a = 0; a < 3; ++a) {
+            int ijk[3]; ijk[fixed] = val; ijk[d0] = a; ijk[d1] = b;
+            nodes[a + 3 * b] = ijk[0] + 3 * ijk[1] + 9 * ijk[2];
+        }
+}
+
+// DoFHandler::distribute_dofs for FE_Q(2) + DoFTools::make_sparsity_pattern (DealSolver.cpp:368-387) and
+// calc_vertex2dof (:317-341: vertex_dof_index -> only the vertex dofs are exported)
+void q2_distribute(Oracle& o) {
+    const int n_cells = (int) o.cells.size(), n_vert = (int) o.vert2node.size();
+    o.vertex2dof.assign(n_vert, -1);
+    std::map<std::pair<int, int>, int> line_dof;
+    std::map<std::array<int, 4>, int> quad_dof;
+    o.cdofs.assign(n_cells, {});
+    o.n_dofs = 0;
+    for (int c = 0; c < n_cells; ++c)
+        for (int l = 0; l < 27; ++l) {
+            const int* ijk = Q2_ORDER[l];
+            // the vertices of the entity (vertex / line / quad / hex) this node sits on
+            int ent[8], ne = 0;
+            for (int v = 0; v < 8; ++v) {
+                const int b[3] = {v & 1, (v >> 1) & 1, (v >> 2) & 1};
+                bool on = true;
+                for (int d = 0; d < 3; ++d) if (ijk[d] != 1 && ijk[d] != 2 * b[d]) on = false;
+                if (on) ent[ne++] = o.cells[c][v];
+            }
+            std::sort(ent, ent + ne);
+            int* slot = nullptr; int hexdof = -1;
+            if (ne == 1) slot = &o.vertex2dof[ent[0]];
+            else if (ne == 2) slot = &line_dof.emplace(std::make_pair(ent[0], ent[1]), -1).first->second;
+            else if (ne == 4) slot = &quad_dof.emplace(std::array<int, 4>{ent[0], ent[1], ent[2], ent[3]}, -1).first->second;
+            else slot = &hexdof;
+            if (*slot < 0) *slot = o.n_dofs++;
+            o.cdofs[c][ijk[0] + 3 * ijk[1] + 9 * ijk[2]] = *slot;
+        }
+    o.dof2vertex.assign(o.n_dofs, -1);
+    for (int v = 0; v < n_vert; ++v) o.dof2vertex[o.vertex2dof[v]] = v;
+    std::vector<int> d2c_off(o.n_dofs + 1, 0);
+    for (int c = 0; c < n_cells; ++c) for (int i = 0; i < 27; ++i) ++d2c_off[o.cdofs[c][i] + 1];
+    for (int r = 0; r < o.n_dofs; ++r) d2c_off[r + 1] += d2c_off[r];
+    std::vector<int> d2c(d2c_off[o.n_dofs]), fill(d2c_off.begin(), d2c_off.end() - 1);
+    for (int c = 0; c < n_cells; ++c) for (int i = 0; i < 27; ++i) d2c[fill[o.cdofs[c][i]]++] = c;
+    o.rowptr.assign(o.n_dofs + 1, 0);
+    std::vector<std::vector<int>> rows(o.n_dofs);
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int r = 0; r < o.n_dofs; ++r) {
+        std::vector<int>& row = rows[r];
+        for (int k = d2c_off[r]; k < d2c_off[r + 1]; ++k)
+            for (int j = 0; j < 27; ++j) row.push_back(o.cdofs[d2c[k]][j]);
+        std::sort(row.begin(), row.end());
+        row.erase(std::unique(row.begin(), row.end()), row.end());
+    }
+    for (int r = 0; r < o.n_dofs; ++r) o.rowptr[r + 1] = o.rowptr[r] + (int) rows[r].size();
+    o.col.resize(o.rowptr[o.n_dofs]);
+    for (int r = 0; r < o.n_dofs; ++r) std::copy(rows[r].begin(), rows[r].end(), o.col.begin() + o.rowptr[r]);
+    o.val.assign(o.col.size(), 0.0); o.val_save.assign(o.col.size(), 0.0);
+    o.rhs.assign(o.n_dofs, 0.0); o.sol.assign(o.n_dofs, 0.0);
+}
+
+// PoissonSolver.cpp:213-263 with FE_Q(2) / QGauss(3): K_ab = sum_q JxW_q grad phi_a . grad phi_b
+void q2_assemble_matrix(Oracle& o) {
+    const int n_cells = (int) o.cells.size();
+    std::vector<double> Ke(27 * 27);
+    for (int c = 0; c < n_cells; ++c) {
+        std::fill(Ke.begin(), Ke.end(), 0.0);
+        V3 xv[8];
+        for (int v = 0; v < 8; ++v) xv[v] = cell_vertex(o, c, v);
+        for (int q = 0; q < 27; ++q) {
+            const double xi[3] = {Q2_GP[q % 3], Q2_GP[(q / 3) % 3], Q2_GP[q / 9]};
+            double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};      // MappingQ1: J[d][e] = dx_d / dxi_e
+            for (int v = 0; v < 8; ++v) {
+                double f[3], df[3];
+                for (int d = 0; d < 3; ++d) { const int bit = (v >> d) & 1; f[d] = bit ? xi[d] : 1.0 - xi[d]; df[d] = bit ? 1.0 : -1.0; }
+                const double dn[3] = {df[0] * f[1] * f[2], f[0] * df[1] * f[2], f[0] * f[1] * df[2]};
+                for (int e = 0; e < 3; ++e) { J[0][e] += xv[v].x * dn[e]; J[1][e] += xv[v].y * dn[e]; J[2][e] += xv[v].z * dn[e]; }
+            }
+            const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0])
+                             + J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+            double inv[3][3];
+            inv[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det; inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
+            inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det; inv[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / det;
+            inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det; inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+            inv[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det; inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
+            inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+            const double JxW = det * Q2_GW[q % 3] * Q2_GW[(q / 3) % 3] * Q2_GW[q / 9];
+            double L[3][3], dL[3][3];
+            for (int d = 0; d < 3; ++d) lagrange2(xi[d], L[d], dL[d]);
+            V3 g[27];
+            for (int a = 0; a < 27; ++a) {
+                const int i = a % 3, j = (a / 3) % 3, k = a / 9;
+                const double r[3] = {dL[0][i] * L[1][j] * L[2][k], L[0][i] * dL[1][j] * L[2][k], L[0][i] * L[1][j] * dL[2][k]};
+                g[a].x = r[0] * inv[0][0] + r[1] * inv[1][0] + r[2] * inv[2][0];
+                g[a].y = r[0] * inv[0][1] + r[1] * inv[1][1] + r[2] * inv[2][1];
+                g[a].z = r[0] * inv[0][2] + r[1] * inv[1][2] + r[2] * inv[2][2];
+            }
+            for (int a = 0; a < 27; ++a) for (int b = 0; b < 27; ++b) Ke[27 * a + b] += JxW * dot(g[a], g[b]);
+        }
+        for (int a = 0; a < 27; ++a)
+            for (int b = 0; b < 27; ++b) o.val[csr_pos(o, o.cdofs[c][a], o.cdofs[c][b])] += Ke[27 * a + b];
+    }
+    o.val_save = o.val;
+}
+
+// DealSolver.cpp:389-430 assemble_rhs(bid) with FE_Q(2) face shape functions and QGauss<2>(3)
+void q2_assemble_rhs_faces(Oracle& o, int bid) {
+    for (const auto& bf : o.bfaces) {
+        if (bf.id != bid) continue;
+        V3 p[4];
+        for (int v = 0; v < 4; ++v) p[v] = cell_vertex(o, bf.cell, FACE_VERTS[bf.face][v]);
+        int nodes[9]; q2_face_nodes(bf.face, nodes);
+        double cell_rhs[9] = {};
+        for (int q = 0; q < 9; ++q) {
+            const double s = Q2_GP[q % 3], t = Q2_GP[q / 3];
+            const V3 ds = (p[1] - p[0]) * (1 - t) + (p[3] - p[2]) * t;
+            const V3 dt = (p[2] - p[0]) * (1 - s) + (p[3] - p[1]) * s;
+            const V3 n = cross(ds, dt);
+            const double JxW = std::sqrt(dot(n, n)) * Q2_GW[q % 3] * Q2_GW[q / 3];
+            double Ls[3], Lt[3], dummy[3];
+            lagrange2(s, Ls, dummy); lagrange2(t, Lt, dummy);
+            for (int i = 0; i < 9; ++i) cell_rhs[i] += Ls[i % 3] * Lt[i / 3] * o.applied_field * JxW;
+        }
+        for (int i = 0; i < 9; ++i) o.rhs[o.cdofs[bf.cell][nodes[i]]] += cell_rhs[i];
+    }
+}
+
+// DealSolver.cpp:432-435 append_dirichlet: interpolate_boundary_values touches every dof on the face (9 for FE_Q(2))
+void q2_append_dirichlet(Oracle& o, int bid, double value) {
+    for (const auto& bf : o.bfaces)
+        if (bf.id == bid) {
+            int nodes[9]; q2_face_nodes(bf.face, nodes);
+            for (int i = 0; i < 9; ++i) o.boundary_values[o.cdofs[bf.cell][nodes[i]]] = value;
+        }
 }
 
 // PoissonSolver.cpp:162-167 setup + DealSolver.cpp:368-387 setup_system
@@ -366,6 +533,7 @@ void setup(Oracle& o, double field, double potential, int anode_dirichlet) {
 
 // PoissonSolver.cpp:213-263 assemble_parallel / assemble_local_cell, DealSolver.cpp:64-72 copy_global_cell
 void assemble_matrix(Oracle& o) {
+    if (o.fe_degree == 2) { q2_assemble_matrix(o); return; }
     const int n_cells = (int) o.cells.size();
     for (int c = 0; c < n_cells; ++c) {
         double Ke[8][8] = {};
@@ -386,6 +554,7 @@ void assemble_matrix(Oracle& o) {
 // DealSolver.cpp:389-430 assemble_rhs(bid) with get_face_bc = applied_field (PoissonSolver.cpp:152-154)
 // face_bc != nullptr: EmissionSolver::get_face_bc = (*bc_values)[boundary_face_index++] (CurrentHeatSolver.h:53-56)
 void assemble_rhs_faces(Oracle& o, int bid, const double* face_bc = nullptr) {
+    if (o.fe_degree == 2) { q2_assemble_rhs_faces(o, bid); return; }
     const double g[2] = {0.5 * (1.0 - 1.0 / std::sqrt(3.0)), 0.5 * (1.0 + 1.0 / std::sqrt(3.0))};
     int boundary_face_index = 0;
     for (const auto& bf : o.bfaces) {
@@ -410,6 +579,7 @@ void assemble_rhs_faces(Oracle& o, int bid, const double* face_bc = nullptr) {
 
 // DealSolver.cpp:432-435 append_dirichlet (VectorTools::interpolate_boundary_values, ConstantFunction)
 void append_dirichlet(Oracle& o, int bid, double value) {
+    if (o.fe_degree == 2) { q2_append_dirichlet(o, bid, value); return; }
     for (const auto& bf : o.bfaces)
         if (bf.id == bid)
             for (int v = 0; v < 4; ++v)
@@ -511,10 +681,10 @@ void assemble(Oracle& o, int first_time, const double* pxyz, const int* pcell, l
     append_dirichlet(o, BID_COPPER, 0.0);
     if (!o.anode_dirichlet) assemble_rhs_faces(o, BID_TOP);
     else append_dirichlet(o, BID_TOP, o.applied_potential);
-    if (pxyz && n_parts > 0) assemble_space_charge(o, pxyz, pcell, n_parts, charge_factor);
+    if (pxyz && n_parts > 0 && o.fe_degree == 1) assemble_space_charge(o, pxyz, pcell, n_parts, charge_factor);   // FE_Q(2): Laplace only
     // PoissonSolver.cpp:196-207: charge density for the files, before the Dirichlet conditions; DealSolver.cpp:344-366 calc_dof_volumes
     o.charge_density.assign(o.n_dofs, 0.0);
-    if (o.write_time) {
+    if (o.write_time && o.fe_degree == 1) {
         std::vector<double> dof_volume(o.n_dofs, 0.0);
         for (int c = 0; c < (int) o.cells.size(); ++c)
             for (int q = 0; q < 8; ++q) {
@@ -1135,6 +1305,12 @@ int fo_get_max_threads() { return omp_get_max_threads(); }
 void* fo_create() { return new Oracle(); }
 void fo_destroy(void* h) { delete (Oracle*) h; }
 
+// 1 (the reference build) or 2; read by the next fo_import_mesh
+void fo_set_fe_degree(void* h, int degree) { ((Oracle*) h)->fe_degree = degree == 2 ? 2 : 1; }
+void fo_get_cell_dofs27(void* h, int* out) {
+    Oracle& o = *(Oracle*) h;
+    for (size_t c = 0; c < o.cdofs.size(); ++c) std::copy(o.cdofs[c].begin(), o.cdofs[c].end(), out + 27 * c);
+}
 int fo_import_mesh(void* h, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {
     return import_mesh(*(Oracle*) h, xyz, n_nodes, hex8, hex_marker, n_hex);
 }

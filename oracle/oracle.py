@@ -37,6 +37,8 @@ def lib():
         L.fo_set_num_threads.argtypes = [C.c_int]
         L.fo_get_max_threads.restype = C.c_int
         L.fo_import_mesh.argtypes = [C.c_void_p, _dp, C.c_int, _ip, _ip, C.c_int]
+        L.fo_set_fe_degree.argtypes = [C.c_void_p, C.c_int]
+        L.fo_get_cell_dofs27.argtypes = [C.c_void_p, _ip]
         L.fo_setup.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int]
         L.fo_assemble.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_long, C.c_double]
         L.fo_solve.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double)]
@@ -105,6 +107,15 @@ class Oracle:
             pass
 
     # ---- solver ------------------------------------------------------------------
+    def set_fe_degree(self, degree):
+        """1 = FE_Q(1) (the reference build), 2 = FE_Q(2) (DealSolver.h:130 shape_degree = 2); read by the next import_mesh"""
+        self.L.fo_set_fe_degree(self.h, int(degree))
+
+    def cell_dofs27(self):
+        out = np.zeros((self.n_cells, 27), np.int32)
+        self.L.fo_get_cell_dofs27(self.h, out.reshape(-1))
+        return out
+
     def import_mesh(self, nodes, hexs, hex_markers):
         nodes = _f(nodes); hexs = _i(hexs); hex_markers = _i(hex_markers)
         self.n_nodes = len(nodes)
