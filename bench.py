@@ -637,12 +637,13 @@ def native_step(fb, torch, args):
         f = fb.FieldReader(interp); f.set_preferences(False, 2, 1); f.interpolate(atoms)
         return it
 
-    def run(fn):
+    def run(fn, st=None):
+        st = st or stream
         tot = 0.0; its = 0
         for s in range(W + K):
             flush.fill_(s & 0xff); torch.cuda.synchronize()           # L2 flush between steps
             a, b = ev(), ev()
-            a.record(stream); it = fn(); b.record(stream); b.synchronize()
+            a.record(st); it = fn(); b.record(st); b.synchronize()
             if s >= W:
                 tot += a.elapsed_time(b); its += abs(it)
         return tot / K, its / K
@@ -738,6 +739,74 @@ def native_step(fb, torch, args):
         ref = ref_interp_baseline(m, atoms, all_atoms)
         if ref:
             out["cpu_baseline_reference_code"] = ref
+    ctx.close()
+    out["q2"] = native_q2_step(fb, torch, args, m, atoms, run)
+    return out
+
+
+def native_q2_step(fb, torch, args, m, atoms, run):
+    """BASELINE.json config 2 as it is worded ("nanotip_big Q2 Laplace solve + surface-atom field interpolation"): the same
+    field step with the quadratic element (option fe_degree = 2, csrc/q2.cu), checked against the oracle's FE_Q(2)
+    restatement and timed beside it"""
+    ctx = fb.Context(torch.cuda.current_device())
+    ctx.set_option("fe_degree", 2)
+    conf = fb.FieldConfig(E0=E0, cg_tolerance=CG_TOL, n_cg=N_CG)
+    solver = fb.PoissonSolver(ctx, conf)
+    t0 = time.perf_counter()
+    assert solver.import_mesh(m["nodes"], m["hexs"], m["hex_markers"])
+    import_ms = 1e3 * (time.perf_counter() - t0)
+    interp = fb.Interpolator(ctx); interp.initialize(m)
+    na = len(atoms)
+    d_atoms = torch.from_numpy(atoms).cuda()
+    d_cells = torch.empty(na, dtype=torch.int32, device="cuda"); d_sol = torch.empty(na, 5, dtype=torch.float64, device="cuda")
+
+    def step_dev():
+        solver.setup(-E0, 0.0); solver.assemble(True)
+        it = solver.solve()
+        interp.extract_solution(solver, True)
+        ctx.check(ctx.L.fb_locate_interpolate_dev(ctx.h, 2, 1, na, d_atoms.data_ptr(), d_cells.data_ptr(), d_sol.data_ptr()))
+        ctx.synchronize()
+        return it
+
+    out = {"workload": "config 2 with FE_Q(2): nanotip_big mesh (%d DoF, %d hexahedra, nnz %d), Laplace field step (27-node stiffness assembly + "
+                       "CG + extract_solution) + field on %d surface atoms" % (solver.n_dofs, solver.n_cells, solver.nnz, na),
+           "import_mesh_ms": import_ms}
+    o = None
+    if not args.skip_cpu:
+        from oracle.oracle import Oracle
+        use_all_host_threads()
+        t = time.perf_counter()
+        o = Oracle(); o.set_fe_degree(2); o.import_mesh(m["nodes"], m["hexs"], m["hex_markers"]); o.interp_initialize(m)
+        t1 = time.perf_counter()
+        o.setup(-E0, 0.0, False); o.assemble(True)
+        t2 = time.perf_counter()
+        it_cpu = o.solve(N_CG, CG_TOL, 1.2, 0)
+        t3 = time.perf_counter()
+        o.extract_solution(True); o.locate_interpolate(2, 1, atoms)
+        t4 = time.perf_counter()
+        out["cpu_baseline"] = {"field_step_ms": 1e3 * (t4 - t1), "assemble_ms": 1e3 * (t2 - t1), "solve_ms": 1e3 * (t3 - t2), "cg_iterations": it_cpu,
+                               "cores": cpu_threads(), "kind": "port (FE_Q(2) restatement, SSOR-CG; the reference fixes shape_degree = 1 at compile time)"}
+        assert o.solve(N_CG, 1e-11, 1.2, 0) >= 0
+        nod = o.extract_solution(True)
+        oc, osol = o.locate_interpolate(2, 1, atoms)
+        conf.cg_tolerance = 1e-11
+        assert step_dev() > 0
+        conf.cg_tolerance = CG_TOL
+        v = {"phi_rel": rel_diff(solver.export_solution(), o.export_solution()), "nodal_rel": rel_diff(interp.get_solutions(), nod),
+             "surface_cells_equal": bool(np.array_equal(d_cells.cpu().numpy(), oc)), "surface_field_rel": rel_diff(d_sol.cpu().numpy(), osol)}
+        assert v["surface_cells_equal"] and max(v["phi_rel"], v["nodal_rel"], v["surface_field_rel"]) < 1e-8, v
+        out["verified"] = v
+        log("[verify] native Q2: %s" % v)
+    st = torch.cuda.ExternalStream(ctx.stream)
+    ms_dev, it_dev = run(step_dev, st)
+    solve_ms, it_last, _ = solver.solve_stats()
+    out.update(field_step_ms=ms_dev, cg_iterations=it_dev, solve_ms=solve_ms, us_per_cg_iteration=1e3 * solve_ms / max(1, it_last),
+               gdof_per_s_per_iteration=solver.n_dofs / (solve_ms * 1e-3 / max(1, it_last)) / 1e9, spmv_kernel=ctx.L.fb_last_solve_kernel(ctx.h),
+               preconditioner="Jacobi")
+    solver.conf.precond = fb.PRECOND_TWOLEVEL
+    step_dev()
+    ms_tl, it_tl = run(step_dev, st)
+    out.update(two_level_field_step_ms=ms_tl, two_level_cg_iterations=it_tl)
     ctx.close()
     return out
 

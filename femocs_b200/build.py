@@ -20,6 +20,7 @@ UNITS = [
     ("poisson_kernels.cu", []),
     ("interp_kernels.cu", ["-fmad=false"]),
     ("twolevel.cu", []),
+    ("q2.cu", []),
     ("api.cu", []),
 ]
 

@@ -184,6 +184,10 @@ int fb_set_option(fb_ctx* c, const char* key, double value) {
     else if (k == "cheb_power_iters") { c->cheb_power_iters = std::max(0, (int) value); c->cheb_lmax = 0; }
     else if (k == "dof_order") c->dof_order = (int) value;
     else if (k == "spmv_kernel") { c->spmv_kernel = (int) value; drop_graph(c); }
+    else if (k == "fe_degree") {            // element of the NEXT fb_import_mesh: 1 = FE_Q(1) (DealSolver.h:130 as shipped), 2 = FE_Q(2)
+        if ((int) value != 1 && (int) value != 2) return c->fail(FB_ERR_ARG, "fe_degree must be 1 or 2");
+        c->fe_degree = (int) value;
+    }
     else if (k == "cg_persistent") c->cg_persistent = (int) value;
     else if (k == "cg_debug") c->cg_debug = (int) value;
     else if (k == "mesh_reuse") c->mesh_reuse = (int) value;
@@ -360,6 +364,7 @@ int fb_import_bulk_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* he
 
 static int import_mesh_impl(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex) {
     FB_REQUIRE(c, xyz && hex8 && hex_marker && n_nodes > 0 && n_hex > 0, "fb_import_mesh: empty mesh");
+    FB_REQUIRE(c, c->fe_degree == 1 || (c->world == 1 && c->mesh_kind == 0), "fb_import_mesh: fe_degree 2 is provided for the un-partitioned field solver only");
     cudaSetDevice(c->device);
     c->last_import_reused = false;
     if (c->world == 1 && fb_host_try_reuse(c, xyz, n_nodes, hex8, hex_marker, n_hex, c->mesh_kind)) {
@@ -411,7 +416,10 @@ static int import_mesh_impl(fb_ctx* c, const double* xyz, int n_nodes, const int
     }
     const int n = c->n_cols;              // vectors indexed by column (owned rows + ghosts)
     // coordinates in DoF order
+    const bool q2 = c->imported_degree == 2;
     std::vector<double> vxyz(3 * (size_t) n);
+    if (q2) vxyz.swap(c->q2_xyz);         // support points of FE_Q(2), computed with the numbering
+    else
     for (int d = 0; d < n; ++d) {
         const double* p = &c->xyz[3 * (size_t) c->vert2node[c->dof2vertex[d]]];
         vxyz[3 * (size_t) d] = p[0]; vxyz[3 * (size_t) d + 1] = p[1]; vxyz[3 * (size_t) d + 2] = p[2];
@@ -422,6 +430,7 @@ static int import_mesh_impl(fb_ctx* c, const double* xyz, int n_nodes, const int
         if (bf.id == (c->mesh_kind ? 2 : 8)) for (int k = 0; k < 4; ++k) top.push_back(c->cells_dof[8 * (size_t) bf.cell + FV[bf.face][k]]);
     FB_CUDA(c, c->d_vxyz.upload(vxyz, s));
     FB_CUDA(c, c->d_cells.upload(c->cells_dof, s));
+    if (q2) { FB_CUDA(c, c->d_cells27.upload(c->cells27, s)); FB_CUDA(c, c->d_topfaces9.upload(c->topfaces9, s)); }
     FB_CUDA(c, c->d_rowptr.upload(c->rowptr, s));
     FB_CUDA(c, c->d_col.upload(c->col, s));
     c->n_rowblk = 0; c->rowblk_chunk = 0; c->win_cap = 0; c->jds_ready = false; c->jds_val_dirty = true;
@@ -467,6 +476,12 @@ int fb_get_sizes(const fb_ctx* c, long* out) {
     return FB_OK;
 }
 
+int fb_get_cells27(const fb_ctx* c, int* cells27) {
+    if (!c->mesh_ok || c->imported_degree != 2 || !cells27) return FB_ERR_ARG;
+    std::copy(c->cells27.begin(), c->cells27.end(), cells27);
+    return FB_OK;
+}
+
 int fb_poisson_setup(fb_ctx* c, double field, double potential, int anode_is_dirichlet) {
     FB_REQUIRE(c, c->mesh_ok, "fb_poisson_setup: no mesh imported");
     FB_REQUIRE(c, c->mesh_kind == 0, "fb_poisson_setup: the context holds a bulk mesh (fb_import_bulk_mesh)");
@@ -480,6 +495,7 @@ int fb_poisson_setup(fb_ctx* c, double field, double potential, int anode_is_dir
 
 static int assemble_impl(fb_ctx* c, int first_time, const double* d_pxyz, const int* d_pcell, long n_parts, double charge_factor) {
     cudaStream_t s = c->stream;
+    FB_REQUIRE(c, c->imported_degree == 1 || n_parts == 0, "fb_poisson_assemble: the space-charge right-hand side is provided for fe_degree 1 only (FE_Q(2): Laplace)");
     const int n = c->n_dofs;
     if (first_time || !c->matrix_ok) {
         // stiffness matrix -> val_save (the reference's system_matrix_save).  It is never modified afterwards: the
@@ -516,7 +532,7 @@ static int assemble_impl(fb_ctx* c, int first_time, const double* d_pxyz, const 
     // PoissonSolver.cpp:196-207: when a file is about to be written (option "charge_density", the reference's write_time())
     // charge_density = rhs / dof_volume is kept, BEFORE the Dirichlet conditions touch the right-hand side; zeros otherwise
     c->rho_valid = false;
-    if (c->want_charge_density && c->world == 1) {
+    if (c->want_charge_density && c->world == 1 && c->imported_degree == 1) {
         FB_CUDA(c, c->d_rho.alloc(n));
         fb::launch_charge_density(c, c->d_h.p);          // d_h is scratch until the solve
         c->rho_valid = true;
@@ -855,6 +871,7 @@ int fb_export_charge_dens(fb_ctx* c, double* rho_vertex) {
 int fb_export_solution_grad(fb_ctx* c, double* grad3) {
     FB_REQUIRE(c, c->mesh_ok && grad3, "fb_export_solution_grad: no mesh");
     FB_REQUIRE(c, c->world == 1, "fb_export_solution_grad: un-partitioned meshes only");
+    FB_REQUIRE(c, c->imported_degree == 1, "fb_export_solution_grad: fe_degree 1 only");
     cudaSetDevice(c->device);
     if (c->d_vert_lastcell.n < (size_t) c->n_vert || c->d_vert_lastcell.p == nullptr) {
         std::vector<int> lc;

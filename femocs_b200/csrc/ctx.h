@@ -112,6 +112,7 @@ struct fb_ctx {
     int spmv_kernel = -1;                    // -1 auto, 0 row-block stream kernel, 2..32 lanes per row
     int cg_persistent = -1;                  // -1 auto (single cooperative launch when the system fits on chip), 0 off
     int cg_profile = 0;                      // iterations per solve bracketed with CUDA events (0 = off)
+    int fe_degree = 1;                       // 1 = FE_Q(1) (the reference build), 2 = FE_Q(2) (q2.cu); read by the next fb_import_mesh
 
     // ---- multi-GPU partition (one process per GPU; see partition.cpp) ----
     int rank = 0, world = 1;
@@ -143,6 +144,8 @@ struct fb_ctx {
     std::vector<int> node2vert, vert2node, hex2cell, cell2hex;
     std::vector<int> vertex2dof, dof2vertex;
     std::vector<int> cells_dof;              // 8 dof ids per solver cell, lexicographic (deal) order
+    // fe_degree 2: 27 dofs per cell (local node i + 3 j + 9 k), support points per dof, 9 dofs per top face
+    std::vector<int> cells27, topfaces9; std::vector<double> q2_xyz; int imported_degree = 1;
     int n_vert = 0, n_cells = 0, n_dofs = 0;
     long nnz = 0;
     std::vector<int> rowptr, col;            // CSR pattern, columns sorted
@@ -166,6 +169,7 @@ struct fb_ctx {
     // ---- device: solver ----
     fb::DevBuf<double> d_vxyz;               // coordinates per DoF (3*n_dofs)
     fb::DevBuf<int> d_cells;                 // 8*n_cells dof ids (lexicographic)
+    fb::DevBuf<int> d_cells27, d_topfaces9;  // fe_degree 2
     fb::DevBuf<int> d_asm_map; bool asm_map_ready = false; int asm_map_opt = 1;   // scatter map of the assembly (64 positions per hexahedron)
     fb::DevBuf<int> d_rowptr, d_col, d_diagpos, d_rowblk, d_win_off, d_win_list;
     fb::DevBuf<unsigned short> d_col16, d_jds_perm, d_jds_len, d_jds_slot;
@@ -257,6 +261,7 @@ int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* he
 bool fb_host_try_reuse(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex, int mesh_kind);
 int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
 int fb_host_import_phase2(fb_ctx* c);
+int fb_host_q2_phase2(fb_ctx* c);         // q2.cu: numbering, sparsity and boundary sets of FE_Q(2)
 // partition.cpp: cuts the mesh for c->rank of c->world and runs phase 1 on the local sub-mesh
 int fb_host_partition_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
 struct fb_interp_tables {

@@ -265,6 +265,8 @@ int fb_host_import_phase2(fb_ctx* c) {
     }
 
     laps.lap("face ids");
+    c->imported_degree = c->fe_degree;
+    if (c->fe_degree == 2) return fb_host_q2_phase2(c);          // FE_Q(2): numbering, sparsity, boundary sets in q2.cu
     // ---- DoF numbering ----
     c->vertex2dof.assign(n_vert, -1);
     int n_dofs = 0;
@@ -404,6 +406,7 @@ int fb_host_import_phase2(fb_ctx* c) {
 // when the full import has to run.
 bool fb_host_try_reuse(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex, int mesh_kind) {
     if (!c->mesh_ok || c->mesh_reuse == 0 || c->part_n_owned >= 0 || c->mesh_flipped) return false;
+    if (c->fe_degree != 1 || c->imported_degree != 1) return false;      // FE_Q(2) systems are always rebuilt
     if (mesh_kind != c->imported_kind || n_nodes != c->n_nodes || n_hex != c->n_hex) return false;
     if (memcmp(hex_marker, c->hex_marker.data(), sizeof(int) * (size_t) n_hex) != 0) return false;
     if (memcmp(hex8, c->hex8.data(), sizeof(int) * 8 * (size_t) n_hex) != 0) return false;

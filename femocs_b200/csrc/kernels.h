@@ -41,6 +41,10 @@ void launch_solution_grad(fb_ctx* c, double* d_grad3);
 void launch_gather(fb_ctx* c, int n, const int* idx, const double* src, double* dst);
 void launch_scatter(fb_ctx* c, int n, const int* idx, const double* src, double* dst);
 
+// q2.cu
+void launch_q2_stiffness(fb_ctx* c);
+void launch_q2_neumann(fb_ctx* c);
+
 // twolevel.cu
 int tl_prepare(fb_ctx* c);
 void tl_release(fb_ctx* c);

@@ -1582,6 +1582,7 @@ static bool ensure_asm_map(fb_ctx* c) {
 }
 
 void launch_assemble_stiffness(fb_ctx* c) {
+    if (c->imported_degree == 2) { launch_q2_stiffness(c); return; }
     if (ensure_asm_map(c))
         k_assemble_stiffness_mapped<<<(c->n_cells + ASM_BLOCK - 1) / ASM_BLOCK, ASM_BLOCK, 0, c->stream>>>(c->n_cells, c->d_cells.p, c->d_vxyz.p,
                                                                                                       c->d_asm_map.p, c->d_val_save.p);
@@ -1606,6 +1607,7 @@ void launch_cell_volumes(fb_ctx* c, double* d_cell_vol) {
 
 void launch_neumann(fb_ctx* c) {
     if (c->n_top_faces == 0) return;
+    if (c->imported_degree == 2) { launch_q2_neumann(c); return; }
     k_neumann_faces<<<(c->n_top_faces + 127) / 128, 128, 0, c->stream>>>(c->n_top_faces, c->n_dofs, c->d_topfaces.p, c->d_vxyz.p,
                                                                        c->applied_field, c->mesh_kind ? c->d_face_bc.p : nullptr, c->d_rhs.p);
     c->launches++;

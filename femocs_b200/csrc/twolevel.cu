@@ -356,6 +356,7 @@ int tl_prepare(fb_ctx* c) {
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
 #pragma omp parallel for schedule(static) reduction(min : lo[:3]) reduction(max : hi[:3])
         for (long v = 0; v < ng; ++v) {
+            if (!part && c->dof2vertex[v] < 0) continue;          // FE_Q(2): the other support points lie inside the hull of the vertices
             const double* p = part ? &c->part_gxyz[3 * (size_t) v] : &c->xyz[3 * (size_t) c->vert2node[c->dof2vertex[v]]];
             for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); }
         }

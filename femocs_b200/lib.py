@@ -24,6 +24,7 @@ SIGNATURES = {
     "fb_comm_unique_id": (C.c_int, [vp]),
     "fb_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "fb_get_partition": (C.c_int, [vp, vp]),
+    "fb_get_cells27": (C.c_int, [vp, vp]),
     "fb_plan_create": (vp, [C.c_int, C.c_int]),
     "fb_plan_phase1": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "fb_plan_phase2": (C.c_int, [vp, vp]),

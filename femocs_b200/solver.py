@@ -521,11 +521,13 @@ class PartitionPlan:
         self._check(self.L.fb_plan_phase1(self.h, _p(nodes), len(nodes), _p(hexs), _p(hex_markers), len(hexs), _p(bbox)))
         return bbox                      # local (min xyz, max xyz) of the boundary-face centres
 
-    def import_whole(self, nodes, hexs, hex_markers, bulk=False):
+    def import_whole(self, nodes, hexs, hex_markers, bulk=False, fe_degree=1):
         """the un-partitioned host import of fb_import_mesh (world 1): complete numbering and sparsity;
-        bulk=True: the host import of fb_import_bulk_mesh (hexahedra with marker < 0, CurrentHeatSolver::mark_mesh)"""
+        bulk=True: the host import of fb_import_bulk_mesh (hexahedra with marker < 0, CurrentHeatSolver::mark_mesh);
+        fe_degree=2: the FE_Q(2) system (option "fe_degree")"""
         nodes = _f(nodes); hexs = _i(hexs); hex_markers = _i(hex_markers)
         self._check(self.L.fb_plan_set_kind(self.h, int(bulk)))
+        self._check(self.L.fb_set_option(self.h, b"fe_degree", float(fe_degree)))
         self._check(self.L.fb_plan_import(self.h, _p(nodes), len(nodes), _p(hexs), _p(hex_markers), len(hexs)))
         self.reused = bool(self.L.fb_last_import_reused(self.h))
         return self._collect()
@@ -549,6 +551,11 @@ class PartitionPlan:
         a["send_idx"] = a["send_idx"][:self.n_send]
         self.__dict__.update(a)
         return self
+
+    def cells27(self):
+        out = np.zeros((self.n_cells, 27), np.int32)
+        self._check(self.L.fb_get_cells27(self.h, _p(out)))
+        return out
 
     def surface_centroids(self):
         """DealSolver::export_surface_centroids of the imported mesh (copper_surface faces, cell / face order)"""

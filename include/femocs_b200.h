@@ -63,7 +63,10 @@ long        fb_kernel_launches(const fb_ctx* ctx);
  * FB_PRECOND_CHEBYSHEV, default 2 -> k SpMVs per CG iteration), "cheb_eig_ratio" (lmax / lmin of the interval, default 30), "cheb_power_iters" (power iterations that sharpen the
  * Gershgorin bound of lmax, default 15, 0 = Gershgorin only),
  * "dof_order" (0 = deal.II first-touch numbering, 1 = Morton order of vertex coordinates),
- * "cg_profile" (see fb_last_solve_profile) */
+ * "cg_profile" (see fb_last_solve_profile),
+ * "fe_degree" (element of the NEXT fb_import_mesh: 1 = FE_Q(1), the reference as shipped -- include/DealSolver.h:130
+ * shape_degree = 1; 2 = FE_Q(2) with QGauss(3), what the same call sites do when that constant reads 2: Laplace only,
+ * un-partitioned field solver only; fb_export_solution still returns the vertex values, src/DealSolver.cpp:317-341) */
 int         fb_set_option(fb_ctx* ctx, const char* key, double value);
 
 /* ---------------------------------------------------------------------------------------
@@ -139,6 +142,9 @@ int fb_last_import_reused(const fb_ctx* ctx);
 /* sizes after import: out[0]=n_dofs, [1]=n_cells, [2]=nnz, [3]=n_vertices,
  * [4]=n_boundary_faces, [5]=n_top_faces, [6]=n_dirichlet_dofs (after assemble) */
 int fb_get_sizes(const fb_ctx* ctx, long* out7);
+/* fe_degree 2: the 27 dofs of every cell (DoFCellAccessor::get_dof_indices re-ordered to the tensor lattice: local node
+ * (i, j, k) in {0, 1, 2}^3 at index i + 3 j + 9 k); FB_ERR_ARG for an FE_Q(1) mesh */
+int fb_get_cells27(const fb_ctx* ctx, int* cells27);
 
 /* void PoissonSolver<3>::setup(double field, double potential)  src/PoissonSolver.cpp:162-167
  * (+ DealSolver::setup_system src/DealSolver.cpp:368-387: zero matrix/rhs, solution = 0).

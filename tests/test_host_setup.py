@@ -128,3 +128,39 @@ def test_parallel_numbering_on_a_large_mesh_matches_oracle():
     rp, col, _, _ = o.csr()
     assert np.array_equal(p.rowptr, rp) and np.array_equal(p.col, col)
     assert np.array_equal(o.vectors()[2][o.cells()], p.cells_dof)
+
+
+def _q2_face_nodes(f):
+    axis, fixed = f // 2, (f % 2) * 2
+    stride = [1, 3, 9]
+    a0 = 1 if axis == 0 else 0; a1 = 1 if axis == 2 else 2
+    return [fixed * stride[axis] + a * stride[a0] + b * stride[a1] for b in range(3) for a in range(3)]
+
+
+@pytest.mark.parametrize("name", ["box", "hemicone"])
+def test_q2_import_matches_oracle(name, golden):
+    """option fe_degree = 2 (q2.cu, host half): first-touch numbering of vertex / line / quad / hex dofs in deal.II's
+    per-cell order, sparsity and the Dirichlet candidates, against the oracle's FE_Q(2) restatement -- index work, bit-exact"""
+    if name == "box":
+        nodes, hexs, mk = synth.box_mesh(5, 4, 6, 2.0, 1.5, 2.5, jitter=0.15)
+    else:
+        m = golden("mesh", name); nodes, hexs, mk = m["nodes"], m["hexs"], m["hex_markers"]
+    o = Oracle(); o.set_fe_degree(2); o.import_mesh(nodes, hexs, mk)
+    a = PartitionPlan(0, 1).import_whole(nodes, hexs, mk, fe_degree=2)
+    assert (a.n_rows, a.n_cells, a.nnz) == (o.n_dofs, o.n_cells, o.nnz)
+    rp, col, _, _ = o.csr()
+    assert np.array_equal(a.rowptr, rp) and np.array_equal(a.col, col)
+    cd = o.cell_dofs27()
+    assert np.array_equal(a.cells27(), cd)
+    v2d = o.vectors()[2]
+    assert np.array_equal(v2d[o.cells()], a.cells_dof)                    # the 8 vertex dofs per cell (geometry look-ups)
+    cell, face, bid = o.bfaces()
+    for flag, want in ((a.copper, 2), (a.top, 8)):
+        ref = np.zeros(o.n_dofs, np.int32)
+        for c_, f_ in zip(cell[bid == want], face[bid == want]):
+            ref[cd[c_, _q2_face_nodes(f_)]] = 1
+        assert ref.sum() > 0 and np.array_equal(flag, ref)
+    # an FE_Q(1) import on the same plan afterwards is the ordinary one
+    b = PartitionPlan(0, 1).import_whole(nodes, hexs, mk)
+    o1 = Oracle(); o1.import_mesh(nodes, hexs, mk)
+    assert b.n_rows == o1.n_dofs and b.nnz == o1.nnz
