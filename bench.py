@@ -406,6 +406,7 @@ def run_b200(args):
         ms, iters, its, launches = timed(step_dev, args.steps, max(0, args.warmup - 1))     # the verification step was warm-up step 1
     clocks = clk.summary()
     spmv_ms, vec_ms, n_samp = solver.solve_profile()
+    kernel_id = solver.solve_kernel()
     solve_ms, last_it, _ = solver.solve_stats()
     ms_e2e, iters_e2e, its_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup - 2))
 
@@ -442,8 +443,9 @@ def run_b200(args):
     if os.path.exists(tp) and world == 1 and args.levels == 2:
         try:
             tj = json.load(open(tp))
-            traffic = tj.get("spmv_dram_bytes_per_launch")
-            traffic_src = "static, not measured in this run: " + tj.get("source", tp)
+            if tj.get("spmv_kernel", 304) == kernel_id:
+                traffic = tj.get("spmv_dram_bytes_per_launch")
+                traffic_src = "static, not measured in this run: " + tj.get("source", tp)
         except Exception:
             traffic = None
 
@@ -468,7 +470,8 @@ def run_b200(args):
                 "call": "fb_poisson_setup + fb_poisson_assemble(host particles) + fb_poisson_solve + fb_check_limits + fb_export_solution"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_spmv_jds (block-JDS SpMV fused with the d.h dot product)" + (
+        "roofline": {"bound": "hbm", "kernel": {306: "k_spmv_jdss (segmented block-JDS SpMV: rows longer than 32 entries split into chained segments; fused with the d.h dot product)",
+                                                 304: "k_spmv_jds (block-JDS SpMV fused with the d.h dot product)"}.get(kernel_id, "SpMV variant %d" % kernel_id) + (
                          "; rank 0 share, timed INCLUDING the halo exchange and the dot-product all-reduce" if world > 1 else ""),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

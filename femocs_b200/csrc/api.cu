@@ -184,6 +184,8 @@ int fb_set_option(fb_ctx* c, const char* key, double value) {
     else if (k == "cheb_power_iters") { c->cheb_power_iters = std::max(0, (int) value); c->cheb_lmax = 0; }
     else if (k == "dof_order") c->dof_order = (int) value;
     else if (k == "spmv_kernel") { c->spmv_kernel = (int) value; drop_graph(c); }
+    else if (k == "spmv_split") { c->spmv_split = std::max(8, (int) value); c->jds_ready = false; drop_graph(c); }   // segment cap of spmv_kernel 306
+    else if (k == "spmv_occ") { c->spmv_occ = std::max(1, std::min(16, (int) value)); drop_graph(c); }
     else if (k == "fe_degree") {            // element of the NEXT fb_import_mesh: 1 = FE_Q(1) (DealSolver.h:130 as shipped), 2 = FE_Q(2)
         if ((int) value != 1 && (int) value != 2) return c->fail(FB_ERR_ARG, "fe_degree must be 1 or 2");
         c->fe_degree = (int) value;
@@ -324,6 +326,20 @@ int fb_plan_jds(fb_ctx* c, int R, int max_window, int sym, long* sizes6) {
     if (!fb_host_jds_build(c, R, max_window, sym != 0)) return c->fail(FB_ERR_ARG, "fb_plan_jds: a window exceeds max_window or a row is too long");
     sizes6[0] = c->jds_nb; sizes6[1] = c->jds_size; sizes6[2] = c->win_off[c->jds_nb]; sizes6[3] = c->jds_maxlen; sizes6[4] = c->win_max;
     sizes6[5] = (long) c->jds_jd.size();
+    return FB_OK;
+}
+// host-only: the same tables with rows longer than `split` entries stored as chained segments (spmv_kernel 306)
+int fb_plan_jds_split(fb_ctx* c, int R, int max_window, int split, long* sizes6) {
+    FB_REQUIRE(c, c->host_only && c->mesh_ok, "fb_plan_jds_split: needs a plan context after fb_plan_phase2");
+    FB_REQUIRE(c, R == 512 && split >= 8, "fb_plan_jds_split: R must be 512 and split >= 8");
+    if (!fb_host_jds_build(c, R, max_window, false, split)) return c->fail(FB_ERR_ARG, "fb_plan_jds_split: a window exceeds max_window or a row is too long");
+    sizes6[0] = c->jds_nb; sizes6[1] = c->jds_size; sizes6[2] = c->win_off[c->jds_nb]; sizes6[3] = c->jds_maxlen; sizes6[4] = c->win_max;
+    sizes6[5] = (long) c->jds_jd.size();
+    return FB_OK;
+}
+int fb_plan_jds_get_split(const fb_ctx* c, int* rowbeg, unsigned short* link) {
+    if (rowbeg) std::copy(c->jds_rowbeg.begin(), c->jds_rowbeg.end(), rowbeg);
+    if (link) std::copy(c->jds_link.begin(), c->jds_link.end(), link);
     return FB_OK;
 }
 int fb_plan_jds_get(const fb_ctx* c, unsigned short* perm, unsigned short* len, unsigned short* slot, int* jdp, int* jd, int* base,
@@ -608,11 +624,12 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
         if ((cheb || tl) && lanes >= 310) lanes = 304;      // the Chebyshev steps multiply by the FULL matrix: the symmetric (lower-triangle) layout cannot serve them
         while (lanes >= 300) {                     // block-JDS SpMV: tables once per mesh, values once per assemble
             const bool sym = lanes >= 310;         // 310/311: symmetric layout (lower triangle only)
-            const int R = sym ? (lanes == 311 ? 256 : 512) : ((lanes == 301) ? 128 : ((lanes >= 302 && lanes <= 305) ? 512 : 256));
-            if (!c->jds_ready || c->jds_R != R || c->jds_sym != sym) {
+            const int R = sym ? (lanes == 311 ? 256 : 512) : ((lanes == 301) ? 128 : ((lanes >= 302 && lanes <= 306) ? 512 : 256));
+            const int split = lanes == 306 ? c->spmv_split : 0;
+            if (!c->jds_ready || c->jds_R != R || c->jds_sym != sym || c->jds_split != split) {
                 drop_graph(c);
                 // window capacity: shared memory holds the input window (and, symmetric layout, its accumulators)
-                if (fb_host_jds_build(c, R, sym ? 6144 : 8192, sym)) {
+                if (fb_host_jds_build(c, R, sym ? 6144 : 8192, sym, split)) {
                     c->win_cap = (c->win_max + 15) & ~15;
                     if (sym) FB_CUDA(c, c->d_diag.alloc(c->n_dofs));
                     FB_CUDA(c, c->d_col16.upload(c->col16, s));
@@ -621,6 +638,7 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
                     FB_CUDA(c, c->d_jds_slot.upload(c->jds_slot, s));
                     FB_CUDA(c, c->d_jds_jdp.upload(c->jds_jdp, s)); FB_CUDA(c, c->d_jds_jd.upload(c->jds_jd, s));
                     FB_CUDA(c, c->d_jds_base.upload(c->jds_base, s));
+                    if (split > 0) { FB_CUDA(c, c->d_jds_rowbeg.upload(c->jds_rowbeg, s)); FB_CUDA(c, c->d_jds_link.upload(c->jds_link, s)); }
                     FB_CUDA(c, c->d_val_jds.alloc((size_t) c->jds_size + 8));
                     FB_CUDA(c, c->d_val_jds.zero(s));                  // padding entries stay 0
                     FB_CUDA(c, cudaStreamSynchronize(s));

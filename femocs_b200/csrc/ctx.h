@@ -109,6 +109,8 @@ struct fb_ctx {
     int cg_graph_iters = 32;
     int cheb_degree = 2;
     int dof_order = 0;
+    int spmv_split = 32;                     // spmv_kernel 306: rows longer than this are stored as chained segments
+    int spmv_occ = 6;                        // CTAs per SM the grid of the 512-row block-JDS kernels is sized for (tuning point)
     int spmv_kernel = -1;                    // -1 auto, 0 row-block stream kernel, 2..32 lanes per row
     int cg_persistent = -1;                  // -1 auto (single cooperative launch when the system fits on chip), 0 off
     int cg_profile = 0;                      // iterations per solve bracketed with CUDA events (0 = off)
@@ -157,6 +159,8 @@ struct fb_ctx {
     // block-JDS layout of the HBM-roofline SpMV
     int jds_R = 0, jds_nb = 0, jds_maxlen = 0; bool jds_ready = false, jds_val_dirty = true, jds_sym = false, h_needs_zero = false;
     std::vector<unsigned short> jds_perm, jds_len, jds_slot; std::vector<int> jds_jdp, jds_jd, jds_base; int jds_size = 0;
+    // rows split into segments (spmv_kernel 306): first row of every block, next segment of a slot's row (0xFFFF: none), cap in use
+    std::vector<int> jds_rowbeg; std::vector<unsigned short> jds_link; int jds_split = 0;
     struct BFace { int cell, face, id; };
     std::vector<BFace> bfaces;
     std::vector<int> copper_dofs, top_dofs;  // Dirichlet candidates
@@ -173,7 +177,7 @@ struct fb_ctx {
     fb::DevBuf<int> d_asm_map; bool asm_map_ready = false; int asm_map_opt = 1;   // scatter map of the assembly (64 positions per hexahedron)
     fb::DevBuf<int> d_rowptr, d_col, d_diagpos, d_rowblk, d_win_off, d_win_list;
     fb::DevBuf<unsigned short> d_col16, d_jds_perm, d_jds_len, d_jds_slot;
-    fb::DevBuf<int> d_jds_jdp, d_jds_jd, d_jds_base; fb::DevBuf<double> d_val_jds, d_diag;
+    fb::DevBuf<int> d_jds_jdp, d_jds_jd, d_jds_base, d_jds_rowbeg; fb::DevBuf<unsigned short> d_jds_link; fb::DevBuf<double> d_val_jds, d_diag;
     // CurrentHeatSolver (mesh_kind 1): the CG engine works on d_val_save / d_x; the system that is NOT active is parked in
     // d_val_other / d_x_other (ch_active: 0 = current, 1 = heat)
     fb::DevBuf<double> d_val_other, d_x_other, d_res_T, d_res_rho;
@@ -256,7 +260,7 @@ long fb_host_count_edges(const fb_ctx* c);
 void fb_host_vertex_lastcell(const fb_ctx* c, std::vector<int>& out);
 bool fb_host_row_blocks(fb_ctx* c, int chunk, int maxrows);
 bool fb_host_col_windows(fb_ctx* c, int max_window);
-bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym);
+bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym, int split = 0);
 int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
 bool fb_host_try_reuse(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex, int mesh_kind);
 int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);

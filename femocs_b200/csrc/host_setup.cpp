@@ -535,36 +535,76 @@ bool fb_host_col_windows(fb_ctx* c, int max_window) {
 // diagonals: diagonal j holds the j-th entry of every row longer than j, so that thread t of the
 // CTA walks "its" row with perfectly coalesced loads and NO padding.  Columns are replaced by 16-bit
 // positions inside the block's window (the sorted distinct columns the block touches).
-bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym) {
+bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym, int split) {
     // sym: only the strictly lower triangle (columns < row: a prefix of every sorted CSR row) is stored; the window
     // list then holds the distinct columns BELOW the block (sorted), and the block's own rows follow implicitly:
     // window position of column j is  rank(j) for j < r0,  n_ext + (j - r0) for r0 <= j < row.
+    // split > 0 (full layout only): a row longer than `split` entries is stored as ceil(len / split) SEGMENTS of (nearly)
+    // equal length, each in a slot of its own, chained by jds_link; the kernel adds the segment sums in chain order.  A
+    // block then holds R slots instead of R rows (jds_rowbeg gives its first row).  Without it the one warp that owns the
+    // longest rows of a block walks 2-4x more diagonals than the other seven, which wait for it at the block's barrier.
     const int n = c->n_dofs;
-    const int nb = (n + R - 1) / R;
+    if (sym) split = 0;
     auto rowlen = [&](int r) {
         const int* lo = c->col.data() + c->rowptr[r]; const int* hi = c->col.data() + c->rowptr[r + 1];
         return sym ? (int) (std::lower_bound(lo, hi, r) - lo) : (int) (hi - lo);
     };
-    c->jds_R = R; c->jds_nb = nb; c->jds_sym = sym;
-    c->jds_perm.assign((size_t) nb * R, 0); c->jds_len.assign((size_t) nb * R, 0); c->jds_slot.assign(n, 0);
-    c->jds_jdp.assign(nb + 1, 0); c->jds_base.assign(nb + 1, 0);
-    std::vector<int> maxlen(nb, 0);
-    // pass 1: per-block row order and jagged-diagonal counts
-#pragma omp parallel for schedule(static)
-    for (int b = 0; b < nb; ++b) {
-        const int r0 = b * R, nr = std::min(R, n - r0);
-        std::vector<int> ord(nr);
-        std::iota(ord.begin(), ord.end(), 0);
-        std::vector<int> lens(nr);
-        for (int a = 0; a < nr; ++a) lens[a] = rowlen(r0 + a);
-        std::stable_sort(ord.begin(), ord.end(), [&](int a, int q) { return lens[a] > lens[q]; });
-        for (int t = 0; t < nr; ++t) {
-            const int len = lens[ord[t]];
-            c->jds_perm[(size_t) b * R + t] = (unsigned short) ord[t];
-            c->jds_len[(size_t) b * R + t] = (unsigned short) std::min(len, 65535);
-            c->jds_slot[r0 + ord[t]] = (unsigned short) t;
+    auto nseg_of = [&](int len) { return (split > 0 && len > split) ? (len + split - 1) / split : 1; };
+    std::vector<int>& rb = c->jds_rowbeg;
+    rb.clear(); rb.push_back(0);
+    if (split > 0) {
+        int used = 0;
+        for (int r = 0; r < n; ++r) {
+            const int k = nseg_of(c->rowptr[r + 1] - c->rowptr[r]);
+            if (k > R) return false;
+            if (used + k > R) { rb.push_back(r); used = 0; }
+            used += k;
         }
-        maxlen[b] = lens[ord[0]];
+    } else {
+        for (long r = R; r < n; r += R) rb.push_back((int) r);
+    }
+    rb.push_back(n);
+    const int nb = (int) rb.size() - 1;
+    c->jds_R = R; c->jds_nb = nb; c->jds_sym = sym; c->jds_split = split;
+    c->jds_perm.assign((size_t) nb * R, 0xFFFF); c->jds_len.assign((size_t) nb * R, 0); c->jds_slot.assign(n, 0);
+    c->jds_link.assign(split > 0 ? (size_t) nb * R : 0, 0xFFFF);
+    std::vector<unsigned short> seg_start(split > 0 ? (size_t) nb * R : 0, 0);      // first entry (within its row) of the slot's segment
+    c->jds_jdp.assign(nb + 1, 0); c->jds_base.assign(nb + 1, 0);
+    std::vector<int> maxlen(nb, 0), nslot(nb, 0);
+    // pass 1: per-block slot order (longest first) and jagged-diagonal counts
+#pragma omp parallel
+    {
+        std::vector<int> ord, lens, loc, off, first;
+#pragma omp for schedule(static)
+        for (int b = 0; b < nb; ++b) {
+            const int r0 = rb[b], nr = rb[b + 1] - r0;
+            lens.clear(); loc.clear(); off.clear(); first.assign(nr + 1, 0);
+            for (int a = 0; a < nr; ++a) {
+                const int len = rowlen(r0 + a), k = nseg_of(len), sl = (len + k - 1) / k;
+                first[a] = (int) lens.size();
+                for (int q = 0; q < k; ++q) { lens.push_back(std::max(0, std::min(sl, len - q * sl))); loc.push_back(a); off.push_back(q * sl); }
+            }
+            first[nr] = (int) lens.size();
+            const int nv = (int) lens.size();
+            ord.resize(nv);
+            std::iota(ord.begin(), ord.end(), 0);
+            std::stable_sort(ord.begin(), ord.end(), [&](int a, int q) { return lens[a] > lens[q]; });
+            std::vector<int> slot_of(nv);
+            for (int t = 0; t < nv; ++t) slot_of[ord[t]] = t;
+            for (int t = 0; t < nv; ++t) {
+                const int v = ord[t], a = loc[v];
+                const bool head = (v == first[a]);
+                c->jds_perm[(size_t) b * R + t] = (unsigned short) (a | (head ? 0 : 0x8000));
+                c->jds_len[(size_t) b * R + t] = (unsigned short) std::min(lens[v], 65535);
+                if (head) c->jds_slot[r0 + a] = (unsigned short) t;
+                if (split > 0) {
+                    seg_start[(size_t) b * R + t] = (unsigned short) off[v];
+                    if (v + 1 < first[a + 1]) c->jds_link[(size_t) b * R + t] = (unsigned short) slot_of[v + 1];
+                }
+            }
+            maxlen[b] = nv ? lens[ord[0]] : 0;
+            nslot[b] = nv;
+        }
     }
     for (int b = 0; b < nb; ++b) {
         if (maxlen[b] > 60000) return false;
@@ -572,12 +612,11 @@ bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym) {
     }
     c->jds_jd.assign(c->jds_jdp[nb], 0);
     // every diagonal is padded to an even number of entries (zero value, window position 0) so that a
-    // thread can fetch the entries of two neighbouring rows with one 16-byte load
+    // thread can fetch the entries of two neighbouring slots with one 16-byte load
 #pragma omp parallel for schedule(static)
     for (int b = 0; b < nb; ++b) {
-        const int nr = std::min(R, n - b * R);
         int* jd = &c->jds_jd[c->jds_jdp[b]];
-        int t_active = nr;
+        int t_active = nslot[b];
         jd[0] = 0;
         for (int j = 0; j < maxlen[b]; ++j) {
             while (t_active > 0 && (int) c->jds_len[(size_t) b * R + t_active - 1] <= j) --t_active;
@@ -598,7 +637,7 @@ bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym) {
         std::vector<int> buf;
 #pragma omp for schedule(dynamic, 16)
         for (int b = 0; b < nb; ++b) {
-            const int r0 = b * R, nr = std::min(R, n - r0);
+            const int r0 = rb[b], nr = rb[b + 1] - r0;
             const int* jd = &c->jds_jd[c->jds_jdp[b]];      // jd[j] = (padded) entries stored before diagonal j
             const int k0 = c->rowptr[r0], k1 = c->rowptr[r0 + nr];
             const size_t base = (size_t) c->jds_base[b];
@@ -616,13 +655,14 @@ bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym) {
                 continue;
             }
             const int n_ext = (int) buf.size();
-            for (int t = 0; t < nr; ++t) {
-                const int r = r0 + c->jds_perm[(size_t) b * R + t];
+            for (int t = 0; t < nslot[b]; ++t) {
+                const int r = r0 + (c->jds_perm[(size_t) b * R + t] & 0x7FFF);
                 const int len = (int) c->jds_len[(size_t) b * R + t];
+                const int kfirst = c->rowptr[r] + (split > 0 ? (int) seg_start[(size_t) b * R + t] : 0);
                 // the columns of a row ascend, so do their window positions: gallop from the previous position instead of
                 // a binary search of the whole window per non-zero (6e8 x 10 steps on the 2.3e7-DoF mesh)
                 const int* wb = buf.data(); int pos = 0;
-                for (int k = c->rowptr[r]; k < c->rowptr[r] + len; ++k) {
+                for (int k = kfirst; k < kfirst + len; ++k) {
                     const int cj = c->col[k];
                     int w;
                     if (sym && cj >= r0) w = n_ext + (cj - r0);
@@ -633,7 +673,7 @@ bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym) {
                         pos = (int) (std::lower_bound(wb + pos, wb + hi, cj) - wb);
                         w = pos;
                     }
-                    c->col16[base + jd[k - c->rowptr[r]] + t] = (unsigned short) w;
+                    c->col16[base + jd[k - kfirst] + t] = (unsigned short) w;
                 }
             }
             win[b] = buf;
@@ -652,9 +692,9 @@ bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym) {
     c->win_max = wmax;
     c->jds_maxlen = *std::max_element(maxlen.begin(), maxlen.end());
     if (getenv("FB_VERBOSE"))
-        fprintf(stderr, "[fb] block-JDS%s: R=%d, %d blocks, %ld stored entries (%.2f per row), window avg %.0f max %d, longest row %d\n",
-                sym ? " (symmetric, lower triangle)" : "", R, nb, (long) c->jds_size, (double) c->jds_size / std::max(1, n),
-                (double) c->win_off[nb] / std::max(1, nb), wmax, c->jds_maxlen);
+        fprintf(stderr, "[fb] block-JDS%s: R=%d, %d blocks, %ld stored entries (%.2f per row), window avg %.0f max %d, longest %s %d\n",
+                sym ? " (symmetric, lower triangle)" : (split > 0 ? " (rows split into segments)" : ""), R, nb, (long) c->jds_size,
+                (double) c->jds_size / std::max(1, n), (double) c->win_off[nb] / std::max(1, nb), wmax, split > 0 ? "segment" : "row", c->jds_maxlen);
     return true;
 }
 

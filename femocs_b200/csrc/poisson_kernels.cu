@@ -1064,6 +1064,120 @@ __global__ void __launch_bounds__(R / 2) k_spmv_jds(int n, int n_blocks, const i
     }
 }
 
+// Block-JDS SpMV over the SEGMENTED layout (option "spmv_kernel" 306; tables: fb_host_jds_build with split > 0).  A row
+// longer than the cap is stored as chained segments, each in a slot of its own, so every slot of a block walks at most
+// `cap` diagonals: without it the one warp that owns the block's longest rows (high-valence vertices of the tetrahedral
+// mesh: 57 entries on average against 27) runs twice as many trips as the other seven, which wait for it at the block's
+// barrier (29 % of the warp samples of k_spmv_jds on the 3e6-DoF mesh).  A block = R slots covering the rows
+// [rowbeg[b], rowbeg[b + 1]).  perm bit 15 marks a continuation segment: it leaves its sum in shared memory, and the head
+// of the chain adds the segment sums in chain order after the barrier that ends the block (deterministic).  Two sets of
+// sum / link buffers alternate between consecutive blocks of a CTA, so a head may still walk its chain while faster threads
+// stage the next block.
+template <bool INIT, int R>
+__global__ void __launch_bounds__(R / 2) k_spmv_jdss(int n_blocks, const int* __restrict__ rowbeg, const int* __restrict__ jbase,
+                                                     const unsigned short* __restrict__ perm, const unsigned short* __restrict__ rlen,
+                                                     const unsigned short* __restrict__ link,
+                                                     const int* __restrict__ jdp, const int* __restrict__ jd,
+                                                     const unsigned short* __restrict__ col16, const double* __restrict__ val,
+                                                     const int* __restrict__ win_off, const int* __restrict__ win_list,
+                                                     const double* __restrict__ xin, const double* __restrict__ rhs,
+                                                     const double* __restrict__ dinv, double* __restrict__ out,
+                                                     double* __restrict__ partial, unsigned* counter, CgScalars* __restrict__ cgs,
+                                                     double* __restrict__ alpha_out, int wcap, int jcap) {
+    if (!INIT && cgs->done) return;
+    constexpr int T = R / 2;
+    extern __shared__ double s_dyn[];
+    double* s_x = s_dyn;                                          // wcap window entries
+    double* s_sum = s_dyn + wcap;                                 // 2 x R segment sums
+    int* s_jd = (int*) (s_sum + 2 * R);                           // jcap + 1 diagonal offsets (in 2-entry units), padded to even
+    unsigned short* s_link = (unsigned short*) (s_jd + ((jcap + 2) & ~1));      // 2 x R chain links
+    const int tid = threadIdx.x;
+    double acc[2] = {0, 0};
+    int par = 0;
+    for (int b = blockIdx.x; b < n_blocks; b += gridDim.x, par ^= 1) {
+        const int r0 = __ldg(&rowbeg[b]);
+        const int w0 = __ldg(&win_off[b]), nw = __ldg(&win_off[b + 1]) - w0;
+        const int j0 = __ldg(&jdp[b]), nj = __ldg(&jdp[b + 1]) - j0;
+        const long base = __ldg(&jbase[b]);
+        const size_t sl = (size_t) b * R + 2 * tid;
+        const ushort2 ln = __ldg(reinterpret_cast<const ushort2*>(rlen + sl));
+        const ushort2 pm = __ldg(reinterpret_cast<const ushort2*>(perm + sl));
+        const int len0 = ln.x, len1 = ln.y;
+        reinterpret_cast<ushort2*>(s_link + par * R)[tid] = __ldg(reinterpret_cast<const ushort2*>(link + sl));
+        for (int i = tid; i < nw; i += T) s_x[i] = __ldg(&xin[__ldg(&win_list[w0 + i])]);
+        for (int i = tid; i < nj; i += T) s_jd[i] = __ldg(&jd[j0 + i]) >> 1;
+        __syncthreads();
+        const double2* __restrict__ vb = reinterpret_cast<const double2*>(val + base) + tid;
+        const ushort2* __restrict__ cb = reinterpret_cast<const ushort2*>(col16 + base) + tid;
+        double sum0 = 0, sum1 = 0;
+        double2 va[4], vb2[4];
+        ushort2 ca[4], cb2[4];
+#define FB_ISSUE(JJ, V, C)                                                                     \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u)                                          \
+            if ((JJ) + u < len0) { const int o = s_jd[(JJ) + u]; V[u] = __ldcs(&vb[o]); C[u] = __ldcs(&cb[o]); }
+#define FB_CONSUME(JJ, V, C)                                                                   \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                        \
+            if ((JJ) + u < len0) sum0 += V[u].x * s_x[C[u].x];                                 \
+            if ((JJ) + u < len1) sum1 += V[u].y * s_x[C[u].y];                                 \
+        }
+        FB_ISSUE(0, va, ca)
+        for (int j = 0; j < len0; j += 8) {
+            FB_ISSUE(j + 4, vb2, cb2)
+            FB_CONSUME(j, va, ca)
+            FB_ISSUE(j + 8, va, ca)
+            FB_CONSUME(j + 4, vb2, cb2)
+        }
+#undef FB_ISSUE
+#undef FB_CONSUME
+        double* ss = s_sum + par * R;
+        const unsigned short* lk = s_link + par * R;
+        if (pm.x & 0x8000) ss[2 * tid] = sum0;                    // (a dead slot, perm 0xFFFF, parks a zero nobody reads)
+        if (pm.y & 0x8000) ss[2 * tid + 1] = sum1;
+        __syncthreads();                                          // ends the block: window and offsets may be overwritten
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned short p = h ? pm.y : pm.x;
+            if (p & 0x8000) continue;
+            double sum = h ? sum1 : sum0;
+            for (unsigned s = lk[2 * tid + h]; s != 0xFFFFu; s = lk[s]) sum += ss[s];
+            const int row = r0 + p;
+            if (INIT) {
+                const double di = dinv[row]; const double g = di != 0.0 ? sum - rhs[row] : 0.0;
+                out[row] = g; acc[0] += g * g * di; acc[1] += g * g;
+            } else {
+                out[row] = sum; acc[0] += __ldg(&xin[row]) * sum;
+            }
+        }
+    }
+    double tot[2];
+    if (reduce_publish<2>(acc, partial, counter, tot)) {
+        cg_finish_spmv<INIT>(cgs, tot, alpha_out);
+    }
+}
+
+// values of the CSR matrix into the segmented layout: entry o of a row with k segments of length sl sits in segment o / sl
+__global__ void k_csr_to_jds_split(int n, int R, int n_blocks, int cap, const int* __restrict__ rowbeg, const int* __restrict__ rowptr,
+                                   const unsigned short* __restrict__ slot, const unsigned short* __restrict__ link,
+                                   const int* __restrict__ jbase, const int* __restrict__ jdp, const int* __restrict__ jd,
+                                   const double* __restrict__ val, double* __restrict__ val_jds) {
+    const int lane = threadIdx.x & 7;
+    for (long r = ((long) blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < n; r += ((long) gridDim.x * blockDim.x) >> 3) {
+        int lo_b = 0, hi_b = n_blocks;                            // last block whose first row is <= r
+        while (hi_b - lo_b > 1) { const int mid = (lo_b + hi_b) >> 1; if (rowbeg[mid] <= r) lo_b = mid; else hi_b = mid; }
+        const int b = lo_b;
+        const int base = jbase[b], lo = rowptr[r], len = rowptr[r + 1] - lo;
+        const int k = len > cap ? (len + cap - 1) / cap : 1, sl = (len + k - 1) / k;
+        const int* __restrict__ jdb = jd + jdp[b];
+        const unsigned short* __restrict__ lk = link + (size_t) b * R;
+        for (int o = lane; o < len; o += 8) {
+            const int q = o / sl, j = o - q * sl;
+            int t = slot[r];
+            for (int i = 0; i < q; ++i) t = lk[t];
+            val_jds[(long) base + jdb[j] + t] = val[lo + o];
+        }
+    }
+}
+
 // Block-JDS SpMV with the NEXT block's window prefetched (option "spmv_kernel" 303).  Same tables and arithmetic as
 // k_spmv_jds<., 512>; the difference is the prologue: the window of the input vector and the diagonal offsets of the
 // block a CTA will process next are gathered with cp.async (8-byte / 4-byte, straight into the second shared-memory
@@ -1561,7 +1675,7 @@ void stream_block_shape(int kernel, int& chunk, int& maxrows) {
 int choose_lanes(const fb_ctx* c) {
     // 0 selects the row-block streaming kernel (option "spmv_kernel": -1 auto, 0 stream, else lanes per row)
     if (c->spmv_kernel >= 0) return (c->world > 1 && c->spmv_kernel >= 310) ? 304 : c->spmv_kernel;
-    if (c->nnz >= 4000000) return 304;        // block-JDS, 512 rows per block, evict-first matrix stream
+    if (c->nnz >= 4000000) return 306;        // segmented block-JDS (long rows split), 512 slots per block, evict-first matrix stream
     const double avg = c->n_dofs ? (double) c->nnz / c->n_dofs : 1.0;
     if (avg > 48) return 32;
     if (avg > 20) return 8;
@@ -1644,6 +1758,12 @@ void launch_materialize_eliminated(fb_ctx* c, double* d_val_out, double* d_rhs_o
 
 void launch_csr_to_jds(fb_ctx* c) {
     const int g = grid_for(c, (long) c->n_dofs * 8, 256);
+    if (c->jds_split > 0) {
+        k_csr_to_jds_split<<<g, 256, 0, c->stream>>>(c->n_dofs, c->jds_R, c->jds_nb, c->jds_split, c->d_jds_rowbeg.p, c->d_rowptr.p, c->d_jds_slot.p,
+                                                     c->d_jds_link.p, c->d_jds_base.p, c->d_jds_jdp.p, c->d_jds_jd.p, c->d_val_save.p, c->d_val_jds.p);
+        c->launches++;
+        return;
+    }
     k_csr_to_jds<<<g, 256, 0, c->stream>>>(c->n_dofs, c->jds_R, c->d_rowptr.p, c->d_jds_slot.p, c->d_jds_base.p, c->d_jds_jdp.p, c->d_jds_jd.p,
                                            c->d_val_save.p, c->d_val_jds.p, c->jds_sym ? c->d_diagpos.p : nullptr, c->d_diag.p);
     c->launches++;
@@ -1686,10 +1806,20 @@ static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, 
         kern<<<g, (RR) / 2, smem, c->stream>>>(c->n_dofs, nb, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_jdp.p, c->d_jds_jd.p, \
                                          c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin, c->d_rhs.p, c->d_dinv.p, \
                                          out, part, counter, c->d_cg.p, alpha, c->win_cap, c->jds_maxlen); } while (0)
+        if (lanes == 306) {            // segmented layout (long rows split), evict-first matrix stream
+            const size_t smem6 = sizeof(double) * ((size_t) c->win_cap + 2 * 512) + sizeof(int) * (((size_t) c->jds_maxlen + 2 + 1) & ~(size_t) 1) + 2 * 512 * sizeof(unsigned short);
+            auto kern = k_spmv_jdss<INIT, 512>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem6);
+            const int occ = std::max(1, std::min(c->spmv_occ, (int) (200 * 1024 / (smem6 + 1024))));
+            const int g = std::min(nb, c->n_sm * occ);
+            kern<<<g, 256, smem6, c->stream>>>(nb, c->d_jds_rowbeg.p, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_link.p, c->d_jds_jdp.p,
+                                               c->d_jds_jd.p, c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin, c->d_rhs.p, c->d_dinv.p,
+                                               out, part, counter, c->d_cg.p, alpha, c->win_cap, c->jds_maxlen);
+        } else
         if (lanes == 305) {            // evict-first matrix stream, loads pinned in program order (volatile asm)
             auto kern = k_spmv_jds<INIT, 512, 2>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-            const int occ = std::max(1, std::min(6, (int) (200 * 1024 / (smem + 1024))));
+            const int occ = std::max(1, std::min(c->spmv_occ, (int) (200 * 1024 / (smem + 1024))));
             const int g = std::min(nb, c->n_sm * occ);
             kern<<<g, 256, smem, c->stream>>>(c->n_dofs, nb, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_jdp.p, c->d_jds_jd.p,
                                               c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin, c->d_rhs.p, c->d_dinv.p,
@@ -1698,7 +1828,7 @@ static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, 
         if (lanes == 304) {            // evict-first matrix stream
             auto kern = k_spmv_jds<INIT, 512, 1>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-            const int occ = std::max(1, std::min(6, (int) (200 * 1024 / (smem + 1024))));
+            const int occ = std::max(1, std::min(c->spmv_occ, (int) (200 * 1024 / (smem + 1024))));
             const int g = std::min(nb, c->n_sm * occ);
             kern<<<g, 256, smem, c->stream>>>(c->n_dofs, nb, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_jdp.p, c->d_jds_jd.p,
                                               c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin, c->d_rhs.p, c->d_dinv.p,
@@ -1709,7 +1839,7 @@ static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, 
             const size_t smem2 = 2 * sizeof(double) * (size_t) c->win_cap + 2 * sizeof(int) * jstride;
             auto kern = k_spmv_jdsp<INIT, 512>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2);
-            const int occ = std::max(1, std::min(6, (int) (200 * 1024 / (smem2 + 1024))));
+            const int occ = std::max(1, std::min(c->spmv_occ, (int) (200 * 1024 / (smem2 + 1024))));
             const int g = std::min(nb, c->n_sm * occ);
             kern<<<g, 256, smem2, c->stream>>>(c->n_dofs, nb, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_jdp.p, c->d_jds_jd.p,
                                               c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin, c->d_rhs.p, c->d_dinv.p,

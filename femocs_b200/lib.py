@@ -70,6 +70,8 @@ SIGNATURES = {
     "fb_plan_interp_tables": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_int,
                                         vp, vp, vp, vp, vp, vp, vp, vp]),
     "fb_plan_jds": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
+    "fb_plan_jds_split": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
+    "fb_plan_jds_get_split": (C.c_int, [vp, vp, vp]),
     "fb_plan_jds_get": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "fb_get_stream": (vp, [vp]),
     "fb_comm_mode": (C.c_int, [vp]),

@@ -565,10 +565,14 @@ class PartitionPlan:
         self._check(self.L.fb_export_surface_centroids(self.h, _p(out), C.byref(n)))
         return out
 
-    def jds(self, R=512, max_window=8192, sym=False):
-        """block-JDS tables of the HBM SpMV for this plan's sparsity (fb_host_jds_build), as numpy arrays"""
+    def jds(self, R=512, max_window=8192, sym=False, split=0):
+        """block-JDS tables of the HBM SpMV for this plan's sparsity (fb_host_jds_build), as numpy arrays;
+        split > 0: rows longer than that stored as chained segments (spmv_kernel 306): adds rowbeg / link"""
         sz = np.zeros(6, np.int64)
-        self._check(self.L.fb_plan_jds(self.h, int(R), int(max_window), int(sym), _p(sz)))
+        if split:
+            self._check(self.L.fb_plan_jds_split(self.h, int(R), int(max_window), int(split), _p(sz)))
+        else:
+            self._check(self.L.fb_plan_jds(self.h, int(R), int(max_window), int(sym), _p(sz)))
         nb, size, nwin, maxlen, wmax, njd = [int(v) for v in sz]
         t = dict(R=R, nb=nb, size=size, maxlen=maxlen, win_max=wmax,
                  perm=np.zeros(nb * R, np.uint16), len=np.zeros(nb * R, np.uint16), slot=np.zeros(self.n_rows, np.uint16),
@@ -577,6 +581,9 @@ class PartitionPlan:
         self._check(self.L.fb_plan_jds_get(self.h, _p(t["perm"]), _p(t["len"]), _p(t["slot"]), _p(t["jdp"]), _p(t["jd"]), _p(t["base"]),
                                            _p(t["col16"]), _p(t["win_off"]), _p(t["win_list"])))
         t["win_list"] = t["win_list"][:nwin]
+        if split:
+            t["rowbeg"] = np.zeros(nb + 1, np.int32); t["link"] = np.zeros(nb * R, np.uint16)
+            self._check(self.L.fb_plan_jds_get_split(self.h, _p(t["rowbeg"]), _p(t["link"])))
         return t
 
 

@@ -113,6 +113,10 @@ int fb_plan_interp_tables(fb_ctx* plan, const double* xyz, int n_nodes, const in
 /* host-only: block-JDS tables (R rows per block; sym != 0: lower triangle only) of the plan's sparsity.
  * sizes6 = {blocks, stored slots incl. padding, window entries, longest row, largest window, diagonal offsets} */
 int fb_plan_jds(fb_ctx* plan, int R, int max_window, int sym, long* sizes6);
+/* the layout of spmv_kernel 306: rows longer than `split` entries stored as chained segments; rowbeg[nb + 1] = first row of
+ * every block, link[nb * R] = slot of the next segment of the same row (0xFFFF: none); perm gains bit 15 = "not the head" */
+int fb_plan_jds_split(fb_ctx* plan, int R, int max_window, int split, long* sizes6);
+int fb_plan_jds_get_split(const fb_ctx* plan, int* rowbeg, unsigned short* link);
 /* host-only: mesh kind of the next fb_plan_import: 0 = vacuum hexahedra (fb_import_mesh), 1 = bulk (fb_import_bulk_mesh);
  * fb_export_surface_centroids works on plan contexts too */
 int fb_plan_set_kind(fb_ctx* plan, int kind);

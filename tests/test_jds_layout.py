@@ -71,3 +71,56 @@ def test_block_jds_tables_encode_the_csr_pattern(name, refine, R, sym, golden):
     a = np.lexsort((cols, rows)); b = np.lexsort((csr_cols, csr_rows))
     assert np.array_equal(rows[a], csr_rows[b]) and np.array_equal(cols[a], csr_cols[b])
     assert t["maxlen"] == np.max(np.bincount(csr_rows, minlength=p.n_rows))
+
+
+@pytest.mark.parametrize("name,refine", [("mdsmall", 1), ("hemicone", 1)])
+@pytest.mark.parametrize("cap", [32, 12])
+def test_split_row_layout_multiplies_like_csr(name, refine, cap, golden):
+    """spmv_kernel 306: rows longer than `cap` entries are stored as chained segments (jds_link) and a block holds 512 slots
+    instead of 512 rows (jds_rowbeg).  Walking the tables the way k_spmv_jds<., SPLIT> does -- slot sums, then the heads add
+    their chain in order -- reproduces the CSR product; every row is the head of exactly one chain; no segment exceeds cap."""
+    p = _plan(golden, name, refine)
+    t = p.jds(R=512, max_window=8192, split=cap)
+    R = 512; n = p.n_rows
+    rng = np.random.default_rng(5)
+    val = rng.standard_normal(p.nnz); x = rng.standard_normal(p.n_cols)
+    rp, col = p.rowptr, p.col
+    ref = np.add.reduceat(val * x[col], rp[:-1])
+    assert t["maxlen"] <= cap and t["rowbeg"][0] == 0 and t["rowbeg"][-1] == n and np.all(np.diff(t["rowbeg"]) > 0)
+    out = np.full(n, np.nan); stored = 0
+    rowlen = np.diff(rp)
+    for b in range(t["nb"]):
+        r0 = t["rowbeg"][b]; nr = t["rowbeg"][b + 1] - r0
+        perm = t["perm"][b * R:(b + 1) * R].astype(np.int64); lens = t["len"][b * R:(b + 1) * R].astype(np.int64)
+        link = t["link"][b * R:(b + 1) * R].astype(np.int64)
+        live = perm != 0xFFFF
+        nv = int(live.sum())
+        assert np.all(live[:nv]) and np.all(np.diff(lens[:nv]) <= 0) and np.all(lens[nv:] == 0)
+        jd = t["jd"][t["jdp"][b]:t["jdp"][b + 1]]
+        win = t["win_list"][t["win_off"][b]:t["win_off"][b + 1]]
+        # the value array the device kernel k_csr_to_jds_split would produce: entry o of row r -> segment o // seglen
+        sums = np.zeros(R)
+        head = live & ((perm & 0x8000) == 0)
+        assert np.array_equal(np.sort(perm[head]), np.arange(nr))
+        assert np.array_equal(t["slot"][r0 + perm[head]], np.flatnonzero(head))
+        for tt in np.flatnonzero(head):
+            r = r0 + perm[tt]; L = rowlen[r]
+            k = -(-L // cap) if L > cap else 1
+            sl = -(-L // k) if L else 0
+            s = tt; q = 0; total = 0.0; first = True
+            while s != 0xFFFF:
+                assert (perm[s] & 0x7FFF) == perm[tt] and (first or perm[s] & 0x8000)
+                seg = lens[s]
+                assert seg == max(0, min(sl, L - q * sl))
+                pos = t["base"][b] + jd[:seg] + s
+                cols = win[t["col16"][pos].astype(np.int64)]
+                ks = rp[r] + q * sl + np.arange(seg)
+                assert np.array_equal(cols, col[ks])
+                sums[s] = float(np.dot(val[ks], x[cols]))
+                stored += seg
+                total = sums[s] if first else total + sums[s]
+                first = False; q += 1; s = link[s]
+            assert q == k
+            out[r] = total
+    assert stored == p.nnz
+    assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
