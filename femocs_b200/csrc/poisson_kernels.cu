@@ -126,27 +126,37 @@ __device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
 }
 constexpr long long P2P_SPIN_LIMIT = 8000000000LL;      // ~4 s of SM clocks: a peer that died must not hang the GPU
 
+// One WARP per rank: lane p talks to rank p.  It stores this rank's two sums into p's record, publishes the sequence number
+// (st.release.sys orders it behind the sums) and polls its own record for p's contribution; the lanes then add the
+// contributions in rank order through shuffles, so every rank obtains the same bits.  (The first version did all of this
+// in ONE thread: 8 release stores over NVLink and 8 polls back to back, ~20 us per all-reduce at 8 GPUs.)
 __device__ __noinline__ bool p2p_allreduce2(P2pDesc* D, int kind, double* tot) {
+    const int lane = threadIdx.x & 31;
     const long long seq = D->red_count[kind] + 1;
-    D->red_count[kind] = seq;
+    const double t0v = tot[0], t1v = tot[1];
+    __syncwarp();
+    if (lane == 0) D->red_count[kind] = seq;
     const int me = D->rank, W = D->world;
-    for (int p = 0; p < W; ++p) {
-        volatile double* dst = D->slots[p]->red[kind][me];
-        dst[0] = tot[0]; dst[1] = tot[1];
-    }
-    __threadfence_system();
-    for (int p = 0; p < W; ++p) st_release_sys(&D->slots[p]->red_seq[kind][me], seq);
-    P2pSlots* mine = D->slots[me];
     double a = 0, b = 0;
-    const long long t0 = clock64();
-    for (int p = 0; p < W; ++p) {
-        while (ld_acquire_sys(&mine->red_seq[kind][p]) < seq)
-            if (clock64() - t0 > P2P_SPIN_LIMIT) return false;
-        const volatile double* src = mine->red[kind][p];
-        a += src[0]; b += src[1];
+    bool ok = true;
+    if (lane < W) {
+        volatile double* dst = D->slots[lane]->red[kind][me];
+        dst[0] = t0v; dst[1] = t1v;
+        st_release_sys(&D->slots[lane]->red_seq[kind][me], seq);
+        P2pSlots* mine = D->slots[me];
+        const long long c0 = clock64();
+        while (ld_acquire_sys(&mine->red_seq[kind][lane]) < seq)
+            if (clock64() - c0 > P2P_SPIN_LIMIT) { ok = false; break; }
+        const volatile double* src = mine->red[kind][lane];
+        a = src[0]; b = src[1];
     }
-    tot[0] = a; tot[1] = b;
-    return true;
+    ok = __all_sync(0xffffffffu, ok);
+    double sa = 0, sb = 0;
+    for (int p = 0; p < W; ++p) { sa += __shfl_sync(0xffffffffu, a, p); sb += __shfl_sync(0xffffffffu, b, p); }
+    __syncwarp();
+    if (lane == 0) { tot[0] = sa; tot[1] = sb; }
+    __syncwarp();
+    return ok;
 }
 
 template <bool INIT>
@@ -162,15 +172,15 @@ __device__ __forceinline__ void cg_finish_update(CgScalars* cgs, const double* t
 // and not in the epilogue of the reduction kernels on purpose: a call in k_spmv_jds costs that kernel its register
 // schedule (78 registers + stack instead of 80 and none, SpMV 0.74 -> 0.85 ms on half of X).
 template <bool INIT>
-__global__ void k_cg_scalars_spmv(CgScalars* cgs, double* alpha_out) {
+__global__ void __launch_bounds__(32) k_cg_scalars_spmv(CgScalars* cgs, double* alpha_out) {      // one warp
     if (!INIT && cgs->done) return;
-    if (cgs->p2p && !p2p_allreduce2(cgs->p2p, 0, cgs->red)) { cgs->done = 3; return; }
-    cg_scalars_spmv<INIT>(cgs, cgs->red, alpha_out);
+    if (cgs->p2p && !p2p_allreduce2(cgs->p2p, 0, cgs->red)) { if (threadIdx.x == 0) cgs->done = 3; return; }
+    if (threadIdx.x == 0) cg_scalars_spmv<INIT>(cgs, cgs->red, alpha_out);
 }
-__global__ void k_cg_scalars_update(CgScalars* cgs, double* beta_out) {
+__global__ void __launch_bounds__(32) k_cg_scalars_update(CgScalars* cgs, double* beta_out) {
     if (cgs->done) return;
-    if (cgs->p2p && !p2p_allreduce2(cgs->p2p, 1, cgs->red)) { cgs->done = 3; return; }
-    cg_scalars_update(cgs, cgs->red, beta_out);
+    if (cgs->p2p && !p2p_allreduce2(cgs->p2p, 1, cgs->red)) { if (threadIdx.x == 0) cgs->done = 3; return; }
+    if (threadIdx.x == 0) cg_scalars_update(cgs, cgs->red, beta_out);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -2124,19 +2134,20 @@ __global__ void __launch_bounds__(256) k_pack_p2p(int n, const int* __restrict__
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (!is_last || threadIdx.x != 0) return;
-    *counter = 0;
-    __threadfence_system();
+    if (!is_last || threadIdx.x >= 32) return;
+    // the first warp of the last block: lane p announces to / waits for rank p (all peers at once, not one after the other)
+    const int lane = threadIdx.x, me = D->rank;
     const long long seq = D->halo_count + 1;
-    D->halo_count = seq;
-    const int me = D->rank;
-    for (int p = 0; p < W; ++p)
-        if (p != me && D->send_off[p + 1] > D->send_off[p]) st_release_sys(&D->slots[p]->halo_flag[me], seq);
-    const long long t0 = clock64();
-    for (int p = 0; p < W; ++p) {
-        if (p == me || D->n_recv[p] == 0) continue;
-        while (ld_acquire_sys(&D->slots[me]->halo_flag[p]) < seq)
-            if (clock64() - t0 > P2P_SPIN_LIMIT) { cgs->done = 3; return; }
+    __syncwarp();
+    if (lane == 0) { *counter = 0; D->halo_count = seq; }
+    __threadfence_system();
+    if (lane < W && lane != me) {
+        if (D->send_off[lane + 1] > D->send_off[lane]) st_release_sys(&D->slots[lane]->halo_flag[me], seq);
+        if (D->n_recv[lane] > 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_sys(&D->slots[me]->halo_flag[lane]) < seq)
+                if (clock64() - t0 > P2P_SPIN_LIMIT) { cgs->done = 3; break; }
+        }
     }
 }
 
@@ -2169,9 +2180,9 @@ void launch_double_to_ghost_flags(fb_ctx* c, const double* in) {
     c->launches++;
 }
 void launch_cg_scalars(fb_ctx* c, int which) {      // 0: after the initial residual, 1: after SpMV, 2: after the update
-    if (which == 0) k_cg_scalars_spmv<true><<<1, 1, 0, c->stream>>>(c->d_cg.p, nullptr);
-    else if (which == 1) k_cg_scalars_spmv<false><<<1, 1, 0, c->stream>>>(c->d_cg.p, alpha_ptr(c));
-    else k_cg_scalars_update<<<1, 1, 0, c->stream>>>(c->d_cg.p, beta_ptr(c));
+    if (which == 0) k_cg_scalars_spmv<true><<<1, 32, 0, c->stream>>>(c->d_cg.p, nullptr);
+    else if (which == 1) k_cg_scalars_spmv<false><<<1, 32, 0, c->stream>>>(c->d_cg.p, alpha_ptr(c));
+    else k_cg_scalars_update<<<1, 32, 0, c->stream>>>(c->d_cg.p, beta_ptr(c));
     c->launches++;
 }
 void launch_cg_init_spmv(fb_ctx* c, int lanes) { spmv_dispatch<true>(c, lanes, c->d_x.p, c->d_g.p, nullptr); }

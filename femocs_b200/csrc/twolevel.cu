@@ -277,16 +277,18 @@ __global__ void __launch_bounds__(256) k_tl_allreduce_p2p(P2pDesc* D, int nc, co
     if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!is_last) return;
-    if (threadIdx.x == 0) {
-        *counter = 0;
-        __threadfence_system();
+    if (threadIdx.x < 32) {                 // lane p announces to / waits for rank p, all peers at once
+        const int lane = threadIdx.x;
         const long long seq = D->tl_count + 1;
-        D->tl_count = seq;
-        for (int p = 0; p < W; ++p) tl_st_release_sys(&D->slots[p]->tl_seq[me], seq);
-        const long long t0 = clock64();
-        for (int p = 0; p < W && cgs->done != 3; ++p)
-            while (tl_ld_acquire_sys(&D->slots[me]->tl_seq[p]) < seq)
+        __syncwarp();
+        if (lane == 0) { *counter = 0; D->tl_count = seq; }
+        __threadfence_system();
+        if (lane < W) {
+            tl_st_release_sys(&D->slots[lane]->tl_seq[me], seq);
+            const long long t0 = clock64();
+            while (tl_ld_acquire_sys(&D->slots[me]->tl_seq[lane]) < seq)
                 if (clock64() - t0 > 8000000000LL) { cgs->done = 3; break; }
+        }
     }
     __syncthreads();
     if (cgs->done == 3) return;

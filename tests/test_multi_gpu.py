@@ -49,6 +49,11 @@ def _worker(rank, world, port, q, p2p):
         s.assemble(False)                                   # PIC step: warm start from the converged potential
         out["it_warm"] = s.solve(cg_tolerance=1e-7)
         out["launches"] = ctx.kernel_launches
+        # the HBM kernel of the benchmark (segmented block-JDS, chosen automatically only for >= 4e6 non-zeros) on the partition
+        ctx.set_option("spmv_kernel", 306)
+        s.setup(0.5, 0.0); s.assemble(True)
+        out["it_jds"] = s.solve(); out["phi_jds"] = s.export_solution(); out["kernel_jds"] = s.solve_kernel()
+        ctx.set_option("spmv_kernel", -1)
         if p2p:     # the two-level preconditioner on the partitioned mesh (global Morton aggregates, restriction summed over the peer mappings)
             s.conf.precond = fb.PRECOND_TWOLEVEL
             ctx.set_option("tl_agg", 64)
@@ -120,6 +125,7 @@ def test_partitioned_solve_matches_oracle(world, p2p, golden):
         assert rel(x["phi_poisson"], ref_p) < 1e-8
         assert not x["limits"][0] and x["limits"][1] == 0.0 and abs(x["limits"][2] - ref_l.max()) < 1e-8 * ref_l.max()
         assert x["part"]["n_send"] > 0 and x["launches"] > 0
+        assert x["kernel_jds"] == 306 and x["it_jds"] > 0 and rel(x["phi_jds"], ref_p) < 1e-8
         if p2p:
             assert 0 < x["it_tl"] < 0.8 * x["it_poisson"] and x["it_tl"] == outs[0]["it_tl"], (x["it_tl"], x["it_poisson"])
             assert rel(x["phi_tl"], ref_p) < 1e-8
