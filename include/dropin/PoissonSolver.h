@@ -73,6 +73,8 @@ public:
             const char* dev = getenv("FEMOCS_B200_DEVICE");
             ctx = fb_create(dev ? atoi(dev) : 0);
             if (!ctx) { write_silent_msg(string("libfemocs_b200: ") + fb_create_error()); return false; }
+            // the element is a compile-time constant of the reference (include/DealSolver.h:130); here: shape_degree below
+            if (shape_degree != 1 && fb_set_option(ctx, "fe_degree", (double) shape_degree)) { complain("fe_degree"); return false; }
         }
         const size_t nv = vertices.size(), nc = cells.size();
         vector<double> xyz(3 * nv);
@@ -243,6 +245,10 @@ protected:
     }
 
 private:
+    /// degree of the shape functions, as include/DealSolver.h:130 of the reference; 2 selects the library's FE_Q(2) path
+    /// (QGauss(3), Laplace only: PoissonSolver.cpp:267-296 for shape_degree != 1 is refused with an error)
+    static constexpr unsigned int shape_degree = 1;
+
     const ParticleSpecies* particles;
     const Config::Field* conf;
     const LinearHexahedra* interpolator;      ///< kept for signature compatibility; the space-charge weights are computed on the device
