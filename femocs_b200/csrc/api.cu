@@ -511,7 +511,6 @@ int fb_poisson_setup(fb_ctx* c, double field, double potential, int anode_is_dir
 
 static int assemble_impl(fb_ctx* c, int first_time, const double* d_pxyz, const int* d_pcell, long n_parts, double charge_factor) {
     cudaStream_t s = c->stream;
-    FB_REQUIRE(c, c->imported_degree == 1 || n_parts == 0, "fb_poisson_assemble: the space-charge right-hand side is provided for fe_degree 1 only (FE_Q(2): Laplace)");
     const int n = c->n_dofs;
     if (first_time || !c->matrix_ok) {
         // stiffness matrix -> val_save (the reference's system_matrix_save).  It is never modified afterwards: the

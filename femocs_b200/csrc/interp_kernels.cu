@@ -984,7 +984,8 @@ __global__ void __launch_bounds__(128) k_space_charge(const HexRec* __restrict__
                                                       const int* __restrict__ pcell, int n_cells, const int* __restrict__ cell2hex,
                                                       const int* __restrict__ cells_dof, const double* __restrict__ vxyz,
                                                       double charge_factor, double* __restrict__ rhs,
-                                                      const int* __restrict__ gcell2local, int n_cells_global, int n_rows) {
+                                                      const int* __restrict__ gcell2local, int n_cells_global, int n_rows,
+                                                      const int* __restrict__ cells27) {
     const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int cell = pcell[i];
@@ -1016,6 +1017,28 @@ __global__ void __launch_bounds__(128) k_space_charge(const HexRec* __restrict__
         hex_sf(hexrec[cell2hex[cell]], ldp(pts, i), sf);
     }
     const int perm[8] = {0, 1, 4, 5, 3, 2, 7, 6};       // shape_funs_dealii (:1355-1358)
+    if (cells27) {
+        // FE_Q(2) (PoissonSolver.cpp:276-296 -> DealSolver::shape_funs, DealSolver.cpp:75-110): the 27 shape values at the
+        // particle's unit-cell point, clamped to the cell (project_to_unit_cell); the point follows from the trilinear
+        // weights: xi_d = sum of the weights of the vertices with bit d set
+        double xi[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double w = sf[perm[k]];
+            if (k & 1) xi[0] += w;
+            if (k & 2) xi[1] += w;
+            if (k & 4) xi[2] += w;
+        }
+        double L[3][3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const double x = fmin(1.0, fmax(0.0, xi[d]));
+            L[d][0] = 2.0 * (x - 0.5) * (x - 1.0); L[d][1] = 4.0 * x * (1.0 - x); L[d][2] = 2.0 * x * (x - 0.5);
+        }
+        for (int a = 0; a < 27; ++a)
+            atomicAdd(&rhs[cells27[27 * (long) cell + a]], L[0][a % 3] * L[1][(a / 3) % 3] * L[2][a / 9] * charge_factor);
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int dof = cells_dof[8 * (long) cell + k];
@@ -1204,13 +1227,14 @@ void launch_pic_compact(fb_ctx* c, long n, const double* d_pos, const double* d_
 void launch_space_charge(fb_ctx* c, long n, const double* d_pts, const int* d_pcell, double charge_factor) {
     if (n <= 0) return;
     const unsigned g = (unsigned) ((n + 127) / 128);
+    const int* q27 = c->imported_degree == 2 ? c->d_cells27.p : nullptr;
     if (c->interp_ok)
         k_space_charge<false><<<g, 128, 0, c->stream>>>(c->d_hex.p, n, d_pts, d_pcell, c->n_cells, c->d_cell2hex.p, c->d_cells.p,
-                                                         c->d_vxyz.p, charge_factor, c->d_rhs.p, nullptr, 0, c->n_dofs);
+                                                         c->d_vxyz.p, charge_factor, c->d_rhs.p, nullptr, 0, c->n_dofs, q27);
     else
         k_space_charge<true><<<g, 128, 0, c->stream>>>(nullptr, n, d_pts, d_pcell, c->n_cells, c->d_cell2hex.p, c->d_cells.p,
                                                         c->d_vxyz.p, charge_factor, c->d_rhs.p,
-                                                        c->world > 1 ? c->d_gcell2local.p : nullptr, c->n_cells_global, c->n_dofs);
+                                                        c->world > 1 ? c->d_gcell2local.p : nullptr, c->n_cells_global, c->n_dofs, q27);
     c->launches++;
 }
 

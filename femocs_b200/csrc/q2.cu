@@ -11,7 +11,8 @@
 //   src/DealSolver.cpp:317-341   calc_vertex2dof   -> export_solution returns the VERTEX dofs, so the interpolator half
 //                                                    of the path is untouched
 // Everything behind the CSR pattern (Dirichlet mask, block-JDS SpMV, CG, preconditioners, check_limits) is the Q1 code.
-// Laplace only: the space-charge scatter of PoissonSolver.cpp:267-296 for shape_degree != 1 is not provided (loud error).
+// The space-charge scatter of PoissonSolver.cpp:276-296 (shape_degree != 1) is the FE_Q(2) branch of k_space_charge
+// (interp_kernels.cu).  Not provided for FE_Q(2): partitioned meshes, the bulk (current / heat) solvers, export_solution_grad.
 #include <omp.h>
 
 #include <algorithm>

@@ -246,7 +246,7 @@ protected:
 
 private:
     /// degree of the shape functions, as include/DealSolver.h:130 of the reference; 2 selects the library's FE_Q(2) path
-    /// (QGauss(3), Laplace only: PoissonSolver.cpp:267-296 for shape_degree != 1 is refused with an error)
+    /// (QGauss(3); space charge through the general path of PoissonSolver.cpp:276-296)
     static constexpr unsigned int shape_degree = 1;
 
     const ParticleSpecies* particles;

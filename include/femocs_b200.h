@@ -65,7 +65,7 @@ long        fb_kernel_launches(const fb_ctx* ctx);
  * "dof_order" (0 = deal.II first-touch numbering, 1 = Morton order of vertex coordinates),
  * "cg_profile" (see fb_last_solve_profile),
  * "fe_degree" (element of the NEXT fb_import_mesh: 1 = FE_Q(1), the reference as shipped -- include/DealSolver.h:130
- * shape_degree = 1; 2 = FE_Q(2) with QGauss(3), what the same call sites do when that constant reads 2: Laplace only,
+ * shape_degree = 1; 2 = FE_Q(2) with QGauss(3), what the same call sites do when that constant reads 2;
  * un-partitioned field solver only; fb_export_solution still returns the vertex values, src/DealSolver.cpp:317-341) */
 int         fb_set_option(fb_ctx* ctx, const char* key, double value);
 

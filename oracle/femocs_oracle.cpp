@@ -673,6 +673,26 @@ void assemble_space_charge(Oracle& o, const double* pxyz, const int* pcell, long
     }
 }
 
+// PoissonSolver.cpp:276-296, the general path taken when shape_degree != 1: DealSolver::shape_funs (DealSolver.cpp:75-110)
+// = the 27 FE_Q(2) shape values at the particle's unit-cell coordinates (MappingQ1 inverse, clamped to the unit cell by
+// GeometryInfo::project_to_unit_cell).  The unit-cell point is recovered from the trilinear weights of the pinned
+// shape_funs_dealii restatement: xi_d = sum of the weights of the vertices with bit d set.
+void precompute_hexs(Oracle& o);
+void q2_assemble_space_charge(Oracle& o, const double* pxyz, const int* pcell, long n, double charge_factor) {
+    if ((int) o.h_f[0].size() != o.n_hex) precompute_hexs(o);
+    for (long p = 0; p < n; ++p) {
+        const int cell = pcell[p];
+        if (cell < 0 || cell >= (int) o.cells.size()) continue;
+        double sf[8];
+        hex_shape_functions_dealii(o, {pxyz[3 * p], pxyz[3 * p + 1], pxyz[3 * p + 2]}, o.cell2hex[cell], sf);
+        double xi[3] = {0, 0, 0};
+        for (int v = 0; v < 8; ++v) for (int d = 0; d < 3; ++d) if ((v >> d) & 1) xi[d] += sf[v];
+        double L[3][3], dL[3];
+        for (int d = 0; d < 3; ++d) { xi[d] = std::min(1.0, std::max(0.0, xi[d])); lagrange2(xi[d], L[d], dL); }
+        for (int a = 0; a < 27; ++a) o.rhs[o.cdofs[cell][a]] += L[0][a % 3] * L[1][(a / 3) % 3] * L[2][a / 9] * charge_factor;
+    }
+}
+
 // PoissonSolver.cpp:170-210 assemble(first_time)
 void assemble(Oracle& o, int first_time, const double* pxyz, const int* pcell, long n_parts, double charge_factor) {
     if (first_time) std::fill(o.val.begin(), o.val.end(), 0.0);
@@ -681,7 +701,10 @@ void assemble(Oracle& o, int first_time, const double* pxyz, const int* pcell, l
     append_dirichlet(o, BID_COPPER, 0.0);
     if (!o.anode_dirichlet) assemble_rhs_faces(o, BID_TOP);
     else append_dirichlet(o, BID_TOP, o.applied_potential);
-    if (pxyz && n_parts > 0 && o.fe_degree == 1) assemble_space_charge(o, pxyz, pcell, n_parts, charge_factor);   // FE_Q(2): Laplace only
+    if (pxyz && n_parts > 0) {
+        if (o.fe_degree == 2) q2_assemble_space_charge(o, pxyz, pcell, n_parts, charge_factor);
+        else assemble_space_charge(o, pxyz, pcell, n_parts, charge_factor);
+    }
     // PoissonSolver.cpp:196-207: charge density for the files, before the Dirichlet conditions; DealSolver.cpp:344-366 calc_dof_volumes
     o.charge_density.assign(o.n_dofs, 0.0);
     if (o.write_time && o.fe_degree == 1) {

@@ -170,7 +170,7 @@ def test_chebyshev_on_hbm_sized_system(fb, golden):
     c.set_option("cheb_degree", 3)
     s.setup(0.5, 0.0); s.assemble(True)
     itc = s.solve()
-    assert 0 < itc < itj and s.solve_kernel() == 304
+    assert 0 < itc < itj and s.solve_kernel() == 306
     assert _rel(s.export_solution(), phi) < 1e-7
     c.close()
 
@@ -459,7 +459,7 @@ def test_large_refined_mesh_properties(fb, golden):
     assert s.n_cells == 64 * int((m["hex_markers"] > 0).sum())
     s.setup(0.5, 0.0); s.assemble(True)
     assert s.solve() > 0
-    assert s.solve_kernel() == 304          # HBM-sized systems take the block-JDS SpMV (evict-first matrix stream)
+    assert s.solve_kernel() == 306          # HBM-sized systems take the segmented block-JDS SpMV (evict-first matrix stream)
     phi1 = s.export_solution()
     c.set_option("spmv_kernel", 310)         # the symmetric (lower-triangle) layout gives the same solution
     s.setup(0.5, 0.0); s.assemble(True)
@@ -467,7 +467,7 @@ def test_large_refined_mesh_properties(fb, golden):
     assert _rel(s.export_solution(), phi1) < 1e-7        # both stop at |r| <= 1e-9; phi ~ 1e2
     c.set_option("spmv_kernel", -1)
     s.setup(0.5, 0.0); s.assemble(True)
-    assert s.solve() > 0 and s.solve_kernel() == 304
+    assert s.solve() > 0 and s.solve_kernel() == 306
     g = s.get_system()
     K = sp.csr_matrix((g["val_save"], g["col"], g["rowptr"]))
     assert abs(K - K.T).max() <= 1e-12 * np.abs(g["val_save"]).max()                     # symmetry

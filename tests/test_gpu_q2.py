@@ -100,11 +100,7 @@ def test_q2_field_step_matches_oracle(fb, golden):
     o1 = Oracle(); o1.import_mesh(m["nodes"], m["hexs"], m["hex_markers"])
     o1.setup(0.5, 0.0, False); o1.assemble(True); o1.solve(20000, 1e-11, 1.2, 0)
     assert 1e-4 < _rel(s.export_solution(), o1.export_solution()) < 0.2
-    # ... and a PIC step on it is refused loudly, as is the Gauss-point gradient export
-    s.conf.mode = "transient"; s.set_particles(m["surf_atoms"][:4], np.zeros(4, np.int32), 1.0)
-    with pytest.raises(fb.FemocsB200Error):
-        s.assemble(True)
-    s.conf.mode = "laplace"; s.set_particles(None, None, 0.0)
+    # ... and the Gauss-point gradient export (a Q1 formula in the reference) is refused loudly
     with pytest.raises(fb.FemocsB200Error):
         s.export_solution_grad()
     # back to FE_Q(1) on the same context
@@ -112,4 +108,33 @@ def test_q2_field_step_matches_oracle(fb, golden):
     s.import_mesh(m["nodes"], m["hexs"], m["hex_markers"])
     s.setup(0.5, 0.0); s.assemble(True); assert s.solve() > 0
     assert _rel(s.export_solution(), o1.export_solution()) < REL
+    c.close()
+
+
+@pytest.mark.parametrize("with_tables", [True, False])
+def test_q2_space_charge_matches_oracle(with_tables, fb, golden):
+    """Poisson with the quadratic element: PoissonSolver.cpp:276-296 (the path taken when shape_degree != 1) = scatter of the
+    27 shape values at each particle's unit-cell point; right-hand side 1e-11, potential 1e-8; with the interpolator's
+    hexahedron table and with the coefficients rebuilt from the cell vertices"""
+    m = golden("mesh", "mdsmall"); g = golden("interp", "mdsmall")
+    ok = g["pic_ok"]
+    pts = g["points"][ok]; cells = g["pic_cells"][ok]
+    cf = -180.9512268 * 0.01
+    o = _oracle(m); o.interp_initialize(m)
+    c = fb.Context(0)
+    c.set_option("fe_degree", 2)
+    s = fb.PoissonSolver(c, fb.FieldConfig(mode="transient", cg_tolerance=1e-11))
+    s.import_mesh(m["nodes"], m["hexs"], m["hex_markers"])
+    if with_tables:
+        it = fb.Interpolator(c); it.initialize(m)
+    s.set_particles(pts, cells, cf)
+    s.setup(0.5, 0.0); s.assemble(True)
+    o.setup(0.5, 0.0, False); o.assemble(True, pts, cells, cf)
+    rhs = o.vectors()[0]
+    assert np.abs(s.get_system()["rhs"] - rhs).max() <= 1e-11 * np.abs(rhs).max()
+    assert s.solve() > 0 and o.solve(20000, 1e-11, 1.2, 0) > 0
+    assert _rel(s.export_solution(), o.export_solution()) < REL
+    # the charge changes the potential (the particles were not lost on the way)
+    o.setup(0.5, 0.0, False); o.assemble(True); o.solve(20000, 1e-11, 1.2, 0)
+    assert _rel(s.export_solution(), o.export_solution()) > 1e-6
     c.close()

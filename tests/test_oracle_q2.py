@@ -188,3 +188,36 @@ def test_q2_is_closer_to_the_refined_answer_than_q1():
     fine = sols[2][:len(nodes0)][used]                         # refinement keeps the coarse nodes first
     e1 = np.abs(sols[0][used] - fine).max(); e2 = np.abs(sols[1][used] - fine).max()
     assert e2 < e1
+
+
+def test_q2_space_charge_weights_by_construction():
+    """PoissonSolver.cpp:276-296 with FE_Q(2): particles are PLACED at known unit-cell coordinates of known cells (trilinear
+    image), so the right-hand side they must add is the scatter of the 27 tensor Lagrange values at those coordinates --
+    no inverse map involved on this side.  Checks the oracle's inverse map, its axis conventions and the lattice order."""
+    m = _bump_mesh(jitter=0.2)
+    o = _oracle_q2(m)
+    rng = np.random.default_rng(9)
+    n = 400
+    cells = rng.integers(0, o.n_cells, n).astype(np.int32)
+    xi = rng.uniform(0.02, 0.98, (n, 3))
+    v2n = o.vectors()[3]
+    X = m["nodes"][v2n[o.cells()[cells]]]                                   # (n, 8, 3) lexicographic vertices
+    w8 = np.stack([np.where((v >> 0) & 1, xi[:, 0], 1 - xi[:, 0]) * np.where((v >> 1) & 1, xi[:, 1], 1 - xi[:, 1])
+                   * np.where((v >> 2) & 1, xi[:, 2], 1 - xi[:, 2]) for v in range(8)], 1)
+    pts = np.einsum("nv,nvd->nd", w8, X)
+    cf = -1.7
+    o.setup(0.4, 0.0, False); o.assemble(True)
+    rhs0 = o.vectors()[0].copy()
+    o.setup(0.4, 0.0, False); o.assemble(True, pts, cells, cf)
+    rhs1 = o.vectors()[0]
+    lag = lambda x: np.stack([2 * (x - 0.5) * (x - 1), 4 * x * (1 - x), 2 * x * (x - 0.5)], 1)      # (n, 3)
+    Lx, Ly, Lz = lag(xi[:, 0]), lag(xi[:, 1]), lag(xi[:, 2])
+    w27 = np.einsum("ni,nj,nk->nkji", Lx, Ly, Lz).reshape(n, 27)             # index i + 3 j + 9 k
+    assert np.abs(w27.sum(1) - 1).max() < 1e-13
+    expect = np.zeros(o.n_dofs)
+    np.add.at(expect, o.cell_dofs27()[cells].reshape(-1), (cf * w27).reshape(-1))
+    rp, col, val, _ = o.csr()
+    constrained = np.array([np.count_nonzero(val[rp[r]:rp[r + 1]]) == 1 for r in range(o.n_dofs)])
+    free = ~constrained
+    assert np.abs((rhs1 - rhs0)[free] - expect[free]).max() <= 1e-10 * np.abs(expect).max()
+    assert np.array_equal(rhs1[constrained], rhs0[constrained])
