@@ -623,8 +623,8 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
         if ((cheb || tl) && lanes >= 310) lanes = 304;      // the Chebyshev steps multiply by the FULL matrix: the symmetric (lower-triangle) layout cannot serve them
         while (lanes >= 300) {                     // block-JDS SpMV: tables once per mesh, values once per assemble
             const bool sym = lanes >= 310;         // 310/311: symmetric layout (lower triangle only)
-            const int R = sym ? (lanes == 311 ? 256 : 512) : ((lanes == 301) ? 128 : ((lanes >= 302 && lanes <= 306) ? 512 : 256));
-            const int split = lanes == 306 ? c->spmv_split : 0;
+            const int R = sym ? (lanes == 311 ? 256 : 512) : ((lanes == 301) ? 128 : ((lanes >= 302 && lanes <= 307) ? 512 : 256));
+            const int split = (lanes == 306 || lanes == 307) ? c->spmv_split : 0;
             if (!c->jds_ready || c->jds_R != R || c->jds_sym != sym || c->jds_split != split) {
                 drop_graph(c);
                 // window capacity: shared memory holds the input window (and, symmetric layout, its accumulators)

@@ -1285,6 +1285,110 @@ __global__ void __launch_bounds__(R / 2) k_spmv_jdsp(int n, int n_blocks, const 
     }
 }
 
+// k_spmv_jdss with the NEXT block's window INDEX LIST prefetched (option "spmv_kernel" 307; same tables as 306).  ncu of
+// k_spmv_jdss on X: 28 % of the warp samples sit in the block prologue (+ 7.5 % at its barrier), on a chain of three
+// dependent global loads -- win_off -> win_list -> vector entries -- that moves 5 % of the bytes.  Here the window
+// offsets of the next block are loaded at the top of the current one and its index list is copied into the second of two
+// shared-memory buffers with cp.async (4-byte, coalesced, no registers held) behind the first matrix loads of the main
+// loop; the next prologue then gathers through indices that already sit in shared memory: one dependent level instead of
+// three.  (The vector entries themselves cannot be prefetched: they change between launches but not within one -- they
+// could, but the 8-byte scattered cp.async gathers of variant 303 were slower than LDG + STS.)
+template <int R>
+__global__ void __launch_bounds__(R / 2) k_spmv_jdsq(int n_blocks, const int* __restrict__ rowbeg, const int* __restrict__ jbase,
+                                                     const unsigned short* __restrict__ perm, const unsigned short* __restrict__ rlen,
+                                                     const unsigned short* __restrict__ link,
+                                                     const int* __restrict__ jdp, const int* __restrict__ jd,
+                                                     const unsigned short* __restrict__ col16, const double* __restrict__ val,
+                                                     const int* __restrict__ win_off, const int* __restrict__ win_list,
+                                                     const double* __restrict__ xin, double* __restrict__ out,
+                                                     double* __restrict__ partial, unsigned* counter, CgScalars* __restrict__ cgs,
+                                                     double* __restrict__ alpha_out, int wcap, int jcap) {
+    if (cgs->done) return;
+    constexpr int T = R / 2;
+    extern __shared__ double s_dyn[];
+    double* s_x = s_dyn;                                          // wcap window entries
+    double* s_sum = s_dyn + wcap;                                 // 2 x R segment sums
+    int* s_jd = (int*) (s_sum + 2 * R);                           // jcap + 1 diagonal offsets (in 2-entry units), padded to even
+    int* s_idx = s_jd + ((jcap + 2) & ~1);                        // 2 x wcap window indices (this block / next block)
+    unsigned short* s_link = (unsigned short*) (s_idx + 2 * wcap);      // 2 x R chain links
+    const int tid = threadIdx.x;
+    double acc[2] = {0, 0};
+    int par = 0;
+    int nw = 0;
+    if ((int) blockIdx.x < n_blocks) {                            // index list of the first block
+        const int w0 = __ldg(&win_off[blockIdx.x]);
+        nw = __ldg(&win_off[blockIdx.x + 1]) - w0;
+        for (int i = tid; i < nw; i += T) cp_async4(&s_idx[i], &win_list[w0 + i]);
+        cp_async_commit();
+        cp_async_wait_all();
+    }
+    __syncthreads();
+    for (int b = blockIdx.x; b < n_blocks; b += gridDim.x, par ^= 1) {
+        const int bn = b + gridDim.x;
+        int w0n = 0, nwn = 0;
+        if (bn < n_blocks) { w0n = __ldg(&win_off[bn]); nwn = __ldg(&win_off[bn + 1]) - w0n; }
+        const int r0 = __ldg(&rowbeg[b]);
+        const int j0 = __ldg(&jdp[b]), nj = __ldg(&jdp[b + 1]) - j0;
+        const long base = __ldg(&jbase[b]);
+        const size_t sl = (size_t) b * R + 2 * tid;
+        const ushort2 ln = __ldg(reinterpret_cast<const ushort2*>(rlen + sl));
+        const ushort2 pm = __ldg(reinterpret_cast<const ushort2*>(perm + sl));
+        const int len0 = ln.x, len1 = ln.y;
+        reinterpret_cast<ushort2*>(s_link + par * R)[tid] = __ldg(reinterpret_cast<const ushort2*>(link + sl));
+        const int* __restrict__ idx = s_idx + par * wcap;
+        for (int i = tid; i < nw; i += T) s_x[i] = __ldg(&xin[idx[i]]);
+        for (int i = tid; i < nj; i += T) s_jd[i] = __ldg(&jd[j0 + i]) >> 1;
+        __syncthreads();
+        const double2* __restrict__ vb = reinterpret_cast<const double2*>(val + base) + tid;
+        const ushort2* __restrict__ cb = reinterpret_cast<const ushort2*>(col16 + base) + tid;
+        double sum0 = 0, sum1 = 0;
+        double2 va[4], vb2[4];
+        ushort2 ca[4], cb2[4];
+#define FB_ISSUE(JJ, V, C)                                                                     \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u)                                          \
+            if ((JJ) + u < len0) { const int o = s_jd[(JJ) + u]; V[u] = __ldcs(&vb[o]); C[u] = __ldcs(&cb[o]); }
+#define FB_CONSUME(JJ, V, C)                                                                   \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                        \
+            if ((JJ) + u < len0) sum0 += V[u].x * s_x[C[u].x];                                 \
+            if ((JJ) + u < len1) sum1 += V[u].y * s_x[C[u].y];                                 \
+        }
+        FB_ISSUE(0, va, ca)
+        {   // index list of the next block into the other buffer (nobody reads that one before the barrier that ends this block)
+            int* dst = s_idx + (par ^ 1) * wcap;
+            for (int i = tid; i < nwn; i += T) cp_async4(&dst[i], &win_list[w0n + i]);
+            cp_async_commit();
+        }
+        nw = nwn;
+        for (int j = 0; j < len0; j += 8) {
+            FB_ISSUE(j + 4, vb2, cb2)
+            FB_CONSUME(j, va, ca)
+            FB_ISSUE(j + 8, va, ca)
+            FB_CONSUME(j + 4, vb2, cb2)
+        }
+#undef FB_ISSUE
+#undef FB_CONSUME
+        double* ss = s_sum + par * R;
+        const unsigned short* lk = s_link + par * R;
+        if (pm.x & 0x8000) ss[2 * tid] = sum0;
+        if (pm.y & 0x8000) ss[2 * tid + 1] = sum1;
+        cp_async_wait_all();
+        __syncthreads();                                          // ends the block: window, offsets free; next index list complete
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned short p = h ? pm.y : pm.x;
+            if (p & 0x8000) continue;
+            double sum = h ? sum1 : sum0;
+            for (unsigned s = lk[2 * tid + h]; s != 0xFFFFu; s = lk[s]) sum += ss[s];
+            const int row = r0 + p;
+            out[row] = sum; acc[0] += __ldg(&xin[row]) * sum;
+        }
+    }
+    double tot[2];
+    if (reduce_publish<2>(acc, partial, counter, tot)) {
+        cg_finish_spmv<false>(cgs, tot, alpha_out);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Symmetric block-JDS SpMV: the matrix after the symmetric Dirichlet elimination (apply_boundary_values with
 // eliminate_columns, DealSolver.cpp:439) is symmetric, so only its strictly lower triangle is stored and
@@ -1816,7 +1920,18 @@ static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, 
         kern<<<g, (RR) / 2, smem, c->stream>>>(c->n_dofs, nb, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_jdp.p, c->d_jds_jd.p, \
                                          c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin, c->d_rhs.p, c->d_dinv.p, \
                                          out, part, counter, c->d_cg.p, alpha, c->win_cap, c->jds_maxlen); } while (0)
-        if (lanes == 306) {            // segmented layout (long rows split), evict-first matrix stream
+        if (lanes == 307 && !INIT) {   // segmented layout + index list of the next block prefetched
+            const size_t smem7 = sizeof(double) * ((size_t) c->win_cap + 2 * 512) + sizeof(int) * ((((size_t) c->jds_maxlen + 2 + 1) & ~(size_t) 1) + 2 * (size_t) c->win_cap)
+                                 + 2 * 512 * sizeof(unsigned short);
+            auto kern = k_spmv_jdsq<512>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem7);
+            const int occ = std::max(1, std::min(c->spmv_occ, (int) (200 * 1024 / (smem7 + 1024))));
+            const int g = std::min(nb, c->n_sm * occ);
+            kern<<<g, 256, smem7, c->stream>>>(nb, c->d_jds_rowbeg.p, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_link.p, c->d_jds_jdp.p,
+                                               c->d_jds_jd.p, c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin,
+                                               out, part, counter, c->d_cg.p, alpha, c->win_cap, c->jds_maxlen);
+        } else
+        if (lanes == 306 || lanes == 307) {            // segmented layout (long rows split), evict-first matrix stream
             const size_t smem6 = sizeof(double) * ((size_t) c->win_cap + 2 * 512) + sizeof(int) * (((size_t) c->jds_maxlen + 2 + 1) & ~(size_t) 1) + 2 * 512 * sizeof(unsigned short);
             auto kern = k_spmv_jdss<INIT, 512>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem6);
