@@ -623,12 +623,13 @@ int fb_poisson_solve(fb_ctx* c, int max_iter, double abs_tol, int precond, int* 
         if ((cheb || tl) && lanes >= 310) lanes = 304;      // the Chebyshev steps multiply by the FULL matrix: the symmetric (lower-triangle) layout cannot serve them
         while (lanes >= 300) {                     // block-JDS SpMV: tables once per mesh, values once per assemble
             const bool sym = lanes >= 310;         // 310/311: symmetric layout (lower triangle only)
-            const int R = sym ? (lanes == 311 ? 256 : 512) : ((lanes == 301) ? 128 : ((lanes >= 302 && lanes <= 307) ? 512 : 256));
-            const int split = (lanes == 306 || lanes == 307) ? c->spmv_split : 0;
-            if (!c->jds_ready || c->jds_R != R || c->jds_sym != sym || c->jds_split != split) {
+            const int R = sym ? (lanes == 311 ? 256 : 512) : ((lanes == 301) ? 128 : ((lanes >= 302 && lanes <= 308) ? 512 : 256));
+            const int split = (lanes >= 306 && lanes <= 308) ? c->spmv_split : 0;
+            const int pad = lanes == 308 ? 8 : 2;
+            if (!c->jds_ready || c->jds_R != R || c->jds_sym != sym || c->jds_split != split || c->jds_pad != pad) {
                 drop_graph(c);
                 // window capacity: shared memory holds the input window (and, symmetric layout, its accumulators)
-                if (fb_host_jds_build(c, R, sym ? 6144 : 8192, sym, split)) {
+                if (fb_host_jds_build(c, R, sym ? 6144 : 8192, sym, split, pad)) {
                     c->win_cap = (c->win_max + 15) & ~15;
                     if (sym) FB_CUDA(c, c->d_diag.alloc(c->n_dofs));
                     FB_CUDA(c, c->d_col16.upload(c->col16, s));

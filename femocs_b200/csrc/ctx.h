@@ -160,7 +160,7 @@ struct fb_ctx {
     int jds_R = 0, jds_nb = 0, jds_maxlen = 0; bool jds_ready = false, jds_val_dirty = true, jds_sym = false, h_needs_zero = false;
     std::vector<unsigned short> jds_perm, jds_len, jds_slot; std::vector<int> jds_jdp, jds_jd, jds_base; int jds_size = 0;
     // rows split into segments (spmv_kernel 306): first row of every block, next segment of a slot's row (0xFFFF: none), cap in use
-    std::vector<int> jds_rowbeg; std::vector<unsigned short> jds_link; int jds_split = 0;
+    std::vector<int> jds_rowbeg; std::vector<unsigned short> jds_link; int jds_split = 0, jds_pad = 2;
     struct BFace { int cell, face, id; };
     std::vector<BFace> bfaces;
     std::vector<int> copper_dofs, top_dofs;  // Dirichlet candidates
@@ -260,7 +260,7 @@ long fb_host_count_edges(const fb_ctx* c);
 void fb_host_vertex_lastcell(const fb_ctx* c, std::vector<int>& out);
 bool fb_host_row_blocks(fb_ctx* c, int chunk, int maxrows);
 bool fb_host_col_windows(fb_ctx* c, int max_window);
-bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym, int split = 0);
+bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym, int split = 0, int pad = 2);
 int fb_host_import_mesh(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);
 bool fb_host_try_reuse(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex, int mesh_kind);
 int fb_host_import_phase1(fb_ctx* c, const double* xyz, int n_nodes, const int* hex8, const int* hex_marker, int n_hex);

@@ -535,7 +535,7 @@ bool fb_host_col_windows(fb_ctx* c, int max_window) {
 // diagonals: diagonal j holds the j-th entry of every row longer than j, so that thread t of the
 // CTA walks "its" row with perfectly coalesced loads and NO padding.  Columns are replaced by 16-bit
 // positions inside the block's window (the sorted distinct columns the block touches).
-bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym, int split) {
+bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym, int split, int pad) {
     // sym: only the strictly lower triangle (columns < row: a prefix of every sorted CSR row) is stored; the window
     // list then holds the distinct columns BELOW the block (sorted), and the block's own rows follow implicitly:
     // window position of column j is  rank(j) for j < r0,  n_ext + (j - r0) for r0 <= j < row.
@@ -545,6 +545,8 @@ bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym, int split) {
     // longest rows of a block walks 2-4x more diagonals than the other seven, which wait for it at the block's barrier.
     const int n = c->n_dofs;
     if (sym) split = 0;
+    if (split == 0 || pad != 8) pad = 2;       // entries every diagonal is padded to (8: 16-byte aligned slices of the column stream, spmv_kernel 308)
+    c->jds_pad = pad;
     auto rowlen = [&](int r) {
         const int* lo = c->col.data() + c->rowptr[r]; const int* hi = c->col.data() + c->rowptr[r + 1];
         return sym ? (int) (std::lower_bound(lo, hi, r) - lo) : (int) (hi - lo);
@@ -620,11 +622,12 @@ bool fb_host_jds_build(fb_ctx* c, int R, int max_window, bool sym, int split) {
         jd[0] = 0;
         for (int j = 0; j < maxlen[b]; ++j) {
             while (t_active > 0 && (int) c->jds_len[(size_t) b * R + t_active - 1] <= j) --t_active;
-            jd[j + 1] = jd[j] + ((t_active + 1) & ~1);
+            // (segmented layout: multiples of 8, so that any run of diagonals is a 16-byte aligned slice of the 2-byte column stream)
+            jd[j + 1] = jd[j] + ((t_active + pad - 1) & ~(pad - 1));
         }
     }
     for (int b = 0; b < nb; ++b) {
-        const long next = (long) c->jds_base[b] + c->jds_jd[c->jds_jdp[b + 1] - 1];
+        long next = (long) c->jds_base[b] + c->jds_jd[c->jds_jdp[b + 1] - 1];
         if (next > 2147483000L) return false;
         c->jds_base[b + 1] = (int) next;
     }

@@ -1390,6 +1390,158 @@ __global__ void __launch_bounds__(R / 2) k_spmv_jdsq(int n_blocks, const int* __
 }
 
 // ---------------------------------------------------------------------------------------
+// Segmented block-JDS SpMV with the MATRIX STREAM fed by TMA bulk copies (option "spmv_kernel" 308; tables of 306).
+// In k_spmv_jdss the loads in flight live in the registers of the warps that will consume them, so a CTA that is staging
+// the window of its next block (28 % of the warp samples) streams nothing.  Here a producer warp walks the CTA's blocks
+// ahead of the consumers and copies the value / column streams -- contiguous per block -- group by group (4 diagonals) into
+// a ring of shared-memory stages with cp.async.bulk (1-D TMA, completion on an mbarrier, L2 evict-first policy); the 8
+// consumer warps wait for a stage, read their entries from shared memory and hand the stage back (one arrival per warp).  The stream keeps
+// flowing across block boundaries and through the prologues.  Consumers synchronise among themselves with a named
+// barrier (bar.sync 1, 256); the producer warp joins only the final reduction.
+// ---------------------------------------------------------------------------------------
+namespace tma {
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) { while (!mbar_try_wait(bar, parity)) { } }
+__device__ __forceinline__ unsigned long long evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+}  // namespace tma
+
+template <int NS, int GD>
+__global__ void __launch_bounds__(288) k_spmv_jdst(int n_blocks, const int* __restrict__ rowbeg, const int* __restrict__ jbase,
+                                                   const unsigned short* __restrict__ perm, const unsigned short* __restrict__ rlen,
+                                                   const unsigned short* __restrict__ link,
+                                                   const int* __restrict__ jdp, const int* __restrict__ jd,
+                                                   const unsigned short* __restrict__ col16, const double* __restrict__ val,
+                                                   const int* __restrict__ win_off, const int* __restrict__ win_list,
+                                                   const double* __restrict__ xin, double* __restrict__ out,
+                                                   double* __restrict__ partial, unsigned* counter, CgScalars* __restrict__ cgs,
+                                                   double* __restrict__ alpha_out, int wcap, int jcap) {
+    // A stage holds a GROUP of GD consecutive diagonals of one block (at most GD x 512 entries: values + window positions).
+    if (cgs->done) return;
+    constexpr int R = 512, T = 256, SC = GD * R;
+    __shared__ __align__(8) unsigned long long s_full[NS], s_empty[NS];
+    extern __shared__ __align__(16) unsigned char s_tma[];                  // (a named array of its own: the alignment, and the compiler keeps the shared state space)
+    double* s_val = reinterpret_cast<double*>(s_tma);                       // NS x SC values (16-byte aligned stages)
+    unsigned short* s_col = (unsigned short*) (s_val + NS * SC);            // NS x SC window positions
+    double* s_x = (double*) (s_col + NS * SC);                              // wcap window entries
+    double* s_sum = s_x + wcap;                                             // 2 x R segment sums
+    int* s_jd = (int*) (s_sum + 2 * R);                                     // jcap + 1 diagonal offsets (entries), padded to even
+    unsigned short* s_link = (unsigned short*) (s_jd + ((jcap + 2) & ~1));  // 2 x R chain links
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { tma::mbar_init(&s_full[s], 1); tma::mbar_init(&s_empty[s], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    double acc[2] = {0, 0};
+    if (warp == 8) {
+        // ---- producer warp: lane g looks up the bounds of group g, lane 0 keeps the ring full ----
+        const unsigned long long pol = tma::evict_first_policy();
+        int stage = 0; unsigned use = 0;                              // ring position; use = times the ring has wrapped
+        for (int b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+            const int base = __ldg(&jbase[b]);
+            const int j0 = __ldg(&jdp[b]), maxlen = __ldg(&jdp[b + 1]) - j0 - 1;
+            const int ng = (maxlen + GD - 1) / GD;                    // <= 32 groups: one lane each
+            int lo = 0, hi = 0;
+            if (lane < ng) { lo = __ldg(&jd[j0 + lane * GD]); hi = __ldg(&jd[j0 + min(maxlen, (lane + 1) * GD)]); }
+            for (int g = 0; g < ng; ++g) {
+                const int glo = __shfl_sync(0xffffffffu, lo, g), ghi = __shfl_sync(0xffffffffu, hi, g);
+                if (lane == 0) {
+                    if (use > 0) tma::mbar_wait(&s_empty[stage], (use - 1) & 1);      // the consumers have left the previous tenant
+                    const unsigned cnt = (unsigned) (ghi - glo);
+                    tma::mbar_expect_tx(&s_full[stage], cnt * 10u);
+                    if (cnt) {
+                        tma::bulk_g2s(s_val + (size_t) stage * SC, val + (size_t) base + glo, cnt * 8u, &s_full[stage], pol);
+                        tma::bulk_g2s(s_col + (size_t) stage * SC, col16 + (size_t) base + glo, cnt * 2u, &s_full[stage], pol);
+                    }
+                }
+                if (++stage == NS) { stage = 0; ++use; }
+            }
+        }
+    } else {
+        // ---- consumers: 8 warps, thread t owns the slots 2t and 2t + 1 of every block ----
+        int stage = 0; unsigned phase = 0;
+        int par = 0;
+        for (int b = blockIdx.x; b < n_blocks; b += gridDim.x, par ^= 1) {
+            const int r0 = __ldg(&rowbeg[b]);
+            const int w0 = __ldg(&win_off[b]), nw = __ldg(&win_off[b + 1]) - w0;
+            const int j0 = __ldg(&jdp[b]), nj = __ldg(&jdp[b + 1]) - j0;
+            const size_t sl = (size_t) b * R + 2 * tid;
+            const ushort2 ln = __ldg(reinterpret_cast<const ushort2*>(rlen + sl));
+            const ushort2 pm = __ldg(reinterpret_cast<const ushort2*>(perm + sl));
+            const int len0 = ln.x, len1 = ln.y;
+            reinterpret_cast<ushort2*>(s_link + par * R)[tid] = __ldg(reinterpret_cast<const ushort2*>(link + sl));
+            for (int i = tid; i < nw; i += T) s_x[i] = __ldg(&xin[__ldg(&win_list[w0 + i])]);
+            for (int i = tid; i < nj; i += T) s_jd[i] = __ldg(&jd[j0 + i]);
+            tma::consumer_bar();
+            const int ng = (nj - 1 + GD - 1) / GD;
+            double sum0 = 0, sum1 = 0;
+            for (int g = 0; g < ng; ++g) {
+                tma::mbar_wait(&s_full[stage], phase);
+                const int gbase = s_jd[g * GD];
+                const double* sv = s_val + (size_t) stage * SC + 2 * tid - gbase;
+                const unsigned short* sc = s_col + (size_t) stage * SC + 2 * tid - gbase;
+#pragma unroll
+                for (int u = 0; u < GD; ++u) {
+                    const int jj = g * GD + u;
+                    if (jj < len0) {
+                        const int o = s_jd[jj];
+                        const double2 v = *reinterpret_cast<const double2*>(sv + o);
+                        const ushort2 cc = *reinterpret_cast<const ushort2*>(sc + o);
+                        sum0 += v.x * s_x[cc.x];
+                        if (jj < len1) sum1 += v.y * s_x[cc.y];
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) tma::mbar_arrive(&s_empty[stage]);
+                if (++stage == NS) { stage = 0; phase ^= 1; }
+            }
+            double* ss = s_sum + par * R;
+            const unsigned short* lk = s_link + par * R;
+            if (pm.x & 0x8000) ss[2 * tid] = sum0;
+            if (pm.y & 0x8000) ss[2 * tid + 1] = sum1;
+            tma::consumer_bar();                                      // ends the block: window and offsets may be overwritten
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const unsigned short p = h ? pm.y : pm.x;
+                if (p & 0x8000) continue;
+                double sum = h ? sum1 : sum0;
+                for (unsigned s = lk[2 * tid + h]; s != 0xFFFFu; s = lk[s]) sum += ss[s];
+                const int row = r0 + p;
+                out[row] = sum; acc[0] += __ldg(&xin[row]) * sum;
+            }
+        }
+    }
+    double tot[2];
+    if (reduce_publish<2>(acc, partial, counter, tot)) {
+        cg_finish_spmv<false>(cgs, tot, alpha_out);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Symmetric block-JDS SpMV: the matrix after the symmetric Dirichlet elimination (apply_boundary_values with
 // eliminate_columns, DealSolver.cpp:439) is symmetric, so only its strictly lower triangle is stored and
 // streamed -- half the bytes of k_spmv_jds.  Thread t owns two rows i of the block; for every stored entry
@@ -1920,6 +2072,18 @@ static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, 
         kern<<<g, (RR) / 2, smem, c->stream>>>(c->n_dofs, nb, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_jdp.p, c->d_jds_jd.p, \
                                          c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin, c->d_rhs.p, c->d_dinv.p, \
                                          out, part, counter, c->d_cg.p, alpha, c->win_cap, c->jds_maxlen); } while (0)
+        if (lanes == 308 && !INIT && c->jds_pad == 8 && c->jds_maxlen <= 128) {   // segmented layout, matrix stream through a TMA-fed shared-memory ring
+            constexpr int NS = 3, GD = 4;
+            const size_t smem8 = 16 + (size_t) NS * GD * 512 * 10 + sizeof(double) * ((size_t) c->win_cap + 2 * 512)
+                                 + sizeof(int) * (((size_t) c->jds_maxlen + 2 + 1) & ~(size_t) 1) + 2 * 512 * sizeof(unsigned short);
+            auto kern = k_spmv_jdst<NS, GD>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem8);
+            const int occ = std::max(1, std::min(c->spmv_occ, (int) (224 * 1024 / (smem8 + 2048))));
+            const int g = std::min(nb, c->n_sm * occ);
+            kern<<<g, 288, smem8, c->stream>>>(nb, c->d_jds_rowbeg.p, c->d_jds_base.p, c->d_jds_perm.p, c->d_jds_len.p, c->d_jds_link.p, c->d_jds_jdp.p,
+                                               c->d_jds_jd.p, c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin,
+                                               out, part, counter, c->d_cg.p, alpha, c->win_cap, c->jds_maxlen);
+        } else
         if (lanes == 307 && !INIT) {   // segmented layout + index list of the next block prefetched
             const size_t smem7 = sizeof(double) * ((size_t) c->win_cap + 2 * 512) + sizeof(int) * ((((size_t) c->jds_maxlen + 2 + 1) & ~(size_t) 1) + 2 * (size_t) c->win_cap)
                                  + 2 * 512 * sizeof(unsigned short);
@@ -1931,7 +2095,7 @@ static void spmv_dispatch(fb_ctx* c, int lanes, const double* xin, double* out, 
                                                c->d_jds_jd.p, c->d_col16.p, c->d_val_jds.p, c->d_win_off.p, c->d_win_list.p, xin,
                                                out, part, counter, c->d_cg.p, alpha, c->win_cap, c->jds_maxlen);
         } else
-        if (lanes == 306 || lanes == 307) {            // segmented layout (long rows split), evict-first matrix stream
+        if (lanes >= 306 && lanes <= 308) {            // segmented layout (long rows split), evict-first matrix stream
             const size_t smem6 = sizeof(double) * ((size_t) c->win_cap + 2 * 512) + sizeof(int) * (((size_t) c->jds_maxlen + 2 + 1) & ~(size_t) 1) + 2 * 512 * sizeof(unsigned short);
             auto kern = k_spmv_jdss<INIT, 512>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem6);

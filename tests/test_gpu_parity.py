@@ -107,7 +107,7 @@ def test_solution_matches_oracle(name, fb, ctx, golden, oracles):
     assert s.solve(n_cg=5) == -5
 
 
-@pytest.mark.parametrize("kernel", [0, 100, 101, 102, 103, 200, 201, 202, 203, 204, 300, 301, 302, 303, 304, 305, 306, 307, 310, 311, 2, 8, 32])
+@pytest.mark.parametrize("kernel", [0, 100, 101, 102, 103, 200, 201, 202, 203, 204, 300, 301, 302, 303, 304, 305, 306, 307, 308, 310, 311, 2, 8, 32])
 def test_spmv_kernel_variants_agree(kernel, fb, golden, oracles):
     """every SpMV kernel of the multi-kernel CG (windowed / plain row-block streaming variants, lanes-per-row
     variants) gives the oracle's solution"""
@@ -119,11 +119,11 @@ def test_spmv_kernel_variants_agree(kernel, fb, golden, oracles):
     s.import_mesh(m["nodes"], m["hexs"], m["hex_markers"])
     s.setup(0.5, 0.0); s.assemble(True)
     assert s.solve() > 0
-    if kernel >= 310 or kernel in (306, 307):
+    if kernel >= 310 or kernel in (306, 307, 308):
         assert s.solve_kernel() == kernel       # no silent fall-back to the full-matrix layout
     o.setup(0.5, 0.0, False); o.assemble(True); o.solve(10000, 1e-11, 1.2, 0)
     assert _rel(s.export_solution(), o.export_solution()) < REL
-    if kernel in (306, 307):
+    if kernel in (306, 307, 308):
         # segmented layout: other caps (chains of up to 6 segments on this mesh), and under the other preconditioners
         for cap, precond in ((12, fb.PRECOND_JACOBI), (20, fb.PRECOND_CHEBYSHEV), (32, fb.PRECOND_TWOLEVEL)):
             c.set_option("spmv_split", cap); s.conf.precond = precond
