@@ -457,7 +457,7 @@ def run_b200(args):
         "sizes": {"n_dofs": n, "nnz": int(nnz_all), "n_cells": part["n_cells_global"],
                   "parallelism": ("element-partitioned over %d GPUs (RCB), %s; rank 0: %d rows, %d ghosts, %d halo values sent"
                                   % (world, {2: "peer-mapped iteration: halo values and dot-product sums stored into the peers' memory over NVLink by the kernels, "
-                                                "4 kernels per iteration in a CUDA graph, no NCCL inside the loop",
+                                                "6 kernels per iteration (pack, SpMV, all-reduce, update, all-reduce, direction) in a CUDA graph, no NCCL inside the loop",
                                              1: "NCCL inside the iteration (grouped send/recv halo + 2 all-reduces, host-issued)"}.get(ctx.comm_mode, "?"),
                                      part["n_rows"], part["n_ghost"], part["n_send"])) if world > 1 else "1 GPU",
                   "comm_mode": ctx.comm_mode,
