@@ -353,8 +353,11 @@ int fb_last_solve_stats(const fb_ctx* ctx, double* solve_ms, int* iterations, lo
 int fb_last_solve_profile(const fb_ctx* ctx, double* spmv_ms_avg, double* vector_ms_avg, int* n_samples);
 /* which SpMV kernel the last fb_poisson_solve ran (option "spmv_kernel" codes: -2 = single cooperative launch
  * k_cg_persistent, 2..32 = CSR lanes per row, 100.. = row-block streaming, 200.. = windowed streaming, 300..305 =
- * block-JDS (304, the default for HBM-sized systems: matrix stream read evict-first; 305: same with the load order pinned), 310/311 = symmetric block-JDS
- * storing the lower triangle only) */
+ * block-JDS (304: matrix stream read evict-first; 305: same with the load order pinned), 306 = segmented block-JDS, the
+ * default for HBM-sized systems (rows longer than option "spmv_split" = 32 entries stored as chained segments), 307 = 306 with
+ * the next block's index list prefetched, 308 = 306 with the matrix stream through a TMA / mbarrier ring of shared-memory
+ * stages (both measured slower, kept as tested variants), 310/311 = symmetric block-JDS storing the lower triangle only;
+ * option "spmv_occ" = CTAs per SM the grid of the 512-slot kernels is sized for) */
 int fb_last_solve_kernel(const fb_ctx* ctx);
 /* the context's cudaStream_t (for callers that record their own events around fb_*_dev calls) */
 void* fb_get_stream(fb_ctx* ctx);
